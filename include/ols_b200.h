@@ -1,0 +1,275 @@
+/*
+ * ols_b200.h — C ABI of the B200-native Per-State Rejection Sampling (PSRS) engine.
+ *
+ * This is the drop-in boundary for ONE path of microsoft/rl-offline-simulation (package
+ * `offsim4rl`): offline learner simulation by per-state rejection sampling.  Every entry
+ * point names the reference interface it replaces (paths relative to the reference's
+ * `offsim4rl/` directory).  The reference is pure Python and has no FFI of its own; the
+ * binding a maintainer would add is a ctypes stub (shown in INTEGRATION.md, shipped in
+ * rl-offline-simulation_b200/_abi.py).
+ *
+ * Conventions
+ *   - plain C: pointers, sizes and POD structs only; no C++ or torch types.
+ *   - every pointer is a DEVICE pointer (cudaMalloc'd by the caller, e.g. a torch CUDA tensor's
+ *     data_ptr) unless its comment says HOST.  The library allocates nothing and keeps no state:
+ *     the caller owns all buffers, including scratch (sizes via the *_scratch_bytes queries).
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous and stream-ordered.
+ *   - every function returns OLS_OK or an OLS_ERR_* code and never throws; ols_last_error()
+ *     gives the thread-local message of the last failure.
+ *   - row indices, queue offsets and cursors are int32: a log holds < 2^31 transitions.
+ *   - integer/byte results (ids, offsets, order, accepted rows) are bit-exact with the reference;
+ *     the accept rule runs in IEEE float64 (or float32, see OLS_COMPUTE_F32) exactly as NumPy does.
+ */
+#ifndef OLS_B200_H
+#define OLS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OLS_ABI_VERSION 1
+
+/* ---- return codes ------------------------------------------------------------------------- */
+enum {
+  OLS_OK = 0,
+  OLS_ERR_INVALID = 1,      /* bad argument (null pointer, size out of range, misaligned buffer) */
+  OLS_ERR_CUDA = 2,         /* a CUDA runtime call or kernel launch failed                        */
+  OLS_ERR_UNSUPPORTED = 3   /* valid request outside what the kernels cover (e.g. n_actions > 16) */
+};
+
+/* ---- per-replica status (evaluators/psrs.py return conventions) -------------------------- */
+enum {
+  OLS_RUNNING = 0,        /* holds a current state, can step                                      */
+  OLS_DONE = 1,           /* a fused driver reached n_episodes (psrs.py:149)                       */
+  OLS_QUEUE_EMPTY = 2,    /* psrs.py:44-45 — step() returned (None,)*4: the state's queue ran dry  */
+  OLS_INIT_EMPTY = 3,     /* psrs.py:33-35 — reset() returned None: no initial state left          */
+  OLS_NO_QUEUE = 4,       /* psrs.py:44 raises KeyError — state never logged as a from-state       */
+  OLS_FEED_EMPTY = 5,     /* harness-fed uniform / tie stream exhausted (parity mode only)         */
+  OLS_IDLE = 6            /* fresh replica: reset() has not been called yet                        */
+};
+
+/* ---- options ------------------------------------------------------------------------------ */
+enum { OLS_REJECT_DEFAULT = 0,   /* psrs.py:53-57 `_default_reject`                                */
+       OLS_REJECT_ACCEPT_ALL = 1 /* trivial_baselines.py:8-10,22-24 `_reject -> False`             */ };
+enum { OLS_COMPUTE_F64 = 0,      /* NumPy promotion when either distribution is float64            */
+       OLS_COMPUTE_F32 = 1       /* both p_new and p_log float32: ratio, max and compare in float32 */ };
+enum { OLS_RNG_FEED = 0,         /* u = u_feed[replica*stride + draw]  (harness-fed, parity tests)  */
+       OLS_RNG_PCG64 = 1,        /* np.random.default_rng(seed).random() replayed bit for bit        */
+       OLS_RNG_PHILOX = 2        /* Philox4x32-10 keyed by (seed, replica id), counter = draw index  */ };
+enum { OLS_AGENT_FIXED_PI = 0,   /* psrs.py:241-271 evalMC_psrs                                     */
+       OLS_AGENT_EXPSARSA = 1,   /* psrs.py:187-239 expSARSA_psrs                                   */
+       OLS_AGENT_QLEARN = 2      /* psrs.py:119-185 qlearn_psrs + tabular.py:24-32 epsilon-greedy    */ };
+
+/* ---- the logged transitions, one column per field (data.py:100-118 `experience`) ---------- *
+ * Row i is the transition (s_i, a_i, r_i, s'_i, done_i, p_b(.|s_i)); z / z_next are the integer
+ * state ids that key the queues (encoder output, per_state_rejection.py:30-31), s / s_next the
+ * integer observation the tabular agent indexes Q with (psrs.py:36,49-50; == z in the configs the
+ * reference ships).                                                                            */
+typedef struct ols_log {
+  int64_t n_rows;
+  int32_t n_actions;          /* <= 16                                                           */
+  int32_t p_is_f64;           /* dtype of p_log: 0 float32, 1 float64                            */
+  const int32_t* z;           /* [n_rows] from-state id, in [-z_offset, n_buckets - z_offset)     */
+  const int32_t* z_next;      /* [n_rows]                                                        */
+  const int32_t* s;           /* [n_rows] or NULL (= z)                                          */
+  const int32_t* s_next;      /* [n_rows] or NULL (= z_next)                                     */
+  const int32_t* action;      /* [n_rows] in [0, n_actions)                                      */
+  const float* reward;        /* [n_rows]                                                        */
+  const uint8_t* terminal;    /* [n_rows] 0/1                                                    */
+  const void* p_log;          /* [n_rows][n_actions] logged action distribution                  */
+  const int32_t* step;        /* [n_rows] or NULL: row is an initial state iff step == 0
+                                 (psrs.py:22; data.py:72 — no column means every row is)          */
+} ols_log_t;
+
+/* ---- the bucketed log: per-state FIFO queues in CSR form (psrs.py:22-30) ------------------ *
+ * Queue b holds slots offsets[b] .. offsets[b+1]-1; slot k carries the packed record of row
+ * order[k].  Record layout (rec_bytes = 16 * (1 + ceil(n_actions / 4))):
+ *     float    p[4 * ceil(n_actions/4)]   logged distribution, zero padded (rounded to float32
+ *                                         when the log is float64; the exact path then reads
+ *                                         p_log64[order[k]])
+ *     float    reward
+ *     int32_t  z_next
+ *     int32_t  s_next
+ *     uint32_t meta                       bits 0..7 action, bit 8 terminal                    */
+typedef struct ols_queues {
+  int64_t n_rows;
+  int64_t n_init;             /* number of initial rows                                          */
+  int32_t n_actions;
+  int32_t n_buckets;          /* number of queue keys                                            */
+  int32_t z_offset;           /* bucket = z + z_offset (1 when the encoder can emit -1,
+                                 encoders/heuristic.py:23-24)                                    */
+  int32_t rec_bytes;
+  int32_t* offsets;           /* [n_buckets + 1]                                                 */
+  int32_t* order;             /* [n_rows]                                                        */
+  void* records;              /* [n_rows * rec_bytes], 16-byte aligned                           */
+  int32_t* init_row;          /* [n_init] initial rows in queue order (psrs.py:22-23)            */
+  int32_t* init_z;            /* [n_init] their z                                                */
+  int32_t* init_s;            /* [n_init] their s                                                */
+  const double* p_log64;      /* NULL, or the float64 log distribution [n_rows][n_actions] in ROW
+                                 order when it is not exactly float32-representable              */
+} ols_queues_t;
+
+/* ---- a block of independent simulation replicas ------------------------------------------ *
+ * One replica == one reference `PSRS` object over the same bucketed log (its own queue cursors,
+ * initial-state cursor, current (z, s) and uniform stream).                                    */
+typedef struct ols_replicas {
+  int64_t n_replicas;
+  int64_t replica_id0;        /* global id of replica 0 of this block (multi-GPU sharding; keys
+                                 the Philox streams and the ring offsets)                        */
+  int32_t* cursor;            /* [n_replicas][n_buckets] records consumed from each queue        */
+  int32_t* init_cursor;       /* [n_replicas] initial states consumed                            */
+  int32_t* cur_z;             /* [n_replicas]                                                    */
+  int32_t* cur_s;             /* [n_replicas]                                                    */
+  int32_t* status;            /* [n_replicas] OLS_RUNNING ...                                    */
+  uint64_t* draws;            /* [n_replicas] uniforms consumed (one per pop, psrs.py:56)        */
+  uint64_t* ties;             /* [n_replicas] tie-break values consumed (tabular.py:4-5)         */
+  uint64_t* pops;             /* [n_replicas] records popped                                     */
+  uint64_t* accepted;         /* [n_replicas] transitions accepted                               */
+  /* episode registers of the fused drivers; they make ols_run resumable across calls          */
+  int32_t* ep_index;          /* [n_replicas] episodes appended to Gs so far                     */
+  int32_t* ep_len_count;      /* [n_replicas] entries written to `lengths` (psrs.py:265)         */
+  int32_t* ep_t;              /* [n_replicas] step inside the open episode                       */
+  int32_t* ep_open;           /* [n_replicas] 1 while an episode is in progress                  */
+  double* ep_G;               /* [n_replicas] discounted return of the open episode              */
+  double* ep_disc;            /* [n_replicas] gamma^t of the open episode                        */
+  /* uniform stream of the rejection rule                                                      */
+  int32_t rng_mode;           /* OLS_RNG_*                                                       */
+  int32_t tie_mode;           /* OLS_RNG_FEED or OLS_RNG_PHILOX                                  */
+  uint64_t seed;              /* Philox key                                                      */
+  uint64_t* pcg_state;        /* [n_replicas][4] {state_hi, state_lo, inc_hi, inc_lo} (PCG64)    */
+  const double* u_feed;       /* FEED: uniforms; element [replica * u_stride + draw]             */
+  int64_t u_feed_len;
+  int64_t u_stride;           /* 0: one stream shared by all replicas                            */
+  const double* tie_feed;
+  int64_t tie_feed_len;
+  int64_t tie_stride;
+  /* optional decorrelation of replicas that share one queue order (not in the reference; 0 in
+   * parity runs): queue b of replica r is consumed as a ring starting at hash(ring_seed, r, b)
+   * mod len_b, the initial-state list at hash(ring_seed, r) mod n_init.                        */
+  int32_t ring_mode;          /* 0 off, 1 on                                                     */
+  int32_t _pad;
+  uint64_t ring_seed;
+} ols_replicas_t;
+
+/* ---- batched step: outputs of one accepted transition per replica ------------------------- */
+typedef struct ols_step_out {
+  int32_t* row;               /* [n_replicas] accepted log row, -1 when nothing was accepted     */
+  int32_t* action;            /* [n_replicas] info['a'] (psrs.py:51)                             */
+  float* reward;              /* [n_replicas]                                                    */
+  uint8_t* terminal;          /* [n_replicas]                                                    */
+  int32_t* s_next;            /* [n_replicas]                                                    */
+  int32_t* z_from;            /* [n_replicas] info['z']                                          */
+} ols_step_out_t;
+
+/* ---- fused learner / evaluator run -------------------------------------------------------- */
+typedef struct ols_run {
+  int32_t agent;              /* OLS_AGENT_*                                                     */
+  int32_t n_states;           /* rows of Q and pi (env.nS, psrs.py:139)                          */
+  int32_t q_is_f64;           /* dtype of Q: 0 float32 (production), 1 float64 (parity)          */
+  int32_t pi_is_f64;          /* dtype of pi                                                     */
+  int32_t reject_mode;        /* OLS_REJECT_*                                                    */
+  int32_t compute_mode;       /* OLS_COMPUTE_* (F32 only meaningful with a float32 pi)           */
+  int32_t lanes;              /* lane-group width per replica: 1,2,4,8,16 or 32                  */
+  int32_t n_episodes;         /* stop a replica after this many episodes                         */
+  int32_t ep_cap;             /* row length of Gs / lengths (>= n_episodes + 1)                  */
+  int32_t stage_smem;         /* 1: stage the replica's cursor table (and Q) in shared memory
+                                 when it fits; 0: operate on global memory                       */
+  int64_t max_steps;          /* > 0: every replica stops after this many accepted transitions in
+                                 THIS call and stays resumable (not in the reference)            */
+  double gamma;
+  const double* alpha;        /* [n_episodes] step size per episode (psrs.py:134-136), QLEARN/EXPSARSA */
+  const double* epsilon;      /* [n_episodes] exploration per episode (psrs.py:129-132), QLEARN  */
+  const void* pi;             /* [n_states][n_actions] fixed policy, FIXED_PI/EXPSARSA           */
+  void* Q;                    /* [n_replicas][n_states][n_actions], QLEARN/EXPSARSA              */
+  double* Gs;                 /* [n_replicas][ep_cap] discounted return per episode              */
+  int32_t* lengths;           /* [n_replicas][ep_cap] episode lengths                            */
+  /* optional parity taps (NULL to disable)                                                    */
+  int32_t* trace_row;         /* [n_replicas][trace_cap] accepted rows, indexed by `accepted`    */
+  double* td_error;           /* [n_replicas][trace_cap] TD errors (psrs.py:165), QLEARN         */
+  int64_t trace_cap;
+} ols_run_t;
+
+/* ---- library ------------------------------------------------------------------------------ */
+int ols_abi_version(void);
+const char* ols_last_error(void);                          /* HOST string, thread-local          */
+/* sizeof() of each struct as compiled, indexed 0..4 = log, queues, replicas, step_out, run —
+ * lets a binding verify its mirror of the layouts.                                            */
+size_t ols_struct_bytes(int which);
+
+/* ---- state encoders: observation -> integer state id (the queue key) ---------------------- */
+/* Grid discretiser for MyGridNaviCoords observations (envs/gridworld.py:205-211,123-124):
+ * id = sum_d min(floor(cells * obs[d]), cells-1) * cells^d, float32 arithmetic.                */
+int ols_encode_grid(const float* obs, int64_t n, int32_t d_obs, int32_t cells, int32_t* ids, void* stream);
+/* encoders/heuristic.py:20-60 `CartpoleBoxEncoder.get_box` (+ :65-71 `encode`): 162 boxes, -1 on
+ * failure; comparisons in the observation dtype (obs_is_f64).  obs is [n][4].                  */
+int ols_encode_cartpole_box(const void* obs, int32_t obs_is_f64, int64_t n, int32_t* ids, void* stream);
+/* encoders/homer.py:159-168 `HOMEREncoder.encode` over encoders/models.py:15-19 `obs_encoder`:
+ * argmax_k( W2 · leaky_relu(W1 · x + b1, slope) + b2 ), float32 FMA in index order, first max.
+ * W1 [hidden][d_obs], W2 [n_latent][hidden], row-major as torch.nn.Linear stores them.         */
+int ols_encode_mlp(const float* obs, int64_t n, int32_t d_obs, const float* W1, const float* b1, int32_t hidden,
+                   const float* W2, const float* b2, int32_t n_latent, float negative_slope, int32_t* ids,
+                   void* stream);
+
+/* ---- bucketing: psrs.py:19-30 `PSRS.reset_sampler` ---------------------------------------- */
+int32_t ols_record_bytes(int32_t n_actions);
+size_t ols_bucket_scratch_bytes(int64_t n_rows, int32_t n_buckets);
+/* Stable counting sort of the rows by z (psrs.py:26: sorted + groupby) fused with record packing.
+ * Fills q->offsets, q->order, q->records (log order inside every queue).  q's scalar fields and
+ * buffer pointers are set by the caller.                                                       */
+int ols_bucket(const ols_log_t* log, const ols_queues_t* q, void* scratch, size_t scratch_bytes, void* stream);
+/* psrs.py:22 — initial rows (step == 0) in log order -> q->init_row/init_z/init_s; the count is
+ * written to *n_init_dev (device int64).  scratch: ols_bucket_scratch_bytes(n_rows, 1).        */
+int ols_init_queue(const ols_log_t* log, const ols_queues_t* q, int64_t* n_init_dev, void* scratch,
+                   size_t scratch_bytes, void* stream);
+/* psrs.py:23,29-30 — replay `np.random.default_rng(seed).shuffle` on the initial-state list and on
+ * every queue (a fresh generator each): dst gets the permuted order/records/init_* of src (src
+ * stays the log-order CSR; dst->offsets may alias src->offsets).  perm_scratch: n_rows + n_init
+ * int32.                                                                                       */
+int ols_shuffle_queues(const ols_queues_t* src, const ols_queues_t* dst, uint64_t seed, int32_t* perm_scratch,
+                       void* stream);
+
+/* ---- replicas ----------------------------------------------------------------------------- */
+/* Zero cursors/counters, status = OLS_IDLE, and (PCG64 mode) seed every replica's generator with
+ * seeds[r] (device array, NULL = r->seed for all) exactly as np.random.default_rng does.       */
+int ols_replicas_init(const ols_queues_t* q, const ols_replicas_t* r, const uint64_t* seeds, void* stream);
+/* psrs.py:32-37 `PSRS.reset` for the replicas with mask[r] != 0 (mask NULL = all): pops the next
+ * initial state into (cur_z, cur_s) or sets OLS_INIT_EMPTY.                                     */
+int ols_reset(const ols_queues_t* q, const ols_replicas_t* r, const uint8_t* mask, void* stream);
+/* psrs.py:39-57 `PSRS.step` + `_default_reject` for every RUNNING replica with mask[r] != 0:
+ * p_new is [n_replicas][n_actions] (p_stride = n_actions) or one shared row (p_stride = 0),
+ * float64 or float32 (p_new_is_f64).                                                           */
+int ols_step(const ols_queues_t* q, const ols_replicas_t* r, const uint8_t* mask, const void* p_new,
+             int32_t p_new_is_f64, int64_t p_stride, int32_t reject_mode, int32_t compute_mode, int32_t lanes,
+             const ols_step_out_t* out, void* stream);
+/* psrs.py:119-271 `qlearn_psrs` / `expSARSA_psrs` / `evalMC_psrs`, one independent run per replica,
+ * fused with the agent update and the per-episode return evaluator.                            */
+int ols_run(const ols_queues_t* q, const ols_replicas_t* r, const ols_run_t* run, void* stream);
+
+/* ---- evaluators --------------------------------------------------------------------------- */
+size_t ols_curve_scratch_bytes(int64_t n_replicas, int32_t n_episodes);
+/* Learning curve over replicas: for every episode index e < n_episodes, over the replicas with
+ * ep_index[r] > e: sum[e] = Σ Gs[r][e], sumsq[e] = Σ Gs[r][e]^2, count[e] (as double) — the
+ * mean ± std curve of utils/vis_utils.py:15-21 on the Gs of psrs.py:180-185.  Deterministic.    */
+int ols_reduce_curves(const double* Gs, const int32_t* ep_index, int64_t n_replicas, int32_t ep_cap,
+                      int32_t n_episodes, double* sum, double* sumsq, double* count, void* scratch,
+                      size_t scratch_bytes, void* stream);
+/* Per-replica segment reduction: ret_sum[r] = Σ_e Gs[r][e], len_sum[r] = Σ_e lengths[r][e] over
+ * that replica's own episodes (segments of ragged length ep_index[r] / ep_len_count[r]).        */
+int ols_replica_totals(const double* Gs, const int32_t* lengths, const int32_t* ep_index,
+                       const int32_t* ep_len_count, int64_t n_replicas, int32_t ep_cap, double* ret_sum,
+                       int64_t* len_sum, void* stream);
+
+/* ---- synthetic logged data of the benchmark shape -------------------------- */
+/* Row i from Philox(seed, i): z, z_next ~ U{0..n_states-1}; a ~ pb_state[z]; r ~ N(0,1);
+ * terminal ~ Bernoulli(p_done); step = 0 iff i == 0 or terminal[i-1].  Writes the columns of
+ * `log` (its pointers must be writable; p_log float32).                                         */
+int ols_synth_log(const ols_log_t* log, const float* pb_state, int32_t n_states, uint64_t seed, double p_done,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OLS_B200_H */

@@ -1,0 +1,602 @@
+// Bucketing of the logged transitions into per-state FIFO queues (CSR), on the GPU.
+//
+// Replaces offsim4rl/evaluators/psrs.py:19-30 `PSRS.reset_sampler`:
+//   :22     init_queue = rows with info['t'] == 0, in log order        -> init_* kernels
+//   :26     sorted(buffer, key=z) (stable) + groupby -> queues[z]      -> histogram / scan / scatter
+//   :23,29-30  default_rng(seed).shuffle(...) of init_queue and of every queue
+//                                                                      -> shuffle_perm / gather kernels
+//
+// The sort is a STABLE counting sort in one scatter pass.  The rows are cut into T contiguous
+// tiles, one tile per warp.  Pass 1 builds a per-tile histogram in the warp's private slice of
+// shared memory; a column scan over the [tile][bucket] table gives every tile its first slot in
+// every queue; pass 2 re-walks the tile in log order, ranks equal keys inside each 32-row batch
+// with __match_any_sync (lower lane = earlier row), and writes `order` plus the packed 16B-aligned
+// record straight to the final slot.  Algorithmic traffic per row: z twice (8 B), the log columns
+// once (~17 + 4*nA B), record + order written once (rec_bytes + 4 B).
+#include <limits.h>
+
+#include "ols_common.cuh"
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+struct BucketPlan {
+  int warps_per_cta;
+  int ctas;
+  int tiles;          // = warps_per_cta * ctas
+  int64_t tile_rows;  // multiple of 32
+  size_t smem_bytes;  // per CTA
+};
+
+// One private histogram of n_buckets counters per warp; up to 16 warps per CTA, as many CTAs as
+// fit the 148 SMs once or twice (grid = multiple of the SM count).
+inline bool make_plan(int64_t n_rows, int n_buckets, BucketPlan* p) {
+  const size_t smem_cap = 200 * 1024;
+  size_t per_warp = (size_t)n_buckets * sizeof(uint32_t);
+  if (per_warp > smem_cap) return false;
+  int w = (int)(smem_cap / per_warp);
+  if (w > 16) w = 16;
+  const int ctas_per_sm = ((size_t)w * per_warp <= 100 * 1024) ? 2 : 1;
+  const int64_t max_tiles = (int64_t)OLS_SM_COUNT * ctas_per_sm * w;
+  int64_t want = (n_rows + 2047) / 2048;  // small logs: no tile shorter than ~2048 rows
+  if (want < 1) want = 1;
+  int64_t tiles = want < max_tiles ? want : max_tiles;
+  int ctas = (int)((tiles + w - 1) / w);
+  p->warps_per_cta = w;
+  p->ctas = ctas;
+  p->tiles = w * ctas;
+  int64_t tr = (n_rows + p->tiles - 1) / p->tiles;
+  tr = (tr + 31) / 32 * 32;
+  if (tr < 32) tr = 32;
+  p->tile_rows = tr;
+  p->smem_bytes = (size_t)w * per_warp;
+  return true;
+}
+
+struct Scratch {
+  uint32_t* tile_hist;  // [tiles][n_buckets]
+  uint32_t* totals;     // [n_buckets]
+  uint32_t* invalid;    // [1] rows whose bucket is out of range (skipped)
+};
+
+inline size_t scratch_bytes_for(const BucketPlan& p, int n_buckets) {
+  size_t a = ((size_t)p.tiles * n_buckets + n_buckets + 64) * sizeof(uint32_t);
+  return (a + 255) / 256 * 256;
+}
+inline Scratch carve(void* base, const BucketPlan& p, int n_buckets) {
+  Scratch s;
+  s.tile_hist = (uint32_t*)base;
+  s.totals = s.tile_hist + (size_t)p.tiles * n_buckets;
+  s.invalid = s.totals + n_buckets;
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------- pass 1
+__global__ void __launch_bounds__(512) tile_histogram_kernel(const int32_t* __restrict__ z, int64_t n_rows, int z_offset,
+                                                              int n_buckets, int64_t tile_rows,
+                                                              uint32_t* __restrict__ tile_hist,
+                                                              uint32_t* __restrict__ invalid) {
+  extern __shared__ uint32_t s_hist[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x * (blockDim.x >> 5) + warp;
+  uint32_t* h = s_hist + (size_t)warp * n_buckets;
+  for (int b = lane; b < n_buckets; b += 32) h[b] = 0;
+  __syncwarp();
+  const int64_t lo = (int64_t)tile * tile_rows;
+  const int64_t hi = min(lo + tile_rows, n_rows);
+  uint32_t bad = 0;
+  for (int64_t base = lo; base < hi; base += 128) {
+    int key[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int64_t i = base + j * 32 + lane;
+      key[j] = (i < hi) ? __ldg(z + i) + z_offset : INT_MIN;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (key[j] >= 0 && key[j] < n_buckets) atomicAdd(&h[key[j]], 1u);
+      else if (key[j] != INT_MIN) ++bad;  // id outside [-z_offset, n_buckets - z_offset): row is dropped
+    }
+  }
+  __syncwarp();
+  uint32_t* out = tile_hist + (size_t)tile * n_buckets;
+  for (int b = lane; b < n_buckets; b += 32) out[b] = h[b];
+  if (bad) atomicAdd(invalid, bad);
+}
+
+// ---------------------------------------------------------------------------------------- scans
+// Column scan of the [tiles][n_buckets] table: block = 32 buckets (x) by 32 tile stripes (y).
+__global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t* __restrict__ tile_hist, int tiles, int n_buckets,
+                                                         uint32_t* __restrict__ totals) {
+  __shared__ uint32_t part[32][33];
+  const int b = blockIdx.x * 32 + threadIdx.x;
+  const int y = threadIdx.y;
+  const int per = (tiles + 31) / 32;
+  const int t0 = y * per, t1 = min(t0 + per, tiles);
+  uint32_t sum = 0;
+  if (b < n_buckets)
+    for (int t = t0; t < t1; ++t) sum += tile_hist[(size_t)t * n_buckets + b];
+  part[y][threadIdx.x] = sum;
+  __syncthreads();
+  if (y == 0) {
+    uint32_t run = 0;
+    for (int k = 0; k < 32; ++k) {
+      uint32_t v = part[k][threadIdx.x];
+      part[k][threadIdx.x] = run;
+      run += v;
+    }
+    if (b < n_buckets) totals[b] = run;
+  }
+  __syncthreads();
+  if (b < n_buckets) {
+    uint32_t run = part[y][threadIdx.x];
+    for (int t = t0; t < t1; ++t) {
+      size_t idx = (size_t)t * n_buckets + b;
+      uint32_t v = tile_hist[idx];
+      tile_hist[idx] = run;
+      run += v;
+    }
+  }
+}
+
+// Exclusive scan of the bucket totals -> CSR offsets (single CTA; n_buckets is at most ~51k).
+__global__ void __launch_bounds__(1024) offsets_kernel(const uint32_t* __restrict__ totals, int n_buckets,
+                                                        int32_t* __restrict__ offsets) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n_buckets; base += 1024) {
+    int i = base + threadIdx.x;
+    uint32_t v = (i < n_buckets) ? totals[i] : 0u;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t o = __shfl_up_sync(kFull, inc, d);
+      if (lane >= d) inc += o;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = warp_sums[lane];
+      uint32_t winc = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(kFull, winc, d);
+        if (lane >= d) winc += o;
+      }
+      warp_sums[lane] = winc - w;  // exclusive
+    }
+    __syncthreads();
+    uint32_t excl = carry + warp_sums[warp] + inc - v;
+    if (i < n_buckets) offsets[i] = (int32_t)excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offsets[n_buckets] = (int32_t)carry;
+}
+
+// ---------------------------------------------------------------------------------------- pass 2
+template <int NV>
+struct RowData {
+  float4 p[NV];
+  float r;
+  int zn, sn;
+  uint32_t meta;
+};
+
+template <int NV>
+__device__ __forceinline__ void load_row(const ols_log_t& log, int64_t i, RowData<NV>& d) {
+  const int nA = log.n_actions;
+  float pv[4 * NV];
+#pragma unroll
+  for (int j = 0; j < 4 * NV; ++j) pv[j] = 0.0f;
+  if (log.p_is_f64) {
+    const double* p = (const double*)log.p_log + i * nA;
+#pragma unroll
+    for (int j = 0; j < 4 * NV; ++j)
+      if (j < nA) pv[j] = (float)__ldg(p + j);
+  } else if (NV == 1 && nA == 4) {
+    float4 v = __ldg((const float4*)log.p_log + i);
+    pv[0] = v.x; pv[1] = v.y; pv[2] = v.z; pv[3] = v.w;
+  } else if (NV == 1 && nA == 2) {
+    float2 v = __ldg((const float2*)log.p_log + i);
+    pv[0] = v.x; pv[1] = v.y;
+  } else {
+    const float* p = (const float*)log.p_log + i * nA;
+#pragma unroll
+    for (int j = 0; j < 4 * NV; ++j)
+      if (j < nA) pv[j] = __ldg(p + j);
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) d.p[v] = make_float4(pv[4 * v], pv[4 * v + 1], pv[4 * v + 2], pv[4 * v + 3]);
+  d.r = __ldg(log.reward + i);
+  d.zn = __ldg(log.z_next + i);
+  d.sn = log.s_next ? __ldg(log.s_next + i) : d.zn;
+  d.meta = ols_pack_meta(__ldg(log.action + i), __ldg(log.terminal + i));
+}
+
+template <int NV>
+__global__ void __launch_bounds__(512) scatter_pack_kernel(ols_log_t log, ols_queues_t q, int64_t tile_rows,
+                                                            const uint32_t* __restrict__ tile_hist) {
+  extern __shared__ uint32_t s_next_slot[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x * (blockDim.x >> 5) + warp;
+  const int nB = q.n_buckets;
+  uint32_t* slot = s_next_slot + (size_t)warp * nB;
+  const uint32_t* th = tile_hist + (size_t)tile * nB;
+  for (int b = lane; b < nB; b += 32) slot[b] = (uint32_t)__ldg(q.offsets + b) + th[b];
+  __syncwarp();
+  const int64_t lo = (int64_t)tile * tile_rows;
+  const int64_t hi = min(lo + tile_rows, log.n_rows);
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  constexpr int U = 2;  // batches in flight per warp iteration
+  for (int64_t base = lo; base < hi; base += 32 * U) {
+    int key[U];
+    RowData<NV> row[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      int64_t i = base + j * 32 + lane;
+      key[j] = -1;
+      if (i < hi) {
+        int b = __ldg(log.z + i) + q.z_offset;
+        if (b >= 0 && b < nB) {
+          key[j] = b;
+          load_row<NV>(log, i, row[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const bool valid = key[j] >= 0;
+      // lanes holding the same key, lowest lane = earliest row; invalid lanes form their own group
+      unsigned peers = __match_any_sync(kFull, key[j]);
+      unsigned rank = __popc(peers & lt_mask);
+      int leader = __ffs(peers) - 1;
+      uint32_t first = 0;
+      if (valid && lane == leader) {
+        first = slot[key[j]];
+        slot[key[j]] = first + __popc(peers);
+      }
+      first = __shfl_sync(kFull, first, leader);
+      __syncwarp();
+      if (valid) {
+        uint32_t pos = first + rank;
+        int64_t i = base + j * 32 + lane;
+        q.order[pos] = (int32_t)i;
+        float4* dst = (float4*)((char*)q.records + (size_t)pos * q.rec_bytes);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) dst[v] = row[j].p[v];
+        float4 tail;
+        tail.x = row[j].r;
+        tail.y = __int_as_float(row[j].zn);
+        tail.z = __int_as_float(row[j].sn);
+        tail.w = __uint_as_float(row[j].meta);
+        dst[NV] = tail;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------- initial rows
+// Stable compaction of the rows with step == 0: per-CTA counts -> scan -> ordered write.
+constexpr int kInitThreads = 256;
+
+__global__ void __launch_bounds__(kInitThreads) init_count_kernel(const int32_t* __restrict__ step, int64_t n_rows,
+                                                                   int64_t chunk, uint32_t* __restrict__ counts) {
+  __shared__ uint32_t wsum[kInitThreads / 32];
+  const int64_t lo = (int64_t)blockIdx.x * chunk, hi = min(lo + chunk, n_rows);
+  uint32_t c = 0;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += kInitThreads) c += (__ldg(step + i) == 0);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(kFull, c, d);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < kInitThreads / 32; ++w) t += wsum[w];
+    counts[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(1024) init_scan_kernel(uint32_t* __restrict__ counts, int n, int64_t* __restrict__ total) {
+  // single CTA, n <= a few thousand
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    int i = base + threadIdx.x;
+    uint32_t v = (i < n) ? counts[i] : 0u, inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t o = __shfl_up_sync(kFull, inc, d);
+      if (lane >= d) inc += o;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = warp_sums[lane], winc = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t o = __shfl_up_sync(kFull, winc, d);
+        if (lane >= d) winc += o;
+      }
+      warp_sums[lane] = winc - w;
+    }
+    __syncthreads();
+    uint32_t excl = carry + warp_sums[warp] + inc - v;
+    if (i < n) counts[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = (int64_t)carry;
+}
+
+__global__ void all_rows_prefix_kernel(uint32_t* __restrict__ prefix, int n_chunks, uint32_t chunk, int64_t n_rows,
+                                       int64_t* __restrict__ total) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n_chunks) prefix[c] = (uint32_t)c * chunk;
+  if (c == 0) *total = n_rows;
+}
+
+__global__ void __launch_bounds__(kInitThreads) init_write_kernel(ols_log_t log, ols_queues_t q, int64_t chunk,
+                                                                   const uint32_t* __restrict__ prefix) {
+  __shared__ uint32_t wsum[kInitThreads / 32];
+  __shared__ uint32_t running;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t lo = (int64_t)blockIdx.x * chunk, hi = min(lo + chunk, log.n_rows);
+  if (threadIdx.x == 0) running = prefix[blockIdx.x];
+  __syncthreads();
+  for (int64_t base = lo; base < hi; base += kInitThreads) {
+    int64_t i = base + threadIdx.x;
+    bool flag = (i < hi) && (log.step == nullptr || __ldg(log.step + i) == 0);
+    unsigned ballot = __ballot_sync(kFull, flag);
+    if (lane == 0) wsum[warp] = __popc(ballot);
+    __syncthreads();
+    uint32_t before = running;
+    for (int w = 0; w < warp; ++w) before += wsum[w];
+    if (flag) {
+      uint32_t pos = before + __popc(ballot & ((1u << lane) - 1u));
+      int zz = __ldg(log.z + i);
+      q.init_row[pos] = (int32_t)i;
+      q.init_z[pos] = zz;
+      q.init_s[pos] = log.s ? __ldg(log.s + i) : zz;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t t = 0;
+      for (int w = 0; w < kInitThreads / 32; ++w) t += wsum[w];
+      running += t;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------- seeded shuffle
+// np.random.default_rng(seed).shuffle(x) on a length-n list: for i = n-1 .. 1: j = interval(i);
+// swap(x[i], x[j]); interval() is NumPy's masked rejection on buffered 32-bit halves of PCG64 output
+// (64-bit draws when i > 2^32-1, which cannot occur with int32 row indices).  One thread replays one
+// queue: the chain is inherently sequential (every draw count depends on the rejections before it).
+// perm[] holds absolute slot indices, pre-filled with iota; segment `seg` covers [lo, lo+len).
+__global__ void iota_kernel(int32_t* __restrict__ perm, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    perm[i] = (int32_t)i;
+}
+
+__global__ void __launch_bounds__(128) shuffle_perm_kernel(const int32_t* __restrict__ offsets, int n_buckets,
+                                                            int64_t n_rows, int64_t n_init, uint64_t seed,
+                                                            int32_t* __restrict__ perm) {
+  const int seg = blockIdx.x * blockDim.x + threadIdx.x;
+  if (seg > n_buckets) return;
+  int64_t lo, len;
+  if (seg < n_buckets) {
+    lo = offsets[seg];
+    len = offsets[seg + 1] - lo;
+  } else {  // the initial-state list lives after the n_rows queue slots
+    lo = n_rows;
+    len = n_init;
+  }
+  if (len < 2) return;
+  ols_u128 state, inc;
+  ols_pcg64_seed(seed, &state, &inc);
+  bool has32 = false;
+  uint32_t buffered = 0;
+  int32_t* x = perm + lo;
+  for (uint32_t i = (uint32_t)len - 1; i >= 1; --i) {
+    uint32_t mask = i;
+    mask |= mask >> 1;
+    mask |= mask >> 2;
+    mask |= mask >> 4;
+    mask |= mask >> 8;
+    mask |= mask >> 16;
+    uint32_t j;
+    do {
+      uint32_t v;
+      if (has32) {
+        v = buffered;
+        has32 = false;
+      } else {
+        state = ols_pcg_step(state, inc);
+        uint64_t o = ols_pcg_output(state);
+        v = (uint32_t)o;
+        buffered = (uint32_t)(o >> 32);
+        has32 = true;
+      }
+      j = v & mask;
+    } while (j > i);
+    int32_t a = x[i], b = x[j];
+    x[i] = b;
+    x[j] = a;
+  }
+}
+
+__global__ void __launch_bounds__(256) gather_queues_kernel(ols_queues_t src, ols_queues_t dst,
+                                                             const int32_t* __restrict__ perm) {
+  const int chunks = src.rec_bytes / 16;
+  const int64_t total = src.n_rows * chunks;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t slot = e / chunks;
+    int c = (int)(e % chunks);
+    int32_t from = __ldg(perm + slot);
+    const float4* s = (const float4*)((const char*)src.records + (size_t)from * src.rec_bytes);
+    float4* d = (float4*)((char*)dst.records + (size_t)slot * dst.rec_bytes);
+    d[c] = __ldg(s + c);
+    if (c == 0) dst.order[slot] = __ldg(src.order + from);
+  }
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < src.n_init; k += (int64_t)gridDim.x * blockDim.x) {
+    int32_t from = __ldg(perm + src.n_rows + k) - (int32_t)src.n_rows;
+    dst.init_row[k] = __ldg(src.init_row + from);
+    dst.init_z[k] = __ldg(src.init_z + from);
+    dst.init_s[k] = __ldg(src.init_s + from);
+  }
+}
+
+int check_queues(const ols_queues_t* q, const char* who) {
+  OLS_REQUIRE(q != nullptr, OLS_ERR_INVALID, "%s: null queues", who);
+  OLS_REQUIRE(q->n_rows >= 0 && q->n_rows < (1ll << 31), OLS_ERR_INVALID, "%s: n_rows must be in [0, 2^31)", who);
+  OLS_REQUIRE(q->n_actions >= 1 && q->n_actions <= OLS_MAX_ACTIONS, OLS_ERR_UNSUPPORTED,
+              "%s: n_actions must be in [1, %d]", who, OLS_MAX_ACTIONS);
+  OLS_REQUIRE(q->n_buckets >= 1, OLS_ERR_INVALID, "%s: n_buckets must be >= 1", who);
+  OLS_REQUIRE(q->rec_bytes == ols_record_bytes(q->n_actions), OLS_ERR_INVALID, "%s: rec_bytes must be %d", who,
+              ols_record_bytes(q->n_actions));
+  OLS_REQUIRE(q->offsets != nullptr, OLS_ERR_INVALID, "%s: null offsets", who);
+  OLS_REQUIRE(q->n_rows == 0 || (q->order && q->records), OLS_ERR_INVALID, "%s: null order/records", who);
+  OLS_REQUIRE((uintptr_t)q->records % 16 == 0, OLS_ERR_INVALID, "%s: records must be 16-byte aligned", who);
+  return OLS_OK;
+}
+
+}  // namespace
+
+extern "C" int32_t ols_record_bytes(int32_t n_actions) {
+  if (n_actions < 1 || n_actions > OLS_MAX_ACTIONS) return 0;
+  return 16 * (1 + (n_actions + 3) / 4);
+}
+
+extern "C" size_t ols_bucket_scratch_bytes(int64_t n_rows, int32_t n_buckets) {
+  BucketPlan p;
+  if (n_rows < 0 || n_buckets < 1 || !make_plan(n_rows, n_buckets, &p)) return 0;
+  size_t a = scratch_bytes_for(p, n_buckets);
+  // the initial-row compaction reuses the same scratch: one counter per 4096-row chunk
+  size_t b = (size_t)((n_rows + 4095) / 4096 + 64) * sizeof(uint32_t);
+  return a > b ? a : b;
+}
+
+extern "C" int ols_bucket(const ols_log_t* log, const ols_queues_t* q, void* scratch, size_t scratch_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  OLS_REQUIRE(log != nullptr, OLS_ERR_INVALID, "ols_bucket: null log");
+  int rc = check_queues(q, "ols_bucket");
+  if (rc) return rc;
+  OLS_REQUIRE(log->n_rows == q->n_rows && log->n_actions == q->n_actions, OLS_ERR_INVALID,
+              "ols_bucket: log and queues disagree on n_rows / n_actions");
+  BucketPlan plan;
+  OLS_REQUIRE(make_plan(q->n_rows, q->n_buckets, &plan), OLS_ERR_UNSUPPORTED,
+              "ols_bucket: n_buckets = %d needs more than 200 KB of shared memory per warp histogram", q->n_buckets);
+  OLS_REQUIRE(scratch != nullptr && scratch_bytes >= scratch_bytes_for(plan, q->n_buckets), OLS_ERR_INVALID,
+              "ols_bucket: scratch too small (%zu < %zu)", scratch_bytes, scratch_bytes_for(plan, q->n_buckets));
+  if (q->n_rows > 0) {
+    OLS_REQUIRE(log->z && log->z_next && log->action && log->reward && log->terminal && log->p_log, OLS_ERR_INVALID,
+                "ols_bucket: null log column");
+    OLS_REQUIRE((uintptr_t)log->p_log % 16 == 0, OLS_ERR_INVALID, "ols_bucket: p_log must be 16-byte aligned");
+  }
+  Scratch s = carve(scratch, plan, q->n_buckets);
+  OLS_CUDA_CHECK(cudaMemsetAsync(s.invalid, 0, sizeof(uint32_t), stream));
+  const int threads = plan.warps_per_cta * 32;
+  if (plan.smem_bytes > 48 * 1024) {
+    OLS_CUDA_CHECK(cudaFuncSetAttribute(tile_histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes));
+  }
+  tile_histogram_kernel<<<plan.ctas, threads, plan.smem_bytes, stream>>>(log->z, q->n_rows, q->z_offset, q->n_buckets,
+                                                                        plan.tile_rows, s.tile_hist, s.invalid);
+  OLS_LAUNCH_CHECK();
+  tile_scan_kernel<<<ols_div_up(q->n_buckets, 32), dim3(32, 32), 0, stream>>>(s.tile_hist, plan.tiles, q->n_buckets, s.totals);
+  OLS_LAUNCH_CHECK();
+  offsets_kernel<<<1, 1024, 0, stream>>>(s.totals, q->n_buckets, q->offsets);
+  OLS_LAUNCH_CHECK();
+  if (q->n_rows == 0) return OLS_OK;
+  const int nv = (q->n_actions + 3) / 4;
+#define OLS_SCATTER(NV)                                                                                              \
+  do {                                                                                                               \
+    if (plan.smem_bytes > 48 * 1024)                                                                                 \
+      OLS_CUDA_CHECK(cudaFuncSetAttribute(scatter_pack_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                          (int)plan.smem_bytes));                                                    \
+    scatter_pack_kernel<NV><<<plan.ctas, threads, plan.smem_bytes, stream>>>(*log, *q, plan.tile_rows, s.tile_hist); \
+  } while (0)
+  switch (nv) {
+    case 1: OLS_SCATTER(1); break;
+    case 2: OLS_SCATTER(2); break;
+    case 3: OLS_SCATTER(3); break;
+    default: OLS_SCATTER(4); break;
+  }
+#undef OLS_SCATTER
+  OLS_LAUNCH_CHECK();
+  return OLS_OK;
+}
+
+extern "C" int ols_init_queue(const ols_log_t* log, const ols_queues_t* q, int64_t* n_init_dev, void* scratch,
+                              size_t scratch_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  OLS_REQUIRE(log && q && n_init_dev, OLS_ERR_INVALID, "ols_init_queue: null argument");
+  OLS_REQUIRE(log->n_rows >= 0 && log->n_rows < (1ll << 31), OLS_ERR_INVALID, "ols_init_queue: bad n_rows");
+  const int64_t chunk = 4096;
+  const int n_chunks = (int)((log->n_rows + chunk - 1) / chunk);
+  OLS_REQUIRE(scratch && scratch_bytes >= (size_t)(n_chunks + 1) * sizeof(uint32_t), OLS_ERR_INVALID,
+              "ols_init_queue: scratch too small");
+  if (log->n_rows == 0) {
+    OLS_CUDA_CHECK(cudaMemsetAsync(n_init_dev, 0, sizeof(int64_t), stream));
+    return OLS_OK;
+  }
+  OLS_REQUIRE(log->z && q->init_row && q->init_z && q->init_s, OLS_ERR_INVALID, "ols_init_queue: null buffer");
+  uint32_t* counts = (uint32_t*)scratch;
+  if (log->step) {
+    init_count_kernel<<<n_chunks, kInitThreads, 0, stream>>>(log->step, log->n_rows, chunk, counts);
+    OLS_LAUNCH_CHECK();
+    init_scan_kernel<<<1, 1024, 0, stream>>>(counts, n_chunks, n_init_dev);
+    OLS_LAUNCH_CHECK();
+  } else {
+    // data.py:72 — no steps column: every row is an initial state, chunk c starts at slot c * chunk
+    all_rows_prefix_kernel<<<ols_div_up(n_chunks, 256), 256, 0, stream>>>(counts, n_chunks, (uint32_t)chunk, log->n_rows,
+                                                                         n_init_dev);
+    OLS_LAUNCH_CHECK();
+  }
+  init_write_kernel<<<n_chunks, kInitThreads, 0, stream>>>(*log, *q, chunk, counts);
+  OLS_LAUNCH_CHECK();
+  return OLS_OK;
+}
+
+extern "C" int ols_shuffle_queues(const ols_queues_t* src, const ols_queues_t* dst, uint64_t seed, int32_t* perm_scratch,
+                                  void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = check_queues(src, "ols_shuffle_queues(src)");
+  if (rc) return rc;
+  rc = check_queues(dst, "ols_shuffle_queues(dst)");
+  if (rc) return rc;
+  OLS_REQUIRE(src->n_rows == dst->n_rows && src->n_buckets == dst->n_buckets && src->n_actions == dst->n_actions &&
+                  src->n_init == dst->n_init,
+              OLS_ERR_INVALID, "ols_shuffle_queues: src and dst shapes differ");
+  OLS_REQUIRE(src->records != dst->records && src->order != dst->order, OLS_ERR_INVALID,
+              "ols_shuffle_queues: dst must not alias src (except offsets)");
+  const int64_t total = src->n_rows + src->n_init;
+  OLS_REQUIRE(total < (1ll << 31), OLS_ERR_UNSUPPORTED, "ols_shuffle_queues: n_rows + n_init must be < 2^31");
+  if (total == 0) return OLS_OK;
+  OLS_REQUIRE(perm_scratch != nullptr, OLS_ERR_INVALID, "ols_shuffle_queues: null perm_scratch");
+  OLS_REQUIRE(src->n_init == 0 || (src->init_row && dst->init_row && src->init_z && dst->init_z && src->init_s && dst->init_s),
+              OLS_ERR_INVALID, "ols_shuffle_queues: null init buffers");
+  if (dst->offsets != src->offsets)
+    OLS_CUDA_CHECK(cudaMemcpyAsync(dst->offsets, src->offsets, sizeof(int32_t) * (src->n_buckets + 1),
+                                   cudaMemcpyDeviceToDevice, stream));
+  int blocks = ols_div_up(total, 256);
+  if (blocks > OLS_SM_COUNT * 8) blocks = OLS_SM_COUNT * 8;
+  iota_kernel<<<blocks, 256, 0, stream>>>(perm_scratch, total);
+  OLS_LAUNCH_CHECK();
+  shuffle_perm_kernel<<<ols_div_up(src->n_buckets + 1, 128), 128, 0, stream>>>(src->offsets, src->n_buckets, src->n_rows,
+                                                                              src->n_init, seed, perm_scratch);
+  OLS_LAUNCH_CHECK();
+  gather_queues_kernel<<<blocks, 256, 0, stream>>>(*src, *dst, perm_scratch);
+  OLS_LAUNCH_CHECK();
+  return OLS_OK;
+}

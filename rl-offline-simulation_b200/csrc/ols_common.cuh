@@ -1,0 +1,187 @@
+// Shared device/host helpers for the PSRS engine (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/ols_b200.h"
+
+#ifndef __CUDA_ARCH__
+#define OLS_HOST_ONLY 1
+#endif
+
+// ------------------------------------------------------------------------------------------ errors
+void ols_set_error(const char* fmt, ...);
+
+#define OLS_REQUIRE(cond, code, ...)      \
+  do {                                    \
+    if (!(cond)) {                        \
+      ols_set_error(__VA_ARGS__);         \
+      return (code);                      \
+    }                                     \
+  } while (0)
+
+#define OLS_CUDA_CHECK(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      ols_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return OLS_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+#define OLS_LAUNCH_CHECK()                                                                \
+  do {                                                                                    \
+    cudaError_t _e = cudaGetLastError();                                                  \
+    if (_e != cudaSuccess) {                                                              \
+      ols_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return OLS_ERR_CUDA;                                                                \
+    }                                                                                     \
+  } while (0)
+
+constexpr int OLS_SM_COUNT = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+constexpr int OLS_MAX_ACTIONS = 16;
+
+static inline int ols_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------ records
+// meta word: bits 0..7 action, bit 8 terminal
+__host__ __device__ inline uint32_t ols_pack_meta(int action, int terminal) {
+  return (uint32_t)(action & 0xff) | ((terminal ? 1u : 0u) << 8);
+}
+__host__ __device__ inline int ols_meta_action(uint32_t m) { return (int)(m & 0xff); }
+__host__ __device__ inline int ols_meta_terminal(uint32_t m) { return (int)((m >> 8) & 1); }
+
+// ------------------------------------------------------------------------------------------ Philox4x32-10
+// Salmon et al., "Parallel random numbers: as easy as 1, 2, 3" (SC'11).  Counter-based: the value
+// for (key, counter) is a pure function, so lane k of a lane group can evaluate draw (base + k).
+struct ols_u4 {
+  uint32_t x, y, z, w;
+};
+
+__host__ __device__ inline ols_u4 ols_philox4x32_10(ols_u4 ctr, uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    uint64_t p0 = (uint64_t)M0 * ctr.x;
+    uint64_t p1 = (uint64_t)M1 * ctr.z;
+    ols_u4 n;
+    n.x = (uint32_t)(p1 >> 32) ^ ctr.y ^ k0;
+    n.y = (uint32_t)p1;
+    n.z = (uint32_t)(p0 >> 32) ^ ctr.w ^ k1;
+    n.w = (uint32_t)p0;
+    ctr = n;
+    k0 += W0;
+    k1 += W1;
+  }
+  return ctr;
+}
+
+// 53-bit uniform in [0,1) from 64 random bits — the same mapping NumPy's Generator.random() uses.
+__host__ __device__ inline double ols_u64_to_unit(uint64_t v) { return (double)(v >> 11) * (1.0 / 9007199254740992.0); }
+
+// draw `d` of the stream (seed, stream_id, which): one Philox block yields two doubles
+__host__ __device__ inline double ols_philox_uniform(uint64_t seed, uint64_t stream_id, uint32_t which, uint64_t d) {
+  ols_u4 c;
+  uint64_t blk = d >> 1;
+  c.x = (uint32_t)blk;
+  c.y = (uint32_t)(blk >> 32);
+  c.z = (uint32_t)stream_id;
+  c.w = (uint32_t)(stream_id >> 32) ^ (which << 28);
+  ols_u4 o = ols_philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  uint64_t v = (d & 1) ? (((uint64_t)o.w << 32) | o.z) : (((uint64_t)o.y << 32) | o.x);
+  return ols_u64_to_unit(v);
+}
+
+// splitmix64 finaliser: hashing (seed, replica, bucket) into ring offsets
+__host__ __device__ inline uint64_t ols_mix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__host__ __device__ inline uint32_t ols_ring_start(uint64_t ring_seed, uint64_t replica, uint32_t bucket, uint32_t len) {
+  uint64_t h = ols_mix64(ols_mix64(ring_seed ^ (replica * 0xD1342543DE82EF95ull)) + bucket);
+  return (uint32_t)(((h >> 32) * (uint64_t)len) >> 32);  // multiply-shift: uniform in [0, len)
+}
+
+// ------------------------------------------------------------------------------------------ PCG64 (NumPy)
+// PCG XSL-RR 128/64 exactly as numpy.random.PCG64: state/inc are 128-bit, kept as (hi, lo).
+struct ols_u128 {
+  uint64_t hi, lo;
+};
+#define OLS_PCG_MULT_HI 0x2360ED051FC65DA4ull
+#define OLS_PCG_MULT_LO 0x4385DF649FCCF645ull
+
+__host__ __device__ inline ols_u128 ols_mul128(ols_u128 a, ols_u128 b) {
+  ols_u128 r;
+  r.lo = a.lo * b.lo;
+#ifdef __CUDA_ARCH__
+  r.hi = __umul64hi(a.lo, b.lo) + a.hi * b.lo + a.lo * b.hi;
+#else
+  r.hi = (uint64_t)(((unsigned __int128)a.lo * b.lo) >> 64) + a.hi * b.lo + a.lo * b.hi;
+#endif
+  return r;
+}
+__host__ __device__ inline ols_u128 ols_add128(ols_u128 a, ols_u128 b) {
+  ols_u128 r;
+  r.lo = a.lo + b.lo;
+  r.hi = a.hi + b.hi + (r.lo < a.lo ? 1 : 0);
+  return r;
+}
+__host__ __device__ inline ols_u128 ols_pcg_step(ols_u128 s, ols_u128 inc) {
+  ols_u128 m = {OLS_PCG_MULT_HI, OLS_PCG_MULT_LO};
+  return ols_add128(ols_mul128(s, m), inc);
+}
+__host__ __device__ inline uint64_t ols_pcg_output(ols_u128 s) {
+  uint64_t x = s.hi ^ s.lo;
+  unsigned rot = (unsigned)(s.hi >> 58);
+  return (x >> rot) | (x << ((64 - rot) & 63));
+}
+
+// SeedSequence(seed).generate_state(4, uint64) for a 64-bit seed, then the PCG64 seeding recipe
+// (numpy/random/bit_generator.pyx, _pcg64.pyx; restated in oracle/np_random.py and checked there).
+__host__ __device__ inline void ols_pcg64_seed(uint64_t seed, ols_u128* state, ols_u128* inc) {
+  const uint32_t INIT_A = 0x43B0D7E5u, MULT_A = 0x931E8875u, INIT_B = 0x8B51F9DDu, MULT_B = 0x58F38DEDu;
+  const uint32_t MIX_L = 0xCA01F9DDu, MIX_R = 0x4973F715u;
+  uint32_t ent[4] = {(uint32_t)seed, (uint32_t)(seed >> 32), 0u, 0u};
+  uint32_t pool[4];
+  uint32_t hc = INIT_A;
+  auto hashmix = [&](uint32_t v) {
+    v ^= hc;
+    hc *= MULT_A;
+    v *= hc;
+    v ^= v >> 16;
+    return v;
+  };
+  auto mix = [&](uint32_t x, uint32_t y) {
+    uint32_t r = MIX_L * x - MIX_R * y;
+    r ^= r >> 16;
+    return r;
+  };
+  for (int i = 0; i < 4; ++i) pool[i] = hashmix(ent[i]);
+  for (int s = 0; s < 4; ++s)
+    for (int d = 0; d < 4; ++d)
+      if (s != d) pool[d] = mix(pool[d], hashmix(pool[s]));
+  uint32_t hb = INIT_B;
+  uint32_t w[8];
+  for (int i = 0; i < 8; ++i) {
+    uint32_t v = pool[i & 3];
+    v ^= hb;
+    hb *= MULT_B;
+    v *= hb;
+    v ^= v >> 16;
+    w[i] = v;
+  }
+  uint64_t w0 = w[0] | ((uint64_t)w[1] << 32), w1 = w[2] | ((uint64_t)w[3] << 32);
+  uint64_t w2 = w[4] | ((uint64_t)w[5] << 32), w3 = w[6] | ((uint64_t)w[7] << 32);
+  ols_u128 initstate = {w0, w1}, initseq = {w2, w3};
+  inc->hi = (initseq.hi << 1) | (initseq.lo >> 63);
+  inc->lo = (initseq.lo << 1) | 1ull;
+  ols_u128 s = {0, 0};
+  s = ols_pcg_step(s, *inc);
+  s = ols_add128(s, initstate);
+  s = ols_pcg_step(s, *inc);
+  *state = s;
+}

@@ -1,0 +1,28 @@
+// Library-level entry points of the C ABI: version, error string, struct sizes.
+#include <stdarg.h>
+
+#include "ols_common.cuh"
+
+static thread_local char g_ols_error[512] = "";
+
+void ols_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_ols_error, sizeof(g_ols_error), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" int ols_abi_version(void) { return OLS_ABI_VERSION; }
+
+extern "C" const char* ols_last_error(void) { return g_ols_error; }
+
+extern "C" size_t ols_struct_bytes(int which) {
+  switch (which) {
+    case 0: return sizeof(ols_log_t);
+    case 1: return sizeof(ols_queues_t);
+    case 2: return sizeof(ols_replicas_t);
+    case 3: return sizeof(ols_step_out_t);
+    case 4: return sizeof(ols_run_t);
+    default: return 0;
+  }
+}

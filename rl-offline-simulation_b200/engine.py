@@ -1,0 +1,433 @@
+"""Host side of the B200 PSRS engine: device buffers (torch) + calls through the C ABI.
+
+PyTorch is plumbing here — it owns device memory and streams and nothing else; every computation on
+the path runs in the hand-written kernels of ``libols_b200.so``.  There is no CPU fallback: without a
+CUDA device (or without the built library) construction raises.
+
+Vocabulary follows the reference (offsim4rl): a *log* of transitions is *bucketed* into per-state
+*queues*; a *replica* is one independent reference ``PSRS`` object (own cursors, own uniform stream)
+over the shared, immutable bucketed log.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import secrets
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _abi as abi
+
+
+def _require_cuda(device):
+    if not torch.cuda.is_available():
+        raise RuntimeError("offsim4rl_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device(device if device is not None else "cuda")
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _as_tensor(x, device, dtype=None):
+    """numpy / torch / list -> contiguous device tensor (dtype conversion on the device)."""
+    if isinstance(x, torch.Tensor):
+        t = x.to(device, non_blocking=True)
+    else:
+        a = np.asarray(x)
+        if a.dtype == np.bool_:
+            a = a.astype(np.uint8)
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(device, non_blocking=True)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)            # float -> int truncates toward zero, like the reference's int(a) (psrs.py:54)
+    return t.contiguous()
+
+
+# ----------------------------------------------------------------------------------------------- bucketed log
+class BucketedLog:
+    """The logged transitions bucketed into per-state FIFO queues, resident in HBM.
+
+    Mirrors what ``PSRS.__init__`` + ``reset_sampler`` build (offsim4rl/evaluators/psrs.py:7-30):
+    ``offsets``/``order``/``records`` are the CSR queues, ``init_*`` the list of initial states.
+    ``base`` keeps the log-order queues; :meth:`seeded` derives the permutation ``reset_sampler(seed)``
+    would produce without re-bucketing.
+    """
+
+    def __init__(self, z, z_next, action, reward, terminal, p_log, s=None, s_next=None, steps=None,
+                 n_buckets=None, z_offset=None, device=None, keep_columns=False):
+        dev = _require_cuda(device)
+        self.device = dev
+        lib = abi.load()
+        with torch.cuda.device(dev):
+            z = _as_tensor(z, dev, torch.int32)
+            z_next = _as_tensor(z_next, dev, torch.int32)
+            n = int(z.shape[0])
+            if n >= 2 ** 31:
+                raise ValueError("a log holds at most 2^31 - 1 transitions")
+            action = _as_tensor(action, dev, torch.int32)
+            reward = _as_tensor(reward, dev, torch.float32)
+            terminal = _as_tensor(terminal, dev, torch.uint8)
+            p = _as_tensor(p_log, dev)
+            # NumPy promotion of the accept rule depends on the dtype the LOG was given in
+            self.p_source_f32 = (p.dtype == torch.float32)
+            if p.dim() != 2 or p.shape[0] != n:
+                raise ValueError("p_log must be [n_rows, n_actions]")
+            n_actions = int(p.shape[1])
+            p_log64 = None
+            if p.dtype == torch.float64:
+                p32 = p.to(torch.float32)
+                if n and not bool((p32.to(torch.float64) == p).all()):
+                    p_log64 = p                 # exact float64 distribution kept for the accept rule
+                p = p32 if p_log64 is None else p
+            elif p.dtype != torch.float32:
+                p = p.to(torch.float32)
+            s = None if s is None else _as_tensor(s, dev, torch.int32)
+            s_next = None if s_next is None else _as_tensor(s_next, dev, torch.int32)
+            steps = None if steps is None else _as_tensor(steps, dev, torch.int32)
+            for name, col in [("z_next", z_next), ("action", action), ("reward", reward), ("terminal", terminal)]:
+                if col.shape[0] != n:
+                    raise ValueError(f"column {name} has {col.shape[0]} rows, expected {n}")
+
+            if n:
+                lo = int(min(z.min().item(), z_next.min().item()))
+                hi = int(max(z.max().item(), z_next.max().item()))
+                if action.min().item() < 0 or action.max().item() >= n_actions:
+                    raise ValueError("logged action outside [0, n_actions)")
+            else:
+                lo, hi = 0, -1
+            if z_offset is None:
+                z_offset = max(0, -lo)          # encoders/heuristic.py:23-24 emits -1
+            if lo + z_offset < 0:
+                raise ValueError(f"state id {lo} is below -z_offset")
+            if n_buckets is None:
+                n_buckets = hi + z_offset + 1
+            n_buckets = max(int(n_buckets), hi + z_offset + 1, 1)
+
+            self.n_rows, self.n_actions = n, n_actions
+            self.n_buckets, self.z_offset = n_buckets, int(z_offset)
+            self.rec_bytes = int(lib.ols_record_bytes(n_actions))
+            if self.rec_bytes == 0:
+                raise ValueError(f"n_actions = {n_actions} is outside [1, 16]")
+            self.p_log64 = p_log64
+
+            log = abi.Log(n_rows=n, n_actions=n_actions, p_is_f64=int(p.dtype == torch.float64), z=_ptr(z),
+                          z_next=_ptr(z_next), s=_ptr(s), s_next=_ptr(s_next), action=_ptr(action),
+                          reward=_ptr(reward), terminal=_ptr(terminal), p_log=_ptr(p), step=_ptr(steps))
+            self.offsets = torch.empty(n_buckets + 1, dtype=torch.int32, device=dev)
+            self.order = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+            self.records = torch.empty(max(n, 1) * self.rec_bytes // 4, dtype=torch.float32, device=dev)
+            init_row = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+            init_z = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+            init_s = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+            sb = int(lib.ols_bucket_scratch_bytes(n, n_buckets))
+            if sb == 0:
+                raise ValueError(f"n_buckets = {n_buckets} is beyond what one bucketing pass supports")
+            scratch = torch.empty(sb, dtype=torch.uint8, device=dev)
+            n_init_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+            q = abi.Queues(n_rows=n, n_init=0, n_actions=n_actions, n_buckets=n_buckets, z_offset=self.z_offset,
+                           rec_bytes=self.rec_bytes, offsets=_ptr(self.offsets), order=_ptr(self.order),
+                           records=_ptr(self.records), init_row=_ptr(init_row), init_z=_ptr(init_z),
+                           init_s=_ptr(init_s), p_log64=_ptr(p_log64))
+            abi.check(lib.ols_bucket(C.byref(log), C.byref(q), _ptr(scratch), sb, _stream_ptr()))
+            abi.check(lib.ols_init_queue(C.byref(log), C.byref(q), _ptr(n_init_dev), _ptr(scratch), sb, _stream_ptr()))
+            self.n_init = int(n_init_dev.item())        # one sync: construction is not the step path
+            self.init_row = init_row[: max(self.n_init, 1)]
+            self.init_z = init_z[: max(self.n_init, 1)]
+            self.init_s = init_s[: max(self.n_init, 1)]
+            self.seed = None
+            self.base = self
+            self._columns = dict(z=z, z_next=z_next, action=action, reward=reward, terminal=terminal, p_log=p,
+                                 s=s, s_next=s_next, steps=steps) if keep_columns else None
+
+    # ------------------------------------------------------------------ views
+    def queues_struct(self) -> abi.Queues:
+        return abi.Queues(n_rows=self.n_rows, n_init=self.n_init, n_actions=self.n_actions, n_buckets=self.n_buckets,
+                          z_offset=self.z_offset, rec_bytes=self.rec_bytes, offsets=_ptr(self.offsets),
+                          order=_ptr(self.order), records=_ptr(self.records), init_row=_ptr(self.init_row),
+                          init_z=_ptr(self.init_z), init_s=_ptr(self.init_s), p_log64=_ptr(self.p_log64))
+
+    def seeded(self, seed: Optional[int]) -> "BucketedLog":
+        """Queues as ``reset_sampler(seed)`` leaves them (psrs.py:23,29-30).  ``None`` = log order."""
+        if seed is None:
+            return self.base
+        if not (0 <= int(seed) < 2 ** 64):
+            raise ValueError("seed must be in [0, 2^64)")
+        base = self.base
+        lib = abi.load()
+        out = object.__new__(BucketedLog)
+        out.__dict__.update(base.__dict__)
+        with torch.cuda.device(base.device):
+            out.order = torch.empty_like(base.order)
+            out.records = torch.empty_like(base.records)
+            out.init_row = torch.empty_like(base.init_row)
+            out.init_z = torch.empty_like(base.init_z)
+            out.init_s = torch.empty_like(base.init_s)
+            perm = torch.empty(base.n_rows + base.n_init + 1, dtype=torch.int32, device=base.device)
+            src, dst = base.queues_struct(), out.queues_struct()
+            abi.check(lib.ols_shuffle_queues(C.byref(src), C.byref(dst), C.c_uint64(int(seed)), _ptr(perm), _stream_ptr()))
+        out.seed = int(seed)
+        out.base = base
+        return out
+
+    def queue_rows(self, z: int) -> torch.Tensor:
+        """Row indices of queue ``z`` in queue order (the reference's ``env.queues[z]``)."""
+        b = z + self.z_offset
+        lo, hi = int(self.offsets[b].item()), int(self.offsets[b + 1].item())
+        return self.order[lo:hi]
+
+
+# ----------------------------------------------------------------------------------------------- replicas
+@dataclass
+class RunResult:
+    """Outputs of a fused learner run, as device tensors (reference: psrs.py:180-185, 235-239, 271)."""
+    Q: Optional[torch.Tensor]            # [R, nS, nA]
+    Gs: torch.Tensor                     # [R, ep_cap] discounted returns; row r valid up to n_returns[r]
+    lengths: torch.Tensor                # [R, ep_cap] episode lengths; row r valid up to n_lengths[r]
+    n_returns: torch.Tensor              # [R]
+    n_lengths: torch.Tensor              # [R]
+    status: torch.Tensor                 # [R]
+    accepted: torch.Tensor               # [R] lifetime accepted transitions
+    pops: torch.Tensor                   # [R] lifetime popped records
+    trace_row: Optional[torch.Tensor]    # [R, trace_cap] accepted log rows (parity tap)
+    td_error: Optional[torch.Tensor]     # [R, trace_cap]
+
+
+class BatchedPSRS:
+    """R independent PSRS simulators over one bucketed log — the batched vector form.
+
+    Scalar reference API per replica: ``reset`` = psrs.py:32-37, ``step`` = psrs.py:39-57; fused
+    drivers ``run_qlearn`` / ``run_expsarsa`` / ``run_evalmc`` = psrs.py:119-271.
+    """
+
+    def __init__(self, log: BucketedLog, n_replicas: int, rng: str = "philox", seed: Optional[int] = 0,
+                 seeds=None, u_feed=None, tie_feed=None, reject: str = "default", ring: bool = False,
+                 ring_seed: int = 0, replica_id0: int = 0, lanes: int = 4):
+        self.lib = abi.load()
+        self.log = log
+        dev = log.device
+        self.device = dev
+        R = int(n_replicas)
+        self.R = R
+        self.reject_mode = {"default": abi.REJECT_DEFAULT, "accept_all": abi.REJECT_ACCEPT_ALL}[reject]
+        self.lanes = 1 if self.reject_mode == abi.REJECT_ACCEPT_ALL else int(lanes)
+        self.rng_mode = {"feed": abi.RNG_FEED, "pcg64": abi.RNG_PCG64, "philox": abi.RNG_PHILOX}[rng]
+        if seed is None:
+            seed = secrets.randbits(63)           # psrs.py:13 — default_rng(None) draws OS entropy
+        self.seed = int(seed)
+        with torch.cuda.device(dev):
+            z32 = lambda: torch.zeros(max(R, 1), dtype=torch.int32, device=dev)
+            z64 = lambda: torch.zeros(max(R, 1), dtype=torch.int64, device=dev)
+            self.cursor = torch.empty((max(R, 1), log.n_buckets), dtype=torch.int32, device=dev)
+            self.init_cursor, self.cur_z, self.cur_s, self.status = z32(), z32(), z32(), z32()
+            self.draws, self.ties, self.pops, self.accepted = z64(), z64(), z64(), z64()
+            self.ep_index, self.ep_len_count, self.ep_t, self.ep_open = z32(), z32(), z32(), z32()
+            self.ep_G = torch.zeros(max(R, 1), dtype=torch.float64, device=dev)
+            self.ep_disc = torch.ones(max(R, 1), dtype=torch.float64, device=dev)
+            self.pcg_state = (torch.zeros((max(R, 1), 4), dtype=torch.int64, device=dev)
+                              if self.rng_mode == abi.RNG_PCG64 else None)
+            self.u_feed = None if u_feed is None else _as_tensor(u_feed, dev, torch.float64)
+            self.tie_feed = None if tie_feed is None else _as_tensor(tie_feed, dev, torch.float64)
+            if self.rng_mode == abi.RNG_FEED and self.u_feed is None:
+                raise ValueError("rng='feed' needs u_feed")
+            self.tie_mode = abi.RNG_FEED if self.tie_feed is not None else abi.RNG_PHILOX
+            self._seeds = None if seeds is None else _as_tensor(np.asarray(seeds, dtype=np.uint64).view(np.int64), dev)
+            self.ring, self.ring_seed, self.replica_id0 = bool(ring), int(ring_seed), int(replica_id0)
+            # step outputs
+            self.out_row, self.out_action, self.out_s_next, self.out_z_from = z32(), z32(), z32(), z32()
+            self.out_reward = torch.zeros(max(R, 1), dtype=torch.float32, device=dev)
+            self.out_terminal = torch.zeros(max(R, 1), dtype=torch.uint8, device=dev)
+        self.restart()
+
+    # ------------------------------------------------------------------ structs
+    def _feed_shape(self, t):
+        if t is None:
+            return 0, 0
+        if t.dim() == 1:
+            return int(t.shape[0]), 0
+        return int(t.shape[1]), int(t.stride(0))
+
+    def replicas_struct(self) -> abi.Replicas:
+        ulen, ustride = self._feed_shape(self.u_feed)
+        tlen, tstride = self._feed_shape(self.tie_feed)
+        return abi.Replicas(
+            n_replicas=self.R, replica_id0=self.replica_id0, cursor=_ptr(self.cursor), init_cursor=_ptr(self.init_cursor),
+            cur_z=_ptr(self.cur_z), cur_s=_ptr(self.cur_s), status=_ptr(self.status), draws=_ptr(self.draws),
+            ties=_ptr(self.ties), pops=_ptr(self.pops), accepted=_ptr(self.accepted), ep_index=_ptr(self.ep_index),
+            ep_len_count=_ptr(self.ep_len_count), ep_t=_ptr(self.ep_t), ep_open=_ptr(self.ep_open), ep_G=_ptr(self.ep_G),
+            ep_disc=_ptr(self.ep_disc), rng_mode=self.rng_mode, tie_mode=self.tie_mode, seed=self.seed,
+            pcg_state=_ptr(self.pcg_state), u_feed=_ptr(self.u_feed), u_feed_len=ulen, u_stride=ustride,
+            tie_feed=_ptr(self.tie_feed), tie_feed_len=tlen, tie_stride=tstride, ring_mode=int(self.ring), _pad=0,
+            ring_seed=self.ring_seed)
+
+    # ------------------------------------------------------------------ lifecycle
+    def restart(self, log: Optional[BucketedLog] = None):
+        """Fresh simulators (cursors 0, counters 0, generators re-seeded) — ``reset_sampler`` for the
+        replica side; pass ``log`` to switch to another queue order (``log.seeded(k)``)."""
+        if log is not None:
+            if log.n_buckets != self.log.n_buckets or log.n_actions != self.log.n_actions:
+                raise ValueError("restart(log): shape differs from the log this block was built for")
+            self.log = log
+        with torch.cuda.device(self.device):
+            q, r = self.log.queues_struct(), self.replicas_struct()
+            abi.check(self.lib.ols_replicas_init(C.byref(q), C.byref(r), _ptr(self._seeds), _stream_ptr()))
+
+    def reset(self, mask=None):
+        """psrs.py:32-37 for every replica (or those with ``mask``): returns ``(s, status)`` tensors."""
+        with torch.cuda.device(self.device):
+            m = None if mask is None else _as_tensor(mask, self.device, torch.uint8)
+            q, r = self.log.queues_struct(), self.replicas_struct()
+            abi.check(self.lib.ols_reset(C.byref(q), C.byref(r), _ptr(m), _stream_ptr()))
+        return self.cur_s, self.status
+
+    def step(self, p_new, mask=None, compute: Optional[str] = None):
+        """psrs.py:39-57 for every RUNNING replica.  ``p_new``: [nA] shared or [R, nA] per replica.
+
+        Returns a dict of device tensors: ``row`` (accepted log row, -1 if none), ``action``, ``reward``,
+        ``terminal``, ``s_next``, ``z_from``, ``status``.
+        """
+        with torch.cuda.device(self.device):
+            p = _as_tensor(p_new, self.device)
+            if p.dtype not in (torch.float32, torch.float64):
+                p = p.to(torch.float64)
+            if p.shape[-1] != self.log.n_actions:
+                raise ValueError("p_new must have n_actions entries per row")
+            stride = 0 if p.dim() == 1 else int(p.stride(0))
+            if p.dim() == 2 and p.shape[0] != self.R:
+                raise ValueError("p_new must be [n_actions] or [n_replicas, n_actions]")
+            if compute is None:
+                # NumPy promotion: float32 arithmetic only if BOTH distributions are float32
+                compute = "f32" if (p.dtype == torch.float32 and self.log.p_source_f32) else "f64"
+            cm = abi.COMPUTE_F32 if compute == "f32" else abi.COMPUTE_F64
+            m = None if mask is None else _as_tensor(mask, self.device, torch.uint8)
+            q, r = self.log.queues_struct(), self.replicas_struct()
+            out = abi.StepOut(row=_ptr(self.out_row), action=_ptr(self.out_action), reward=_ptr(self.out_reward),
+                              terminal=_ptr(self.out_terminal), s_next=_ptr(self.out_s_next), z_from=_ptr(self.out_z_from))
+            abi.check(self.lib.ols_step(C.byref(q), C.byref(r), _ptr(m), _ptr(p), int(p.dtype == torch.float64), stride,
+                                        self.reject_mode, cm, self.lanes, C.byref(out), _stream_ptr()))
+        return dict(row=self.out_row, action=self.out_action, reward=self.out_reward, terminal=self.out_terminal,
+                    s_next=self.out_s_next, z_from=self.out_z_from, status=self.status)
+
+    # ------------------------------------------------------------------ fused drivers
+    def _schedule(self, x, n_episodes):
+        if callable(x):
+            vals = [float(x(e)) for e in range(n_episodes + 1)]
+        elif np.ndim(x) == 0:
+            vals = [float(x)] * (n_episodes + 1)
+        else:
+            vals = [float(v) for v in x]
+            if len(vals) < n_episodes:
+                raise ValueError("schedule shorter than n_episodes")
+            vals = vals + [vals[-1]] * (n_episodes + 1 - len(vals))
+        return torch.tensor(vals, dtype=torch.float64, device=self.device)
+
+    def _run(self, agent, n_states, n_episodes, gamma, alpha=None, epsilon=None, pi=None, Q=None,
+             q_dtype=torch.float32, max_steps=0, trace_cap=0, compute=None, ep_cap=None, outputs=None):
+        dev = self.device
+        R, nA = self.R, self.log.n_actions
+        with torch.cuda.device(dev):
+            ep_cap = int(ep_cap or (n_episodes + 1))
+            if outputs is None:
+                Gs = torch.zeros((max(R, 1), ep_cap), dtype=torch.float64, device=dev)
+                lengths = torch.zeros((max(R, 1), ep_cap), dtype=torch.int32, device=dev)
+                trace_row = torch.full((max(R, 1), trace_cap), -1, dtype=torch.int32, device=dev) if trace_cap else None
+                td = torch.zeros((max(R, 1), trace_cap), dtype=torch.float64, device=dev) if (trace_cap and agent == abi.AGENT_QLEARN) else None
+                if agent != abi.AGENT_FIXED_PI and Q is None:
+                    Q = torch.zeros((max(R, 1), n_states, nA), dtype=q_dtype, device=dev)
+            else:
+                Gs, lengths, trace_row, td, Q = outputs.Gs, outputs.lengths, outputs.trace_row, outputs.td_error, outputs.Q
+            pi_t = None
+            pi_is_f64 = 0
+            if pi is not None:
+                pi_t = _as_tensor(pi, dev)
+                if pi_t.dtype not in (torch.float32, torch.float64):
+                    pi_t = pi_t.to(torch.float64)
+                pi_is_f64 = int(pi_t.dtype == torch.float64)
+                if tuple(pi_t.shape) != (n_states, nA):
+                    raise ValueError("pi must be [n_states, n_actions]")
+            if compute is None:
+                compute = "f32" if (pi_t is not None and not pi_is_f64 and self.log.p_source_f32) else "f64"
+            a_t = None if alpha is None else self._schedule(alpha, n_episodes)
+            e_t = None if epsilon is None else self._schedule(epsilon, n_episodes)
+            cfg = abi.Run(agent=agent, n_states=n_states, q_is_f64=int(Q is not None and Q.dtype == torch.float64),
+                          pi_is_f64=pi_is_f64, reject_mode=self.reject_mode,
+                          compute_mode=abi.COMPUTE_F32 if compute == "f32" else abi.COMPUTE_F64, lanes=self.lanes,
+                          n_episodes=int(n_episodes), ep_cap=ep_cap, stage_smem=0, max_steps=int(max_steps),
+                          gamma=float(gamma), alpha=_ptr(a_t), epsilon=_ptr(e_t), pi=_ptr(pi_t), Q=_ptr(Q), Gs=_ptr(Gs),
+                          lengths=_ptr(lengths), trace_row=_ptr(trace_row), td_error=_ptr(td), trace_cap=int(trace_cap))
+            q, r = self.log.queues_struct(), self.replicas_struct()
+            abi.check(self.lib.ols_run(C.byref(q), C.byref(r), C.byref(cfg), _stream_ptr()))
+        return RunResult(Q=Q, Gs=Gs, lengths=lengths, n_returns=self.ep_index, n_lengths=self.ep_len_count,
+                         status=self.status, accepted=self.accepted, pops=self.pops, trace_row=trace_row, td_error=td)
+
+    def run_qlearn(self, n_states, n_episodes, gamma, alpha=0.1, epsilon=1.0, Q=None, q_dtype=torch.float32,
+                   max_steps=0, trace_cap=0, ep_cap=None, outputs=None) -> RunResult:
+        """psrs.py:119-185 with ``behavior_policy = epsilon_greedy_policy`` (tabular.py:24-32), fused."""
+        return self._run(abi.AGENT_QLEARN, n_states, n_episodes, gamma, alpha=alpha, epsilon=epsilon, Q=Q,
+                         q_dtype=q_dtype, max_steps=max_steps, trace_cap=trace_cap, ep_cap=ep_cap, outputs=outputs)
+
+    def run_expsarsa(self, n_states, n_episodes, pi, gamma, alpha=0.1, Q=None, q_dtype=torch.float32, max_steps=0,
+                     trace_cap=0, compute=None, ep_cap=None, outputs=None) -> RunResult:
+        """psrs.py:187-239, fused."""
+        return self._run(abi.AGENT_EXPSARSA, n_states, n_episodes, gamma, alpha=alpha, pi=pi, Q=Q, q_dtype=q_dtype,
+                         max_steps=max_steps, trace_cap=trace_cap, compute=compute, ep_cap=ep_cap, outputs=outputs)
+
+    def run_evalmc(self, n_states, n_episodes, pi, gamma, max_steps=0, trace_cap=0, compute=None, ep_cap=None,
+                   outputs=None) -> RunResult:
+        """psrs.py:241-271, fused."""
+        return self._run(abi.AGENT_FIXED_PI, n_states, n_episodes, gamma, pi=pi, max_steps=max_steps,
+                         trace_cap=trace_cap, compute=compute, ep_cap=ep_cap, outputs=outputs)
+
+    # ------------------------------------------------------------------ evaluators
+    def learning_curve(self, result: RunResult, n_episodes: int, all_reduce: bool = True):
+        """Per-episode ``(sum, sumsq, count)`` of the returns over replicas — over ALL ranks when
+        ``torch.distributed`` is initialised (one small all-reduce, the job's only collective)."""
+        dev = self.device
+        with torch.cuda.device(dev):
+            out = torch.zeros((3, max(n_episodes, 1)), dtype=torch.float64, device=dev)
+            sb = int(self.lib.ols_curve_scratch_bytes(self.R, n_episodes))
+            scratch = torch.empty(max(sb, 8), dtype=torch.uint8, device=dev)
+            abi.check(self.lib.ols_reduce_curves(_ptr(result.Gs), _ptr(result.n_returns), self.R, int(result.Gs.shape[1]),
+                                                 int(n_episodes), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(scratch),
+                                                 sb, _stream_ptr()))
+            if all_reduce and torch.distributed.is_available() and torch.distributed.is_initialized():
+                torch.distributed.all_reduce(out, op=torch.distributed.ReduceOp.SUM)
+        return out[0, :n_episodes], out[1, :n_episodes], out[2, :n_episodes]
+
+    def replica_totals(self, result: RunResult):
+        """Per-replica total return and total simulated length (segmented reduction over its episodes)."""
+        dev = self.device
+        with torch.cuda.device(dev):
+            ret = torch.zeros(max(self.R, 1), dtype=torch.float64, device=dev)
+            ln = torch.zeros(max(self.R, 1), dtype=torch.int64, device=dev)
+            abi.check(self.lib.ols_replica_totals(_ptr(result.Gs), _ptr(result.lengths), _ptr(result.n_returns),
+                                                  _ptr(result.n_lengths), self.R, int(result.Gs.shape[1]), _ptr(ret),
+                                                  _ptr(ln), _stream_ptr()))
+        return ret, ln
+
+
+# ----------------------------------------------------------------------------------------------- synthetic data
+def synth_columns(n_rows, n_states, pb_state, seed=0, p_done=1.0 / 50, device=None):
+    """Device-generated synthetic log of the benchmark shape: returns the column dict
+    ``BucketedLog`` takes.  ``pb_state`` is the per-state behaviour policy [n_states, n_actions]."""
+    dev = _require_cuda(device)
+    lib = abi.load()
+    with torch.cuda.device(dev):
+        pb = _as_tensor(pb_state, dev, torch.float32)
+        nA = int(pb.shape[1])
+        cols = dict(
+            z=torch.empty(n_rows, dtype=torch.int32, device=dev), z_next=torch.empty(n_rows, dtype=torch.int32, device=dev),
+            action=torch.empty(n_rows, dtype=torch.int32, device=dev), reward=torch.empty(n_rows, dtype=torch.float32, device=dev),
+            terminal=torch.empty(n_rows, dtype=torch.uint8, device=dev),
+            p_log=torch.empty((n_rows, nA), dtype=torch.float32, device=dev),
+            steps=torch.empty(n_rows, dtype=torch.int32, device=dev))
+        log = abi.Log(n_rows=n_rows, n_actions=nA, p_is_f64=0, z=_ptr(cols["z"]), z_next=_ptr(cols["z_next"]), s=_ptr(None),
+                      s_next=_ptr(None), action=_ptr(cols["action"]), reward=_ptr(cols["reward"]),
+                      terminal=_ptr(cols["terminal"]), p_log=_ptr(cols["p_log"]), step=_ptr(cols["steps"]))
+        abi.check(lib.ols_synth_log(C.byref(log), _ptr(pb), int(n_states), C.c_uint64(int(seed)), float(p_done), _stream_ptr()))
+    return cols

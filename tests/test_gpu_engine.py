@@ -1,0 +1,388 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden vectors."""
+import numpy as np
+import pytest
+
+from oracle import psrs_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ob():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import offsim4rl_b200
+    return offsim4rl_b200
+
+
+def make_log(seed, N, nS, nA, ep_len=8, p_dtype=np.float32, skew=False, neg_key=False):
+    rng = np.random.default_rng(seed)
+    if skew:
+        w = 1.0 / np.arange(1, nS + 1) ** 1.1
+        z = rng.choice(nS, size=N, p=w / w.sum())
+    else:
+        z = rng.integers(0, nS, size=N)
+    zn = rng.integers(0, nS, size=N)
+    if neg_key:
+        z = z - 1
+        zn = zn - 1
+    pb = rng.dirichlet(np.ones(nA), size=nS + 1).clip(0.05)
+    pb /= pb.sum(1, keepdims=True)
+    p_log = pb[z].astype(p_dtype)
+    u = rng.random(N)
+    a = (u[:, None] > np.cumsum(pb[z], axis=1)).sum(1).clip(0, nA - 1)
+    r = rng.normal(size=N).astype(np.float32)
+    done = rng.random(N) < 1.0 / ep_len
+    t = np.zeros(N, dtype=np.int64)
+    start = np.r_[True, done[:-1]]
+    idx = np.arange(N)
+    t = idx - np.maximum.accumulate(np.where(start, idx, 0))
+    return dict(z=z.astype(np.int64), z_next=zn.astype(np.int64), a=a.astype(np.int64), r=r, done=done, t=t, p_log=p_log)
+
+
+def device_log(ob, g, **kw):
+    kw.setdefault("steps", g["t"])
+    return ob.BucketedLog(z=g["z"], z_next=g["z_next"], action=g["a"], reward=g["r"], terminal=g["done"],
+                          p_log=g["p_log"], **kw)
+
+
+def oracle_env(g, **kw):
+    kw.setdefault("steps", g["t"])
+    return O.OraclePSRS(z=g["z"], z_next=g["z_next"], s=g["z"], s_next=g["z_next"], action=g["a"], reward=g["r"],
+                        terminal=g["done"], p_log=g["p_log"], **kw)
+
+
+# --------------------------------------------------------------------------------------- bucketing
+@pytest.mark.parametrize("N,nS,nA,kw", [
+    (0, 3, 2, {}), (1, 1, 2, {}), (33, 4, 4, {}), (5000, 25, 5, {}), (100000, 1000, 4, {}),
+    (300000, 10000, 4, {}), (200000, 162, 2, dict(neg_key=True)), (150000, 50, 4, dict(skew=True)),
+    (70000, 7, 9, {}), (40000, 3, 16, {}),
+])
+def test_bucketing_is_stable_counting_sort(ob, N, nS, nA, kw):
+    g = make_log(1, N, nS, nA, **kw)
+    z_offset = 1 if kw.get("neg_key") else 0
+    log = device_log(ob, g, n_buckets=nS + z_offset, z_offset=z_offset)
+    offsets, order = O.bucket(g["z"], nS + z_offset, z_offset)
+    assert np.array_equal(log.offsets.cpu().numpy(), offsets)
+    assert np.array_equal(log.order.cpu().numpy()[:N], order)                       # psrs.py:26
+    init = O.init_rows(g["t"], N)
+    assert log.n_init == init.size
+    assert np.array_equal(log.init_row.cpu().numpy()[:init.size], init)              # psrs.py:22
+    assert np.array_equal(log.init_z.cpu().numpy()[:init.size], g["z"][init])
+    # packed records carry the row's fields in queue order
+    if N:
+        nv = (nA + 3) // 4
+        rec = log.records.cpu().numpy().reshape(N, 4 * nv + 4)
+        assert np.array_equal(rec[:, :nA], g["p_log"][order])
+        assert np.all(rec[:, nA:4 * nv] == 0)
+        assert np.array_equal(rec[:, 4 * nv], g["r"][order])
+        tail = rec[:, 4 * nv + 1:].copy().view(np.int32)
+        assert np.array_equal(tail[:, 0], g["z_next"][order])
+        assert np.array_equal(tail[:, 1], g["z_next"][order])
+        assert np.array_equal(tail[:, 2] & 0xFF, g["a"][order])
+        assert np.array_equal((tail[:, 2] >> 8) & 1, g["done"][order].astype(np.int32))
+
+
+def test_no_steps_column_makes_every_row_initial(ob):
+    g = make_log(2, 9000, 12, 3)
+    log = device_log(ob, g, steps=None, n_buckets=12)
+    assert log.n_init == 9000
+    assert np.array_equal(log.init_row.cpu().numpy(), np.arange(9000))               # data.py:72
+
+
+@pytest.mark.parametrize("seed", [0, 3, 98052, 2**40 + 17])
+def test_seeded_shuffle_replays_numpy(ob, seed):
+    g = make_log(3, 6000, 30, 4, skew=True)
+    log = device_log(ob, g, n_buckets=30)
+    sh = log.seeded(seed)
+    order, init = O.apply_seed(*O.bucket(g["z"], 30), O.init_rows(g["t"], 6000), seed)
+    assert np.array_equal(sh.order.cpu().numpy(), order)                             # psrs.py:29-30
+    assert np.array_equal(sh.init_row.cpu().numpy()[:init.size], init)               # psrs.py:23
+    assert np.array_equal(sh.init_z.cpu().numpy()[:init.size], g["z"][init])
+    rec = sh.records.cpu().numpy().reshape(6000, 8)
+    assert np.array_equal(rec[:, :4], g["p_log"][order])
+    # the log-order base is untouched
+    assert np.array_equal(log.order.cpu().numpy(), O.bucket(g["z"], 30)[1])
+
+
+def test_seeded_queues_match_reference_golden(ob, golden):
+    g = golden("seeded_walk")
+    log = ob.BucketedLog(z=g["z"], z_next=g["z_next"], action=g["a"], reward=g["r"], terminal=g["done"],
+                         p_log=g["p_log"], steps=g["t"], n_buckets=9)
+    for seed in [0, 3, 98052]:
+        sh = log.seeded(seed)
+        assert np.array_equal(sh.offsets.cpu().numpy(), g[f"offsets_{seed}"])
+        assert np.array_equal(sh.order.cpu().numpy(), g[f"order_{seed}"])
+        n0 = sh.n_init
+        assert np.array_equal(sh.init_z.cpu().numpy()[:n0], g[f"init_zs_{seed}"][:, 0])
+
+
+# --------------------------------------------------------------------------------------- step API
+@pytest.mark.parametrize("lanes", [1, 2, 4, 8, 32])
+def test_batched_step_matches_oracle_under_fed_uniforms(ob, lanes):
+    import torch
+    g = make_log(4, 8000, 15, 4)
+    R = 37
+    rng = np.random.default_rng(9)
+    U = rng.random((R, 40000))
+    log = device_log(ob, g, n_buckets=15)
+    sim = ob.BatchedPSRS(log, R, rng="feed", u_feed=U, lanes=lanes)
+    envs = [oracle_env(g, n_buckets=15, uniforms=O.FeedUniforms(U[r])) for r in range(R)]
+    pis = rng.dirichlet(np.ones(4), size=R)
+    s_dev, st = sim.reset()
+    s_or = [e.reset() for e in envs]
+    assert np.array_equal(s_dev.cpu().numpy(), np.array(s_or))
+    for it in range(120):
+        out = sim.step(pis)
+        rows = out["row"].cpu().numpy()
+        status = out["status"].cpu().numpy()
+        need_reset = np.zeros(R, dtype=np.uint8)
+        for r, e in enumerate(envs):
+            if e.status not in (O.RUNNING, O.QUEUE_EMPTY):
+                continue
+            row = e.step(pis[r])
+            if row is None:
+                assert rows[r] == -1 and status[r] == O.QUEUE_EMPTY
+            else:
+                assert rows[r] == row, (it, r)
+                if g["done"][row]:
+                    need_reset[r] = 1
+                    e.reset()
+        assert np.array_equal(sim.draws.cpu().numpy(), [e.uniforms.k for e in envs])
+        assert np.array_equal(sim.pops.cpu().numpy(), [e.pops for e in envs])
+        if need_reset.any():
+            sim.reset(mask=need_reset)
+        assert np.array_equal(sim.cur_s.cpu().numpy()[[e.status == O.RUNNING for e in envs]],
+                              [int(e.cur_s) for e in envs if e.status == O.RUNNING])
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("seed", [0, 3, 98052])
+def test_pcg64_walk_reproduces_reference_run_bit_for_bit(ob, golden, seed):
+    """reset_sampler(seed) + the reference's OWN default_rng(seed) uniforms, no injection."""
+    g = golden("seeded_walk")
+    log = ob.BucketedLog(z=g["z"], z_next=g["z_next"], action=g["a"], reward=g["r"], terminal=g["done"],
+                         p_log=g["p_log"], steps=g["t"], n_buckets=9).seeded(seed)
+    sim = ob.BatchedPSRS(log, 3, rng="pcg64", seed=seed, lanes=4)      # three identical replicas
+    trace, resets = [], []
+    s, _ = sim.reset()
+    resets.append(int(s[0]))
+    while True:
+        out = sim.step(g["p_new"])
+        row = int(out["row"][1])
+        assert int(out["row"][0]) == row == int(out["row"][2])
+        if row < 0:
+            break
+        trace.append(row)
+        if g["done"][row]:
+            s, st = sim.reset()
+            if int(st[0]) == O.INIT_EMPTY:
+                resets.append(-1)
+                break
+            resets.append(int(s[0]))
+    assert np.array_equal(trace, g[f"trace_{seed}"])
+    assert np.array_equal(resets, g[f"resets_{seed}"])
+    assert int(sim.pops[0]) == int(g[f"pops_{seed}"])
+
+
+# --------------------------------------------------------------------------------------- fused drivers vs golden
+DRIVER_CASES = ["drivers_f64", "drivers_f32", "drivers_p64_a5", "drivers_edge"]
+
+
+def _golden_log(ob, g):
+    steps = g["t"] if bool(g["with_t"]) else None
+    nS = g["pi"].shape[0]
+    return ob.BucketedLog(z=g["z"], z_next=g["z_next"], action=g["a"], reward=g["r"], terminal=g["done"],
+                          p_log=g["p_log"], steps=steps, n_buckets=nS).seeded(int(g["sampler_seed"]))
+
+
+@pytest.mark.parametrize("case", DRIVER_CASES)
+@pytest.mark.parametrize("tag", ["const", "sched"])
+@pytest.mark.parametrize("lanes", [1, 4, 32])
+def test_fused_qlearn_matches_reference(ob, golden, case, tag, lanes):
+    import torch
+    g = golden(case)
+    nS, nA = g["pi"].shape
+    N = g["z"].shape[0]
+    sim = ob.BatchedPSRS(_golden_log(ob, g), 2, rng="feed", u_feed=g["U"], tie_feed=g["T"], lanes=lanes)
+    eps, alpha = (0.2, 0.1) if tag == "const" else (g["ql_sched_eps"], g["ql_sched_alpha"])
+    res = sim.run_qlearn(nS, 25, gamma=0.9, alpha=alpha, epsilon=eps, q_dtype=torch.float64, trace_cap=N)
+    n = g[f"ql_{tag}_trace"].size
+    for r in range(2):
+        assert int(res.accepted[r]) == n
+        assert np.array_equal(res.trace_row[r, :n].cpu().numpy(), g[f"ql_{tag}_trace"])      # bit-exact accepted rows
+        assert int(sim.draws[r]) == int(g[f"ql_{tag}_draws"])
+        assert int(sim.ties[r]) == int(g[f"ql_{tag}_ties"])
+        assert np.array_equal(res.Q[r].cpu().numpy(), g[f"ql_{tag}_Q"])                      # same IEEE op order
+        assert np.array_equal(res.td_error[r, :n].cpu().numpy(), g[f"ql_{tag}_TD"])
+        ne = int(res.n_returns[r])
+        assert ne == g[f"ql_{tag}_Gs"].size
+        np.testing.assert_allclose(res.Gs[r, :ne].cpu().numpy(), g[f"ql_{tag}_Gs"], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("case", DRIVER_CASES)
+def test_fused_qlearn_fp32_q_within_tolerance(ob, golden, case):
+    import torch
+    g = golden(case)
+    nS, nA = g["pi"].shape
+    N = g["z"].shape[0]
+    sim = ob.BatchedPSRS(_golden_log(ob, g), 1, rng="feed", u_feed=g["U"], tie_feed=g["T"], lanes=4)
+    res = sim.run_qlearn(nS, 25, gamma=0.9, alpha=0.1, epsilon=0.2, q_dtype=torch.float32, trace_cap=N)
+    ref_trace = g["ql_const_trace"]
+    got = res.trace_row[0, :int(res.accepted[0])].cpu().numpy()
+    # FP32 Q may flip a near-tie argmax and fork the trajectory: compare up to the first fork
+    m = min(got.size, ref_trace.size)
+    same = np.nonzero(got[:m] != ref_trace[:m])[0]
+    fork = same[0] if same.size else m
+    assert fork >= 0.5 * ref_trace.size
+    if fork == ref_trace.size == got.size:
+        np.testing.assert_allclose(res.Q[0].cpu().numpy(), g["ql_const_Q"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("case", DRIVER_CASES)
+def test_fused_expsarsa_matches_reference(ob, golden, case):
+    import torch
+    g = golden(case)
+    nS, nA = g["pi"].shape
+    N = g["z"].shape[0]
+    sim = ob.BatchedPSRS(_golden_log(ob, g), 2, rng="feed", u_feed=g["U"], lanes=4)
+    res = sim.run_expsarsa(nS, 25, pi=g["pi"], gamma=0.95, alpha=0.2, q_dtype=torch.float64, trace_cap=N)
+    n = g["es_trace"].size
+    assert int(res.accepted[1]) == n
+    assert np.array_equal(res.trace_row[1, :n].cpu().numpy(), g["es_trace"])
+    assert int(sim.draws[1]) == int(g["es_draws"])
+    np.testing.assert_allclose(res.Q[1].cpu().numpy(), g["es_Q"], rtol=1e-12, atol=1e-14)
+    ne = int(res.n_returns[1])
+    assert ne == g["es_Gs"].size
+    np.testing.assert_allclose(res.Gs[1, :ne].cpu().numpy(), g["es_Gs"], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("case", DRIVER_CASES + ["drivers_float_a"])
+@pytest.mark.parametrize("lanes", [1, 8])
+def test_fused_evalmc_matches_reference(ob, golden, case, lanes):
+    g = golden(case)
+    nS, nA = g["pi"].shape
+    N = g["z"].shape[0]
+    sim = ob.BatchedPSRS(_golden_log(ob, g), 2, rng="feed", u_feed=g["U"], lanes=lanes)
+    res = sim.run_evalmc(nS, 40, pi=g["pi"], gamma=0.97, trace_cap=N)
+    n = g["mc_trace"].size
+    assert int(res.accepted[0]) == n
+    assert np.array_equal(res.trace_row[0, :n].cpu().numpy(), g["mc_trace"])
+    assert int(sim.draws[0]) == int(g["mc_draws"])
+    ne, nl = int(res.n_returns[0]), int(res.n_lengths[0])
+    assert ne == g["mc_Gs"].size and nl == g["mc_lengths"].size                   # psrs.py:265-269
+    assert np.array_equal(res.lengths[0, :nl].cpu().numpy(), g["mc_lengths"])
+    np.testing.assert_allclose(res.Gs[0, :ne].cpu().numpy(), g["mc_Gs"], rtol=1e-5, atol=1e-5)
+
+
+def test_chunked_runs_equal_one_run(ob):
+    """max_steps budgets make ols_run resumable; chunking must be invisible."""
+    import torch
+    g = make_log(7, 20000, 20, 4)
+    R = 50
+    rng = np.random.default_rng(1)
+    U, T = rng.random((R, 60000)), rng.random((R, 60000))
+    log = device_log(ob, g, n_buckets=20)
+    one = ob.BatchedPSRS(log, R, rng="feed", u_feed=U, tie_feed=T, lanes=4)
+    ra = one.run_qlearn(20, 40, gamma=0.95, alpha=0.1, epsilon=0.1, q_dtype=torch.float64, trace_cap=20000)
+    two = ob.BatchedPSRS(log, R, rng="feed", u_feed=U, tie_feed=T, lanes=4)
+    rb = None
+    for _ in range(200):
+        rb = two.run_qlearn(20, 40, gamma=0.95, alpha=0.1, epsilon=0.1, q_dtype=torch.float64, trace_cap=20000,
+                            max_steps=17, outputs=rb)
+        if bool((rb.status != O.RUNNING).all()):
+            break
+    assert torch.equal(ra.status, rb.status) and torch.equal(ra.accepted, rb.accepted)
+    assert torch.equal(ra.trace_row, rb.trace_row) and torch.equal(ra.Q, rb.Q)
+    assert torch.equal(ra.Gs, rb.Gs) and torch.equal(ra.lengths, rb.lengths)
+    # and it matches the oracle replica by replica
+    for r in (0, R - 1):
+        env = oracle_env(g, n_buckets=20, uniforms=O.FeedUniforms(U[r]))
+        Q, info = O.qlearn(env, 40, gamma=0.95, alpha=0.1, epsilon=0.1, ties=O.FeedTies(T[r]), nS=20, nA=4)
+        n = info["trace"].size
+        assert np.array_equal(ra.trace_row[r, :n].cpu().numpy(), info["trace"])
+        assert np.array_equal(ra.Q[r].cpu().numpy(), Q)
+
+
+def test_statuses_and_edge_cases(ob):
+    import torch
+    # state 2 is reachable but never a from-state -> KeyError in the reference -> NO_QUEUE here
+    z = np.array([0, 0, 1, 1]); zn = np.array([1, 2, 0, 0])
+    log = ob.BucketedLog(z=z, z_next=zn, action=np.zeros(4), reward=np.ones(4), terminal=np.zeros(4),
+                         p_log=np.full((4, 2), 0.5, dtype=np.float32), steps=np.array([0, 1, 1, 1]), n_buckets=3)
+    sim = ob.BatchedPSRS(log, 1, rng="philox", seed=1, reject="accept_all")
+    s, st = sim.reset()
+    assert int(st[0]) == O.RUNNING and int(s[0]) == 0
+    out = sim.step(np.array([0.5, 0.5]))
+    assert int(out["row"][0]) == 0 and int(out["s_next"][0]) == 1
+    out = sim.step(np.array([0.5, 0.5]))
+    assert int(out["row"][0]) == 2
+    out = sim.step(np.array([0.5, 0.5]))
+    assert int(out["row"][0]) == 1 and int(out["s_next"][0]) == 2
+    out = sim.step(np.array([0.5, 0.5]))
+    assert int(out["row"][0]) == -1 and int(out["status"][0]) == O.NO_QUEUE
+    s, st = sim.reset()
+    assert int(st[0]) == O.INIT_EMPTY                                               # psrs.py:33-35
+    assert int(sim.draws[0]) == 0                                                   # accept-all draws nothing
+    # empty log
+    empty = ob.BucketedLog(z=np.zeros(0), z_next=np.zeros(0), action=np.zeros(0), reward=np.zeros(0),
+                           terminal=np.zeros(0), p_log=np.zeros((0, 2), dtype=np.float32), n_buckets=2)
+    sim = ob.BatchedPSRS(empty, 4)
+    s, st = sim.reset()
+    assert (st == O.INIT_EMPTY).all()
+    torch.cuda.synchronize()
+
+
+# --------------------------------------------------------------------------------------- encoders
+def test_cartpole_box_encoder_bit_exact(ob, golden):
+    from offsim4rl_b200.encoders.heuristic import CartpoleBoxEncoder
+    g = golden("encoders")
+    enc = CartpoleBoxEncoder()
+    assert np.array_equal(enc.encode(g["box_obs32"]), g["box_ids32"])
+    assert np.array_equal(enc.encode(g["box_obs64"]), g["box_ids64"])
+
+
+@pytest.mark.parametrize("tag", ["mlp_grid", "mlp_cart", "mlp_wide"])
+def test_mlp_encoder_matches_fma_oracle_bit_exact(ob, golden, tag):
+    from offsim4rl_b200.encoders.homer import HOMEREncoder
+    g = golden("encoders")
+    x, W1, b1, W2, b2 = (g[f"{tag}_{k}"] for k in ["x", "W1", "b1", "W2", "b2"])
+    enc = HOMEREncoder.from_weights(W1, b1, W2, b2)
+    ids = enc.encode(x)
+    assert np.array_equal(ids, O.mlp_ids(x, W1, b1, W2, b2))
+    # against torch (the reference's own forward): equal except float32 near-ties (see the oracle test)
+    assert (ids != g[f"{tag}_ids"]).sum() <= 2
+
+
+def test_grid_encoder(ob):
+    from offsim4rl_b200.encoders.heuristic import GridEncoder
+    rng = np.random.default_rng(0)
+    cell = rng.integers(0, 5, size=(50000, 2))
+    obs = (cell / 5 + 0.1 + rng.uniform(-0.1, 0.1, size=cell.shape)).astype(np.float32)   # gridworld.py:205-211
+    ids = GridEncoder(cells=5).encode(obs)
+    assert np.array_equal(ids, O.grid_ids(obs, 5))
+    assert (ids == cell[:, 0] + 5 * cell[:, 1]).mean() > 0.999                             # gridworld.py:123-124
+
+
+# --------------------------------------------------------------------------------------- evaluators
+def test_learning_curve_and_totals(ob):
+    import torch
+    g = make_log(11, 50000, 30, 4)
+    R = 1000
+    log = device_log(ob, g, n_buckets=30)
+    sim = ob.BatchedPSRS(log, R, rng="philox", seed=5, lanes=4)
+    pi = np.full((30, 4), 0.25)
+    res = sim.run_evalmc(30, 60, pi=pi, gamma=0.99)
+    s, s2, c = sim.learning_curve(res, 60, all_reduce=False)
+    Gs = res.Gs.cpu().numpy(); ne = res.n_returns.cpu().numpy()
+    es, es2, ec = O.learning_curve([Gs[r, :ne[r]] for r in range(R)])
+    k = es.size
+    np.testing.assert_allclose(s.cpu().numpy()[:k], es, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(s2.cpu().numpy()[:k], es2, rtol=1e-12, atol=1e-12)
+    assert np.array_equal(c.cpu().numpy()[:k], ec) and np.all(c.cpu().numpy()[k:] == 0)
+    ret, ln = sim.replica_totals(res)
+    nl = res.n_lengths.cpu().numpy(); L = res.lengths.cpu().numpy()
+    np.testing.assert_allclose(ret.cpu().numpy(), [Gs[r, :ne[r]].sum() for r in range(R)], rtol=1e-12, atol=1e-12)
+    assert np.array_equal(ln.cpu().numpy(), [L[r, :nl[r]].sum() for r in range(R)])
+    assert int(ln.sum()) == int(res.accepted.sum())
