@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py — PSRS offline-learner simulation throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|c5|c2]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one complete simulation job over the bucketed log: fresh replicas (cursors, Q, counters
+zeroed), the fused PSRS + epsilon-greedy Q-learning run for `--budget` accepted transitions per replica,
+and the learning-curve reduction (plus its NCCL all-reduce when N > 1).  Replicas shard across GPUs
+(weak scaling: `--replicas` per GPU), the bucketed log is replicated per GPU, no data-path collective.
+
+Printed JSON (one line, rank 0): metric = accepted transitions/s over all GPUs, `roofline` for the
+fused run kernel (algorithmic bytes = pops x record bytes), `e2e` (host log -> H2D -> encode-free
+bucketing -> run -> curve -> D2H every step), `cpu_baseline` (the C restatement of the reference loop on
+this box's host cores, bounded sample), clocks, launches.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[3] sharded weak: 100M-transition / 10k-state / 4-action log, 1M replicas over 8 GPUs
+    "c4": dict(rows=100_000_000, states=10_000, actions=4, replicas=125_000, budget=10_000, delta=None, lanes=4,
+               desc="synthetic 100M-transition log, 10k states, 4 actions, eps-greedy Q-learning, 125k replicas/GPU (1M over 8)"),
+    # configs[4]: rejection-heavy stress, near-deterministic behaviour vs uniform target, 256k replicas over 8 GPUs
+    "c5": dict(rows=100_000_000, states=1_000, actions=4, replicas=32_000, budget=100, delta=1e-3, lanes=32,
+               desc="rejection-heavy: 100M-transition log, 1000 states, p_b=(1-d,d/3,d/3,d/3) d=1e-3, uniform target, 32k replicas/GPU"),
+    # configs[1] shape: cartpole-box sized state space, 10k replicas on one GPU
+    "c2": dict(rows=1_000_000, states=162, actions=2, replicas=10_000, budget=2_000, delta=None, lanes=2,
+               desc="cartpole-shaped: 1M-transition log, 162 states, 2 actions, eps-greedy Q-learning, 10k replicas"),
+}
+EPS, ALPHA, GAMMA = 0.1, 0.1, 0.99
+EP_CAP = 512
+
+
+def behaviour_table(n_states, n_actions, delta, seed=0):
+    rng = np.random.default_rng(seed)
+    if delta is None:
+        pb = rng.dirichlet(np.ones(n_actions), size=n_states)
+        pb = np.maximum(pb, 0.05)
+        pb /= pb.sum(1, keepdims=True)
+    else:  # near-deterministic: (1-d, d/3, ...) permuted per state (a strictly deterministic p_b accepts nothing)
+        pb = np.full((n_states, n_actions), delta / (n_actions - 1))
+        pb[np.arange(n_states), rng.integers(0, n_actions, n_states)] = 1.0 - delta
+    return pb.astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------- CPU legs
+def numpy_log(rows, states, actions, delta, seed=0, p_done=1 / 50):
+    rng = np.random.default_rng(seed + 1)
+    pb = behaviour_table(states, actions, delta)
+    z = rng.integers(0, states, rows).astype(np.int32)
+    zn = rng.integers(0, states, rows).astype(np.int32)
+    a = (rng.random(rows)[:, None] > np.cumsum(pb[z], 1)).sum(1).clip(0, actions - 1).astype(np.int32)
+    done = rng.random(rows) < p_done
+    return dict(z=z, z_next=zn, action=a, reward=rng.normal(size=rows).astype(np.float32), terminal=done.astype(np.uint8),
+                p_log=pb[z], steps=np.where(np.r_[True, done[:-1]], 0, 1).astype(np.int32))
+
+
+def cpu_leg(cols, wl, seconds, threads):
+    """Time the C restatement of the reference's loop (oracle/ols_oracle.c) on `threads` host threads."""
+    from oracle import c_oracle as CO
+    log = CO.Log(z=cols["z"], z_next=cols["z_next"], action=cols["action"], reward=cols["reward"], terminal=cols["terminal"],
+                 p_log=cols["p_log"], steps=cols["steps"], n_buckets=wl["states"])
+    R = threads * 4
+    budget = min(wl["budget"], 10_000)
+    uniform = np.full((wl["states"], wl["actions"]), 1.0 / wl["actions"])
+    total, t0, calls = 0, time.perf_counter(), 0
+    pops = 0
+    while True:
+        if wl["delta"] is None:
+            out = CO.run(log, R, CO.QLEARN, wl["states"], EP_CAP - 1, GAMMA, alpha=ALPHA, epsilon=EPS, seed=calls, max_steps=budget,
+                         ring=True, ring_seed=calls, threads=threads, ep_cap=EP_CAP)
+        else:
+            out = CO.run(log, R, CO.FIXED_PI, wl["states"], EP_CAP - 1, GAMMA, pi=uniform, seed=calls, max_steps=budget, ring=True,
+                         ring_seed=calls, threads=threads, ep_cap=EP_CAP)
+        total += int(out["accepted"].sum())
+        pops += int(out["pops"].sum())
+        calls += 1
+        dt = time.perf_counter() - t0
+        if dt >= seconds:
+            break
+    return dict(value=total / dt, pops_per_s=pops / dt, seconds=dt, accepted=total, threads=out["threads"], replicas=R * calls,
+                budget=budget, rows=log.n_rows)
+
+
+def python_port_leg(cols, wl, seconds):
+    """The pure-python restatement (list-free but interpreter-bound like the reference), one core."""
+    from oracle import psrs_oracle as O
+    n = min(len(cols["z"]), 200_000)
+    env = O.OraclePSRS(z=cols["z"][:n], z_next=cols["z_next"][:n], s=cols["z"][:n], s_next=cols["z_next"][:n],
+                       action=cols["action"][:n], reward=cols["reward"][:n], terminal=cols["terminal"][:n], p_log=cols["p_log"][:n],
+                       steps=cols["steps"][:n], n_buckets=wl["states"], uniforms=O.Pcg64Uniforms(0))
+    rng = np.random.default_rng(0)
+
+    class Ties:
+        def pick(self, cand):
+            return int(cand[rng.integers(0, len(cand))]) if len(cand) > 1 else int(cand[0])
+    t0 = time.perf_counter()
+    steps = 0
+    Q = np.zeros((wl["states"], wl["actions"]))
+    while time.perf_counter() - t0 < seconds:
+        Q, info = O.qlearn(env, 20, GAMMA, ALPHA, EPS, Ties(), wl["states"], wl["actions"], q_init=Q, record=False)
+        got = int(info["lengths"].sum())
+        steps += got
+        if got == 0:
+            break
+    dt = time.perf_counter() - t0
+    return dict(value=steps / dt, seconds=dt, rows=n)
+
+
+def run_reference(args, wl, rank, world):
+    """--impl reference: the CPU implementation of the path on this box's host cores (the oracle's C
+    restatement, all threads), same metric/config; rank 0 only."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    rows = min(wl["rows"], 1_000_000)
+    cols = numpy_log(rows, wl["states"], wl["actions"], wl["delta"])
+    per_step = 4.0
+    vals = []
+    for i in range(args.warmup + args.steps):
+        leg = cpu_leg(cols, wl, per_step if i >= args.warmup else 1.0, threads)
+        if i >= args.warmup:
+            vals.append(leg)
+    acc = sum(v["accepted"] for v in vals)
+    secs = sum(v["seconds"] for v in vals)
+    value = acc / secs
+    sample = (f"C restatement of psrs.py qlearn/evalMC loop, {vals[-1]['threads']} threads, log truncated to {rows} rows, "
+              f"{vals[-1]['budget']} accepted steps per replica, ~{per_step:.0f} s per step")
+    print(json.dumps({
+        "impl": "reference", "metric": "simulated accepted transitions/sec", "value": value, "unit": "transitions/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, len(vals)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload + ": " + wl["desc"], "rows": rows, "states": wl["states"], "actions": wl["actions"]},
+        "cpu_baseline": {"value": value, "unit": "transitions/s", "cores": vals[-1]["threads"], "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--rows", type=int)
+    ap.add_argument("--states", type=int)
+    ap.add_argument("--replicas", type=int, help="replicas per GPU")
+    ap.add_argument("--budget", type=int, help="accepted transitions per replica per step")
+    ap.add_argument("--lanes", type=int)
+    ap.add_argument("--no-ring", action="store_true", help="all replicas consume the queues from slot 0 (L2-resident gather)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    for k in ("rows", "states", "replicas", "budget", "lanes"):
+        if getattr(args, k) is not None:
+            wl[k] = getattr(args, k)
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import offsim4rl_b200 as ob
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+
+    N, nS, nA, R, T = wl["rows"], wl["states"], wl["actions"], wl["replicas"], wl["budget"]
+    pb = behaviour_table(nS, nA, wl["delta"])
+    qlearn = wl["delta"] is None
+    uniform_pi = np.full((nS, nA), 1.0 / nA)
+
+    # ---- setup (untimed): synthetic log generated on the device, bucketed once
+    cols = ob.synth_columns(N, nS, pb, seed=0, device=dev)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    log = ob.BucketedLog(z=cols["z"], z_next=cols["z_next"], action=cols["action"], reward=cols["reward"],
+                         terminal=cols["terminal"], p_log=cols["p_log"], steps=cols["steps"], n_buckets=nS, z_offset=0, device=dev)
+    ev[1].record()
+    torch.cuda.synchronize()
+    bucket_ms = ev[0].elapsed_time(ev[1])
+    rec_bytes = log.rec_bytes
+    bucket_bytes = N * (12 + 17 + 4 * nA + rec_bytes)   # z twice + order, log columns once, record written once
+    sim = ob.BatchedPSRS(log, R, rng="philox", seed=1234, ring=not args.no_ring, ring_seed=99, replica_id0=rank * R, lanes=wl["lanes"])
+    Q = torch.zeros((R, nS, nA), dtype=torch.float32, device=dev) if qlearn else None
+    res = None
+
+    k_ev = {"run": []}
+
+    def one_step(timed):
+        nonlocal res
+        sim.restart()
+        if Q is not None:
+            Q.zero_()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if qlearn:
+            res = sim.run_qlearn(nS, EP_CAP - 1, GAMMA, alpha=ALPHA, epsilon=EPS, Q=Q, max_steps=T, ep_cap=EP_CAP, outputs=res)
+        else:
+            res = sim.run_evalmc(nS, EP_CAP - 1, uniform_pi, GAMMA, max_steps=T, ep_cap=EP_CAP, outputs=res)
+        e1.record()
+        curve = sim.learning_curve(res, EP_CAP - 1)
+        if timed:
+            k_ev["run"].append((e0, e1))
+        return curve
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_step(False)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    acc_total = torch.zeros(2, dtype=torch.float64, device=dev)
+    t0.record()
+    for _ in range(args.steps):
+        one_step(True)
+        acc_total[0] += sim.accepted.sum()
+        acc_total[1] += sim.pops.sum()
+    t1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    run_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in k_ev["run"]) / max(1, len(k_ev["run"]))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(acc_total, op=dist.ReduceOp.SUM)
+    accepted, pops = float(acc_total[0]), float(acc_total[1])
+    secs = float(elapsed_ms) / 1e3
+    value = accepted / secs
+    # roofline of the dominant kernel (fused run kernel) on this rank
+    my_pops = float(sim.pops.sum())
+    run_s = float(run_ms) / 1e3
+    gather_gbs = my_pops * rec_bytes / run_s / 1e9
+    agent_gbs = float(sim.accepted.sum()) * (4 * nA + 4 + 8 if qlearn else 8) / run_s / 1e9
+
+    # ---- e2e: host-resident log -> H2D -> bucket -> run -> curve -> D2H, every step
+    e2e = None
+    if not args.skip_e2e:
+        host = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in cols.items()}
+        for k, v in cols.items():
+            host[k].copy_(v)
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        del cols, log
+        sim.log = None
+        torch.cuda.synchronize()
+        e_acc, d2h = 0.0, 0
+
+        def e2e_step():
+            nonlocal res, d2h
+            c = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            lg = ob.BucketedLog(z=c["z"], z_next=c["z_next"], action=c["action"], reward=c["reward"], terminal=c["terminal"],
+                                p_log=c["p_log"], steps=c["steps"], n_buckets=nS, z_offset=0, device=dev)
+            del c
+            sim.restart(lg)
+            if Q is not None:
+                Q.zero_()
+            if qlearn:
+                res = sim.run_qlearn(nS, EP_CAP - 1, GAMMA, alpha=ALPHA, epsilon=EPS, Q=Q, max_steps=T, ep_cap=EP_CAP, outputs=res)
+            else:
+                res = sim.run_evalmc(nS, EP_CAP - 1, uniform_pi, GAMMA, max_steps=T, ep_cap=EP_CAP, outputs=res)
+            s, s2, cnt = sim.learning_curve(res, EP_CAP - 1)
+            outs = [s.cpu(), s2.cpu(), cnt.cpu(), sim.accepted.sum().cpu()]
+            d2h = sum(o.numel() * o.element_size() for o in outs)
+            return float(outs[3])
+
+        e2e_step()  # warm the allocator
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e_acc += e2e_step()
+        barrier()
+        e_ms = torch.tensor([(time.perf_counter() - w0) * 1e3], dtype=torch.float64, device=dev)
+        e_tot = torch.tensor([e_acc], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(e_tot, op=dist.ReduceOp.SUM)
+        e2e = {"value": float(e_tot) / (float(e_ms) / 1e3), "unit": "transitions/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": float(e_ms) / args.e2e_steps, "steps": args.e2e_steps}
+        cpu_cols = {k: v[:1_000_000].numpy().copy() for k, v in host.items()}
+    else:
+        cpu_cols = {k: v[:1_000_000].cpu().numpy() for k, v in cols.items()}
+
+    if rank == 0:
+        cpu = None
+        if not args.skip_cpu and world == 1:
+            threads = os.cpu_count() or 1
+            leg = cpu_leg(cpu_cols, wl, args.cpu_seconds, threads)
+            py = python_port_leg(cpu_cols, wl, 4.0) if qlearn else None
+            cpu = {"value": leg["value"], "unit": "transitions/s", "cores": leg["threads"], "kind": "port",
+                   "sample": (f"oracle/ols_oracle.c (C restatement of the reference's PSRS + learner loop), {leg['threads']} threads, same "
+                              f"synthetic log truncated to {leg['rows']} rows, {leg['replicas']} replicas x {leg['budget']} accepted steps, "
+                              f"{leg['seconds']:.1f} s"),
+                   "pops_per_s": leg["pops_per_s"],
+                   "python_port_1core": None if py is None else {"value": py["value"], "rows": py["rows"], "seconds": py["seconds"]}}
+        out = {
+            "metric": "simulated accepted transitions/sec", "value": value, "unit": "transitions/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64 accept rule, f32 Q", "data": "synthetic",
+            "config": {"workload": args.workload + ": " + wl["desc"], "rows": N, "states": nS, "actions": nA,
+                       "replicas_per_gpu": R, "accepted_per_replica_per_step": T, "lanes": wl["lanes"],
+                       "queue_order": "log order" + ("" if args.no_ring else " + per-(replica,state) ring offset"),
+                       "l2": "working set (records %.1f GB + cursors %.1f GB + Q %.1f GB) >> 126 MB L2; no flush" % (
+                           N * rec_bytes / 1e9, R * nS * 4 / 1e9, (R * nS * nA * 4 / 1e9) if qlearn else 0.0)},
+            "pops_per_s": pops / secs,
+            "roofline": {"bound": "hbm", "kernel": "run_kernel (fused PSRS step + agent update)", "achieved": gather_gbs, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": gather_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_pop": rec_bytes, "agent_state_GBps": agent_gbs, "kernel_ms": float(run_ms)},
+            "bucketing": {"rows": N, "ms": bucket_ms, "GBps": bucket_bytes / bucket_ms / 1e6, "frac": bucket_bytes / bucket_ms / 1e6 / hbm_peak,
+                          "note": "includes host-side checks and the initial-row compaction"},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 4 * args.steps, "clocks": clocks,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,13 @@
+// Instantiations of the PSRS step/run kernels for records with 1 x 16 B of logged distribution
+// (n_actions in [1, 4]); split per width so the translation units compile in parallel.
+#include "ols_sim_kernels.cuh"
+
+cudaError_t ols_launch_run_nv1(const ols_queues_t& q, const ols_replicas_t& r, const ols_run_t& c,
+                               const ols_sim::RunLaunch& L, int ppl) {
+  return ols_sim::launch_run_nv<1>(q, r, c, L, ppl);
+}
+
+cudaError_t ols_launch_step_nv1(OLS_STEP_ARGS) {
+  return ols_sim::launch_step_nv<1>(q, r, mask, p_new, p_new_is_f64, p_stride, reject_mode, compute_mode, lanes, out, grid,
+                                    stream);
+}

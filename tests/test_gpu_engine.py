@@ -199,13 +199,14 @@ def _golden_log(ob, g):
 
 @pytest.mark.parametrize("case", DRIVER_CASES)
 @pytest.mark.parametrize("tag", ["const", "sched"])
-@pytest.mark.parametrize("lanes", [1, 4, 32])
-def test_fused_qlearn_matches_reference(ob, golden, case, tag, lanes):
+@pytest.mark.parametrize("lanes,ppl,stage", [(1, 1, False), (4, 2, True), (32, 2, False), (2, 2, True), (8, 1, True)])
+def test_fused_qlearn_matches_reference(ob, golden, case, tag, lanes, ppl, stage):
     import torch
     g = golden(case)
     nS, nA = g["pi"].shape
     N = g["z"].shape[0]
-    sim = ob.BatchedPSRS(_golden_log(ob, g), 2, rng="feed", u_feed=g["U"], tie_feed=g["T"], lanes=lanes)
+    sim = ob.BatchedPSRS(_golden_log(ob, g), 2, rng="feed", u_feed=g["U"], tie_feed=g["T"], lanes=lanes,
+                         pops_per_lane=ppl, stage_smem=stage)
     eps, alpha = (0.2, 0.1) if tag == "const" else (g["ql_sched_eps"], g["ql_sched_alpha"])
     res = sim.run_qlearn(nS, 25, gamma=0.9, alpha=alpha, epsilon=eps, q_dtype=torch.float64, trace_cap=N)
     n = g[f"ql_{tag}_trace"].size
@@ -246,7 +247,7 @@ def test_fused_expsarsa_matches_reference(ob, golden, case):
     g = golden(case)
     nS, nA = g["pi"].shape
     N = g["z"].shape[0]
-    sim = ob.BatchedPSRS(_golden_log(ob, g), 2, rng="feed", u_feed=g["U"], lanes=4)
+    sim = ob.BatchedPSRS(_golden_log(ob, g), 2, rng="feed", u_feed=g["U"], lanes=4, pops_per_lane=2)
     res = sim.run_expsarsa(nS, 25, pi=g["pi"], gamma=0.95, alpha=0.2, q_dtype=torch.float64, trace_cap=N)
     n = g["es_trace"].size
     assert int(res.accepted[1]) == n
@@ -259,12 +260,12 @@ def test_fused_expsarsa_matches_reference(ob, golden, case):
 
 
 @pytest.mark.parametrize("case", DRIVER_CASES + ["drivers_float_a"])
-@pytest.mark.parametrize("lanes", [1, 8])
-def test_fused_evalmc_matches_reference(ob, golden, case, lanes):
+@pytest.mark.parametrize("lanes,ppl", [(1, 1), (8, 2), (16, 1), (2, 2)])
+def test_fused_evalmc_matches_reference(ob, golden, case, lanes, ppl):
     g = golden(case)
     nS, nA = g["pi"].shape
     N = g["z"].shape[0]
-    sim = ob.BatchedPSRS(_golden_log(ob, g), 2, rng="feed", u_feed=g["U"], lanes=lanes)
+    sim = ob.BatchedPSRS(_golden_log(ob, g), 2, rng="feed", u_feed=g["U"], lanes=lanes, pops_per_lane=ppl)
     res = sim.run_evalmc(nS, 40, pi=g["pi"], gamma=0.97, trace_cap=N)
     n = g["mc_trace"].size
     assert int(res.accepted[0]) == n
@@ -386,3 +387,84 @@ def test_learning_curve_and_totals(ob):
     np.testing.assert_allclose(ret.cpu().numpy(), [Gs[r, :ne[r]].sum() for r in range(R)], rtol=1e-12, atol=1e-12)
     assert np.array_equal(ln.cpu().numpy(), [L[r, :nl[r]].sum() for r in range(R)])
     assert int(ln.sum()) == int(res.accepted.sum())
+
+
+# --------------------------------------------------------------------------------------- production streams vs the C oracle
+@pytest.mark.parametrize("agent", ["qlearn", "evalmc"])
+@pytest.mark.parametrize("lanes,ppl", [(4, 2), (32, 2), (8, 1), (1, 2)])
+@pytest.mark.parametrize("ring", [False, True])
+def test_philox_replicas_match_c_oracle(ob, agent, lanes, ppl, ring):
+    """Counter-based uniforms + ring offsets: thousands of replicas compared with oracle/ols_oracle.c, which
+    consumes the same (seed, replica, draw) -> uniform mapping strictly sequentially."""
+    import torch
+    from oracle import c_oracle as CO
+    g = make_log(21, 200000, 300, 4, ep_len=25)
+    R, nS = 3000, 300
+    log = device_log(ob, g, n_buckets=nS)
+    sim = ob.BatchedPSRS(log, R, rng="philox", seed=4242, ring=ring, ring_seed=7, replica_id0=10**6, lanes=lanes,
+                         pops_per_lane=ppl)
+    clog = CO.Log(z=g["z"], z_next=g["z_next"], action=g["a"], reward=g["r"], terminal=g["done"], p_log=g["p_log"],
+                  steps=g["t"], n_buckets=nS)
+    pi = np.random.default_rng(5).dirichlet(np.ones(4), size=nS)
+    if agent == "qlearn":
+        res = sim.run_qlearn(nS, 30, gamma=0.95, alpha=0.2, epsilon=0.15, q_dtype=torch.float64, trace_cap=4000)
+        ref = CO.run(clog, R, CO.QLEARN, nS, 30, gamma=0.95, alpha=0.2, epsilon=0.15, seed=4242, replica_id0=10**6,
+                     ring=ring, ring_seed=7, trace_cap=4000, threads=8)
+    else:
+        res = sim.run_evalmc(nS, 30, pi=pi, gamma=0.95, trace_cap=4000)
+        ref = CO.run(clog, R, CO.FIXED_PI, nS, 30, gamma=0.95, pi=pi, seed=4242, replica_id0=10**6, ring=ring,
+                     ring_seed=7, trace_cap=4000, threads=8)
+    assert np.array_equal(res.accepted.cpu().numpy(), ref["accepted"])
+    assert np.array_equal(res.pops.cpu().numpy(), ref["pops"])
+    assert np.array_equal(sim.draws.cpu().numpy(), ref["draws"])
+    assert np.array_equal(res.status.cpu().numpy(), ref["status"])
+    assert np.array_equal(res.trace_row.cpu().numpy(), ref["trace_row"])                 # bit-exact accepted rows
+    assert np.array_equal(res.n_returns.cpu().numpy(), ref["n_returns"])
+    assert np.array_equal(res.lengths.cpu().numpy(), ref["lengths"])
+    np.testing.assert_allclose(res.Gs.cpu().numpy(), ref["Gs"], rtol=1e-12, atol=1e-12)
+    if agent == "qlearn":
+        assert np.array_equal(sim.ties.cpu().numpy(), ref["ties"])
+        assert np.array_equal(res.Q.cpu().numpy(), ref["Q"])
+
+
+def test_accept_filter_never_changes_a_decision(ob):
+    """Adversarial uniforms: u placed exactly on, and one ulp around, the exact threshold of the record it
+    will meet — the float32 pre-filter must defer to the exact rule there."""
+    rng = np.random.default_rng(3)
+    nS, nA, N = 6, 4, 3000
+    g = make_log(31, N, nS, nA)
+    # a single replica walks the log in order; build its uniform stream pop by pop from the oracle's thresholds
+    pi = rng.dirichlet(np.ones(nA), size=nS)
+    env = oracle_env(g, n_buckets=nS, uniforms=O.FeedUniforms(np.zeros(1)))
+    U = []
+    # simulate with the oracle, choosing each u adversarially
+    env.reset()
+    order = env.order; offs = env.offsets
+    cursors = np.zeros(nS, dtype=np.int64)
+    z = env.cur_z; trace = []
+    init_i = 1
+    steps = 0
+    while steps < 1500:
+        lo, hi = offs[z], offs[z + 1]
+        if cursors[z] >= hi - lo:
+            break
+        row = order[lo + cursors[z]]; cursors[z] += 1
+        thr = float(O.threshold(pi[z], g["p_log"][row], g["a"][row]))
+        choice = rng.integers(0, 5)
+        u = [thr, np.nextafter(thr, 0.0), np.nextafter(thr, 2.0), thr * (1 - 2.0**-17), thr * (1 + 2.0**-17)][choice]
+        u = float(min(max(u, 0.0), np.nextafter(1.0, 0.0)))
+        U.append(u)
+        if not (u > thr):
+            trace.append(row); steps += 1
+            z = int(g["z_next"][row])
+            if g["done"][row]:
+                if init_i >= env.init.size:
+                    break
+                z = int(g["z"][env.init[init_i]]); init_i += 1
+    U = np.array(U + [0.5] * 64)
+    log = device_log(ob, g, n_buckets=nS)
+    for lanes, ppl in [(1, 1), (4, 2), (32, 2)]:
+        sim = ob.BatchedPSRS(log, 1, rng="feed", u_feed=U, lanes=lanes, pops_per_lane=ppl)
+        res = sim.run_evalmc(nS, 10**6 // 1000, pi=pi, gamma=1.0, trace_cap=N, max_steps=len(trace), ep_cap=2000)
+        got = res.trace_row[0, :len(trace)].cpu().numpy()
+        assert np.array_equal(got, trace), (lanes, ppl)
