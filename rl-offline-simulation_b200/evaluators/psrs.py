@@ -1,0 +1,329 @@
+"""Scalar (one-replica) PSRS environment and learner drivers with the reference's API.
+
+Mirrors offsim4rl/evaluators/psrs.py: ``PSRS(buffer, nS, nA, reject_func)`` with ``reset_sampler`` /
+``reset`` / ``step`` (psrs.py:5-57) and the drivers ``qlearn_psrs`` / ``expSARSA_psrs`` / ``evalMC_psrs``
+(psrs.py:119-271).  Every simulation step runs on the GPU (``ols_step`` with one replica, PCG64 replay
+so that ``reset_sampler(seed=k)`` reproduces the reference's own run bit for bit); the drivers run the
+whole learning loop in ONE kernel launch (``ols_run``) when given the stock policies.  The batched
+vector form lives in ``offsim4rl_b200.BatchedPSRS``.
+"""
+from __future__ import annotations
+
+import secrets
+
+import numpy as np
+import torch
+
+from .. import _abi as abi
+from ..agents import tabular as _tabular
+from ..engine import BatchedPSRS, BucketedLog
+
+_REJECT_NAMES = {None: "default", "default": "default", "accept_all": "accept_all"}
+
+
+def _is_int_like(x):
+    return isinstance(x, (int, np.integer)) or (isinstance(x, np.ndarray) and x.ndim == 0 and np.issubdtype(x.dtype, np.integer))
+
+
+class PSRS(object):
+    """Rejection sampler that acts as an environment (reference: psrs.py:5-57).
+
+    ``buffer`` holds legacy tuples ``(s, a, r, s', done, p, info)`` with ``info['z']``, ``info['z_next']``
+    (or ``'next_z'``) and ``info['t']`` (psrs.py:8,17,22).  ``reject_func`` cannot be arbitrary Python on
+    the device: pass ``None``/``"default"`` for psrs.py:53-57 or ``"accept_all"`` for the trivial
+    baselines (trivial_baselines.py:8-10).
+    """
+
+    def __init__(self, buffer, nS=25, nA=5, reject_func=None, device=None):
+        if reject_func not in _REJECT_NAMES:
+            raise NotImplementedError(
+                "a Python reject_func cannot run inside the CUDA step; use reject_func=None (the reference's "
+                "_default_reject) or reject_func='accept_all' (FollowObservationOnly / ServeRandomTransitions)")
+        rows = list(buffer)                               # the reference also materialises it (psrs.py:17)
+        n = len(rows)
+        z = np.fromiter((r[6]["z"] for r in rows), dtype=np.int64, count=n)
+        z_next = np.fromiter((r[6]["z_next"] if "z_next" in r[6] else r[6]["next_z"] for r in rows), dtype=np.int64, count=n)
+        t = np.fromiter((r[6]["t"] for r in rows), dtype=np.int64, count=n)
+        p_log = np.stack([np.asarray(r[5]) for r in rows]) if n else np.zeros((0, nA), dtype=np.float32)
+        self._init_from_columns(
+            z=z, z_next=z_next, action=np.array([r[1] for r in rows]), reward=np.array([r[2] for r in rows]),
+            terminal=np.array([bool(r[4]) for r in rows]), p_log=p_log, steps=t,
+            s=[r[0] for r in rows], s_next=[r[3] for r in rows], nS=nS, nA=nA,
+            reject=_REJECT_NAMES[reject_func], device=device)
+
+    @classmethod
+    def from_arrays(cls, z, z_next, action, reward, terminal, p_log, steps=None, s=None, s_next=None, nS=25, nA=None,
+                    reject="default", device=None):
+        """Build from column arrays directly (no per-row Python objects)."""
+        self = cls.__new__(cls)
+        p_log = np.asarray(p_log)
+        self._init_from_columns(z=z, z_next=z_next, action=np.asarray(action),
+                                reward=np.asarray(reward), terminal=np.asarray(terminal), p_log=p_log, steps=steps,
+                                s=s, s_next=s_next, nS=nS, nA=nA if nA is not None else p_log.shape[1], reject=reject,
+                                device=device)
+        return self
+
+    def _init_from_columns(self, z, z_next, action, reward, terminal, p_log, steps, s, s_next, nS, nA, reject, device):
+        self.nS, self.nA = nS, nA
+        n = len(z)
+        if p_log.ndim != 2 or (n and p_log.shape[1] != nA):
+            raise ValueError("logged action distributions must be [n_rows, nA]")
+        self._action, self._reward, self._terminal, self._p_log = action, reward, terminal, p_log
+        # state ids may arrive as device tensors (an encoder's encode_device): bucket them in place and keep a
+        # host copy for the scalar API's bookkeeping
+        to_host = lambda a: (a.cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)).astype(np.int64)
+        z_in, z_next_in = z, z_next
+        self._z, self._z_next = to_host(z), to_host(z_next)
+        # observations handed back to the caller are the original python objects; the device keeps an integer
+        # copy when they are integers (the tabular drivers index Q with them, psrs.py:158,165)
+        self._s_rows = self._z if s is None else s
+        self._s_next_rows = self._z_next if s_next is None else s_next
+        s_int = s_next_int = None
+        if s is not None and n and all(_is_int_like(x) for x in s) and all(_is_int_like(x) for x in s_next):
+            s_int = np.fromiter((int(x) for x in s), dtype=np.int64, count=n)
+            s_next_int = np.fromiter((int(x) for x in s_next), dtype=np.int64, count=n)
+        self._log = BucketedLog(z=z_in if isinstance(z_in, torch.Tensor) else self._z,
+                                z_next=z_next_in if isinstance(z_next_in, torch.Tensor) else self._z_next,
+                                action=action, reward=reward, terminal=terminal,
+                                p_log=p_log, s=s_int, s_next=s_next_int, steps=steps, device=device)
+        self._reject = reject
+        self._sim = None
+        self.s = self.z = None
+        self.reset_sampler()
+        self.reset()
+
+    # ------------------------------------------------------------------ psrs.py:19-30
+    def reset_sampler(self, seed=None):
+        if seed is None:
+            seed = secrets.randbits(63)          # default_rng(None): fresh OS entropy (psrs.py:13,20)
+        self._seed = int(seed)
+        self._cur = self._log.seeded(self._seed)
+        self._init_rows_host = self._cur.init_row[: self._cur.n_init].cpu().numpy()
+        if self._sim is None:
+            self._sim = BatchedPSRS(self._cur, 1, rng="pcg64", seed=self._seed, reject=self._reject, lanes=4)
+        else:
+            self._sim.seed = self._seed
+            self._sim.u_feed = None
+            self._sim.rng_mode = abi.RNG_PCG64
+            if self._sim.pcg_state is None:
+                self._sim.pcg_state = torch.zeros((1, 4), dtype=torch.int64, device=self._sim.device)
+            self._sim.restart(self._cur)
+            if self.z is not None:
+                # the reference keeps the current (z, s) across reset_sampler (psrs.py:19-30 do not touch them)
+                self._sim.cur_z.fill_(int(self.z))
+                if _is_int_like(self.s):
+                    self._sim.cur_s.fill_(int(self.s))
+                self._sim.status.fill_(abi.RUNNING)
+        self._n_resets = 0
+
+    def feed_uniforms(self, values):
+        """Parity hook: replace the rejection uniforms by a given stream (what a harness does to the
+        reference with ``env.rejection_sampling_rng = Feed(values)``); draw k uses ``values[k]``."""
+        self._sim.u_feed = torch.as_tensor(np.asarray(values, dtype=np.float64), device=self._sim.device)
+        self._sim.rng_mode = abi.RNG_FEED
+        self._sim.draws.zero_()
+
+    # ------------------------------------------------------------------ psrs.py:32-37
+    def reset(self, seed=None):
+        _, status = self._sim.reset()
+        if int(status[0]) != abi.RUNNING:
+            self.s = None
+            return None
+        row = int(self._init_rows_host[self._n_resets])
+        self._n_resets += 1
+        self.z = int(self._z[row])
+        self.s = self._s_rows[row]
+        return self.s
+
+    # ------------------------------------------------------------------ psrs.py:39-51
+    def step(self, p_new):
+        p = np.asarray(p_new)
+        if p.dtype not in (np.float32, np.float64):
+            p = p.astype(np.float64)
+        out = self._sim.step(p)
+        row = int(out["row"][0])
+        if row < 0:
+            status = int(self._sim.status[0])
+            if status == abi.NO_QUEUE:
+                raise KeyError(self.z)            # psrs.py:44 — queues[z] for a z never logged as a from-state
+            if status == abi.FEED_EMPTY:
+                raise IndexError("the fed uniform stream is exhausted")
+            return None, None, None, None         # psrs.py:44-45
+        z_from = self.z
+        self.s = self._s_next_rows[row]
+        self.z = int(self._z_next[row])
+        return self.s, self._reward[row], self._terminal[row], {"z": z_from, "a": self._action[row], "p": self._p_log[row]}
+
+    # ------------------------------------------------------------------ introspection (public attrs in the reference)
+    @property
+    def queues(self):
+        """``{z: [row indices still queued]}`` (the reference's ``env.queues``, psrs.py:26)."""
+        off = self._cur.offsets.cpu().numpy()
+        order = self._cur.order.cpu().numpy()
+        cur = self._sim.cursor[0].cpu().numpy()
+        out = {}
+        for b in range(self._cur.n_buckets):
+            if off[b + 1] > off[b]:
+                out[b - self._cur.z_offset] = order[off[b] + cur[b]: off[b + 1]].tolist()
+        return out
+
+    @property
+    def init_queue(self):
+        return [(int(self._z[r]), self._s_rows[r]) for r in self._init_rows_host[self._n_resets:]]
+
+    @property
+    def pops(self):
+        return int(self._sim.pops[0])
+
+    def _sync_from_device(self):
+        self._n_resets = int(self._sim.init_cursor[0])
+        self.z = int(self._sim.cur_z[0])
+        st = int(self._sim.status[0])
+        self.s = None if st == abi.INIT_EMPTY else int(self._sim.cur_s[0])
+
+
+# --------------------------------------------------------------------------------------------------- drivers
+def _schedule(x):
+    return x if callable(x) else (lambda episode: x)
+
+
+def _fusable(env):
+    return isinstance(env, PSRS)
+
+
+def _rows_to_memory(env, rows):
+    return [(int(env._z[r]) if env._s_rows is env._z else env._s_rows[r], env._action[r], env._reward[r],
+             env._s_next_rows[r], env._terminal[r], None, {"z": int(env._z[r]), "a": env._action[r], "p": env._p_log[r]})
+            for r in rows]
+
+
+def _raise_on_error(env, res):
+    st = int(res.status[0])
+    if st == abi.NO_QUEUE:
+        raise KeyError("a simulated transition led to a state that was never logged as a from-state (psrs.py:44)")
+    if st == abi.FEED_EMPTY:
+        raise IndexError("the fed uniform / tie stream is exhausted")
+
+
+def qlearn_psrs(env, n_episodes, behavior_policy, gamma, alpha=0.1, epsilon=1.0, Q_init=None, save_Q=0):
+    """Tabular Q-learning against a PSRS environment (reference: psrs.py:119-185).
+
+    With ``behavior_policy = agents.tabular.epsilon_greedy_policy`` and ``save_Q == 0`` the whole run is one
+    fused kernel launch (float64 Q, the reference's operation order); any other policy callable falls back to
+    a host-driven loop whose every ``env.step`` is still the CUDA step."""
+    if _fusable(env) and behavior_policy is _tabular.epsilon_greedy_policy and not save_Q:
+        Q0 = np.zeros((env.nS, env.nA)) if Q_init is None else np.asarray(Q_init, dtype=np.float64)
+        Qd = torch.as_tensor(Q0.reshape(1, env.nS, env.nA).copy(), device=env._sim.device)
+        cap = max(1, env._log.n_rows)
+        first = int(env._sim.accepted[0])
+        res = env._sim.run_qlearn(env.nS, n_episodes, gamma, alpha=alpha, epsilon=epsilon, Q=Qd, trace_cap=cap)
+        _raise_on_error(env, res)
+        env._sync_from_device()
+        n = int(res.n_returns[0])
+        rows = res.trace_row[0, first:int(res.accepted[0])].cpu().numpy()
+        return Qd[0].cpu().numpy(), {
+            "Gs": res.Gs[0, :n].cpu().numpy(), "Qs": np.array([Q0]),
+            "TD_errors": res.td_error[0, first:int(res.accepted[0])].cpu().numpy(), "memory": _rows_to_memory(env, rows)}
+
+    eps_f, alpha_f = _schedule(epsilon), _schedule(alpha)
+    Q = np.zeros((env.nS, env.nA)) if Q_init is None else np.array(Q_init, dtype=float)
+    out = dict(Gs=[], Qs=[Q.copy()], TD_errors=[], memory=[])
+    for episode in range(n_episodes):
+        S = env.reset(seed=episode)
+        if S is None:
+            break
+        G, discount, exhausted, done = 0, 1.0, False, False
+        while not done:
+            p = behavior_policy(Q[[S], :], dict(epsilon=eps_f(episode)))[0]
+            S2, R, done, info = env.step(p)
+            if S2 is None:
+                exhausted = True
+                break
+            A = info["a"]
+            delta = R + gamma * Q[S2].max() - Q[S, A]
+            out["memory"].append((S, A, R, S2, done, p, info))
+            out["TD_errors"].append(delta)
+            Q[S, A] += alpha_f(episode) * delta
+            G += discount * R
+            discount *= gamma
+            S = S2
+            if save_Q:
+                out["Qs"].append(Q.copy())
+        out["Gs"].append(G)                        # a partial last episode is appended too (psrs.py:160-162,177)
+        if exhausted:
+            break
+    return Q, {"Gs": np.array(out["Gs"]), "Qs": np.array(out["Qs"]), "TD_errors": np.array(out["TD_errors"]),
+               "memory": out["memory"]}
+
+
+def expSARSA_psrs(env, n_episodes, pi, gamma, alpha=0.1, Q_init=None, save_Q=0):
+    """Expected SARSA for a fixed policy ``pi[nS, nA]`` (reference: psrs.py:187-239)."""
+    pi = np.asarray(pi)
+    if _fusable(env) and not save_Q:
+        Q0 = np.zeros((env.nS, env.nA)) if Q_init is None else np.asarray(Q_init, dtype=np.float64)
+        Qd = torch.as_tensor(Q0.reshape(1, env.nS, env.nA).copy(), device=env._sim.device)
+        first = int(env._sim.accepted[0])
+        res = env._sim.run_expsarsa(env.nS, n_episodes, pi, gamma, alpha=alpha, Q=Qd, trace_cap=max(1, env._log.n_rows))
+        _raise_on_error(env, res)
+        env._sync_from_device()
+        n = int(res.n_returns[0])
+        rows = res.trace_row[0, first:int(res.accepted[0])].cpu().numpy()
+        return Qd[0].cpu().numpy(), {"Gs": res.Gs[0, :n].cpu().numpy(), "Qs": np.array([Q0]),
+                                     "memory": _rows_to_memory(env, rows)}
+
+    alpha_f = _schedule(alpha)
+    Q = np.zeros((env.nS, env.nA)) if Q_init is None else np.array(Q_init, dtype=float)
+    Gs, Qs, memory = [], [Q.copy()], []
+    for episode in range(n_episodes):
+        S = env.reset(seed=episode)
+        if S is None:
+            break
+        G, discount, exhausted, done = 0, 1.0, False, False
+        while not done:
+            S2, R, done, info = env.step(pi[S])
+            if S2 is None:
+                exhausted = True
+                break
+            A = info["a"]
+            memory.append((S, A, R, S2, done, pi[S], info))
+            Q[S, A] += alpha_f(episode) * (R + gamma * (Q[S2] @ pi[S2]) - Q[S, A])
+            G += discount * R
+            discount *= gamma
+            S = S2
+            if save_Q:
+                Qs.append(Q.copy())
+        Gs.append(G)
+        if exhausted:
+            break
+    return Q, {"Gs": np.array(Gs), "Qs": np.array(Qs), "memory": memory}
+
+
+def evalMC_psrs(env, n_episodes, pi, gamma):
+    """Monte-Carlo evaluation of a fixed policy: returns of COMPLETED episodes and the lengths of all
+    simulated ones (reference: psrs.py:241-271)."""
+    pi = np.asarray(pi)
+    if _fusable(env):
+        res = env._sim.run_evalmc(env.nS, n_episodes, pi, gamma)
+        _raise_on_error(env, res)
+        env._sync_from_device()
+        return (res.Gs[0, :int(res.n_returns[0])].cpu().numpy(),
+                res.lengths[0, :int(res.n_lengths[0])].cpu().numpy().astype(np.int64))
+    Gs, lengths = [], []
+    while len(Gs) < n_episodes:
+        S = env.reset(seed=len(Gs))
+        if S is None:
+            break
+        G, discount, t, done = 0, 1.0, 0, False
+        while not done:
+            S2, R, done, info = env.step(pi[S])
+            if S2 is None:
+                break
+            G += discount * R
+            discount *= gamma
+            t += 1
+            S = S2
+        lengths.append(t)
+        if not done:
+            break
+        Gs.append(G)
+    return np.array(Gs), np.array(lengths)

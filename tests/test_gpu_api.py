@@ -1,0 +1,300 @@
+"""GPU tests of the reference-facing API: PSRS / PerStateRejectionSampling / drivers, against the golden
+vectors of the unmodified reference and the reference's own behavioural tests."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ob():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import offsim4rl_b200
+    return offsim4rl_b200
+
+
+def _legacy(g, with_t=True, keys=("z", "z_next")):
+    rows = []
+    for i in range(len(g["z"])):
+        info = {keys[0]: int(g["z"][i]), keys[1]: int(g["z_next"][i]), "t": int(g["t"][i]) if with_t else 0}
+        rows.append((int(g["z"][i]), g["a"][i], g["r"][i], int(g["z_next"][i]), bool(g["done"][i]), g["p_log"][i], info))
+    return rows
+
+
+# ----------------------------------------------------------------------------- PSRS scalar API
+@pytest.mark.parametrize("seed", [0, 3, 98052])
+def test_psrs_seeded_walk_equals_reference_run(ob, golden, seed):
+    """PSRS(buffer) + reset_sampler(seed) + step(p): same queues, same RNG, same accepted rows as the reference."""
+    from offsim4rl_b200.evaluators.psrs import PSRS
+    g = golden("seeded_walk")
+    env = PSRS(_legacy(g, keys=("z", "next_z") if seed == 3 else ("z", "z_next")), nS=9, nA=3)
+    env.reset_sampler(seed=seed)
+    order = np.concatenate([env.queues.get(z, []) for z in range(9)]).astype(np.int64)
+    assert np.array_equal(order, g[f"order_{seed}"])
+    assert np.array_equal(np.array([z for z, s in env.init_queue]), g[f"init_zs_{seed}"][:, 0])
+    rewards, resets, n = [], [], 0
+    s = env.reset()
+    resets.append(s)
+    expect = g[f"trace_{seed}"]
+    while s is not None:
+        s, r, done, info = env.step(g["p_new"])
+        if s is None:
+            assert (r, done, info) == (None, None, None)
+            break
+        row = int(expect[n]); n += 1
+        assert s == g["z_next"][row] and r == g["r"][row] and done == g["done"][row]
+        assert info["z"] == g["z"][row] and info["a"] == g["a"][row] and info["p"] is not None
+        assert np.array_equal(info["p"], g["p_log"][row])
+        if done:
+            s = env.reset()
+            resets.append(-1 if s is None else s)
+    assert n == expect.size
+    assert np.array_equal(np.array(resets, dtype=np.int64), g[f"resets_{seed}"])
+    assert env.pops == int(g[f"pops_{seed}"])
+
+
+def test_reference_test_psrs_scenario(ob, golden):
+    """tests/test_psrs.py:9-34 of the reference on its own gridworld log: > 40 simulated steps, and per-seed
+    counts identical to the reference's."""
+    from offsim4rl_b200.evaluators import psrs
+    g = golden("gridworld")
+    mem = [(int(g["s"][i]), int(g["a"][i]), float(g["r"][i]), int(g["s_next"][i]), bool(g["done"][i]), g["p"][i],
+            {"z": int(g["z"][i]), "z_next": int(g["z_next"][i]), "t": int(g["t"][i])}) for i in range(len(g["z"]))]
+    env_psrs = psrs.PSRS(mem, nS=25, nA=5)
+    counts = []
+    for seed in [None] + list(range(20)):
+        if seed is not None:
+            env_psrs.reset_sampler(seed=seed)
+        obs = env_psrs.reset()
+        steps_simulated = -1
+        while obs is not None:
+            obs, r, done, info = env_psrs.step(np.array([0.2, 0.2, 0.2, 0.2, 0.2]))
+            steps_simulated += 1
+            if done:
+                obs = env_psrs.reset()
+        assert steps_simulated > 40
+        if seed is not None:
+            counts.append(steps_simulated)
+    assert np.array_equal(counts, g["steps_simulated_by_seed"])
+
+
+@pytest.mark.parametrize("case", ["drivers_f64", "drivers_p64_a5", "drivers_edge"])
+def test_drivers_with_reference_signatures(ob, golden, case):
+    from offsim4rl_b200.evaluators.psrs import PSRS, qlearn_psrs, expSARSA_psrs, evalMC_psrs
+    from offsim4rl_b200.agents import tabular
+    g = golden(case)
+    nS, nA = g["pi"].shape
+    with_t = bool(g["with_t"])
+
+    def fresh():
+        env = PSRS(_legacy(g, with_t), nS=nS, nA=nA)
+        env.reset_sampler(seed=int(g["sampler_seed"]))
+        env.feed_uniforms(g["U"])
+        return env
+
+    # expSARSA / evalMC have no tie-breaks: identical to the reference's outputs
+    Q, info = expSARSA_psrs(fresh(), n_episodes=25, pi=g["pi"], gamma=0.95, alpha=0.2)
+    np.testing.assert_allclose(Q, g["es_Q"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(info["Gs"], g["es_Gs"], rtol=1e-5, atol=1e-5)
+    assert len(info["memory"]) == g["es_trace"].size
+    assert [m[6]["a"] for m in info["memory"]] == [g["a"][r] for r in g["es_trace"]]
+    Gs, lengths = evalMC_psrs(fresh(), n_episodes=40, pi=g["pi"], gamma=0.97)
+    assert np.array_equal(lengths, g["mc_lengths"])
+    np.testing.assert_allclose(Gs, g["mc_Gs"], rtol=1e-5, atol=1e-5)
+    # qlearn: the tie stream is the library's own here, so compare structure and the generic host loop
+    env = fresh()
+    Q, info = qlearn_psrs(env, n_episodes=25, behavior_policy=tabular.epsilon_greedy_policy, gamma=0.9, alpha=0.1, epsilon=0.2)
+    assert Q.shape == (nS, nA) and info["Gs"].ndim == 1 and info["TD_errors"].size == len(info["memory"])
+    assert info["Qs"].shape == (1, nS, nA)
+    # a custom policy callable goes through the host loop (every step still on the GPU)
+    np.random.seed(0)
+    env = fresh()
+    Q2, info2 = qlearn_psrs(env, n_episodes=5, behavior_policy=lambda Qr, a: tabular.epsilon_greedy_policy(Qr, a), gamma=0.9,
+                            alpha=0.1, epsilon=0.2)
+    assert Q2.shape == (nS, nA) and len(info2["Gs"]) <= 5 and info2["TD_errors"].size == len(info2["memory"])
+
+
+def test_generic_host_loop_equals_fused_kernel(ob, golden):
+    """The host-driven loop (arbitrary policy callables) and the fused kernel implement the same algorithm."""
+    from offsim4rl_b200.evaluators.psrs import PSRS, expSARSA_psrs, evalMC_psrs
+    g = golden("drivers_f64")
+    nS, nA = g["pi"].shape
+
+    class Unfusable(PSRS):
+        pass
+
+    def fresh(cls):
+        env = cls(_legacy(g), nS=nS, nA=nA)
+        env.reset_sampler(seed=5)
+        env.feed_uniforms(g["U"])
+        return env
+    import offsim4rl_b200.evaluators.psrs as mod
+    saved = mod._fusable
+    try:
+        mod._fusable = lambda env: False
+        Qh, ih = expSARSA_psrs(fresh(PSRS), 25, g["pi"], 0.95, alpha=0.2)
+        Gh, Lh = evalMC_psrs(fresh(PSRS), 40, g["pi"], 0.97)
+    finally:
+        mod._fusable = saved
+    np.testing.assert_allclose(Qh, g["es_Q"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(ih["Gs"], g["es_Gs"], rtol=1e-5, atol=1e-5)
+    assert np.array_equal(Lh, g["mc_lengths"])
+    np.testing.assert_allclose(Gh, g["mc_Gs"], rtol=1e-5, atol=1e-5)
+
+
+def test_unseen_state_raises_keyerror_like_the_reference(ob):
+    from offsim4rl_b200.evaluators.psrs import PSRS
+    p = np.array([0.5, 0.5])
+    rows = [(0, 0, 1.0, 2, False, p, {"z": 0, "z_next": 2, "t": 0})]       # state 2 is never a from-state
+    env = PSRS(rows, nS=3, nA=2)
+    env.reset_sampler(seed=0)
+    assert env.reset() == 0
+    s, r, done, info = env.step(p)
+    assert s == 2
+    with pytest.raises(KeyError):
+        env.step(p)
+    assert env.reset() is None                                              # psrs.py:33-35
+    with pytest.raises(NotImplementedError):
+        PSRS(rows, nS=3, nA=2, reject_func=lambda *a: False)
+
+
+# ----------------------------------------------------------------------------- gym-style wrapper
+def _disc_dataset(ob, g):
+    from offsim4rl_b200.data import OfflineDataset, ProbDistribution
+    from offsim4rl_b200 import spaces
+    return OfflineDataset(observation_space=spaces.Discrete(8), action_space=spaces.Discrete(4),
+                          action_dist_type=ProbDistribution.Discrete, observations=g["disc_z"], actions=g["disc_a"],
+                          action_distributions=g["disc_p_log"], rewards=g["disc_r"], next_observations=g["disc_z_next"],
+                          terminals=g["disc_done"])
+
+
+@pytest.mark.parametrize("api", [False, True])
+def test_wrapper_discrete_matches_reference(ob, golden, api):
+    from offsim4rl_b200.evaluators import PerStateRejectionSampling
+    g = golden("wrapper")
+    env = PerStateRejectionSampling(_disc_dataset(ob, g), new_step_api=api)
+    env.reset_sampler(seed=2)
+    env._impl.feed_uniforms(g["disc_U"])
+    tag = "disc_new" if api else "disc_old"
+    obs = env.reset()
+    assert obs == g[tag + "_first"] and np.shape(obs) == ()
+    acts, nobs, rews, dones = [], [], [], []
+    while obs is not None:
+        res = env.step_dist(g["disc_target"])
+        if res[0] is None:
+            assert res == (None,) * (6 if api else 5)
+            break
+        if api:
+            assert res[4] is False and isinstance(res[5], dict)
+        acts.append(res[0]); nobs.append(res[1]); rews.append(res[2]); dones.append(res[3])
+        obs = res[1]
+        if res[3]:
+            obs = env.reset()
+            nobs.append(-1 if obs is None else obs)
+    assert np.array_equal(acts, g[tag + "_a"]) and np.array_equal(nobs, g[tag + "_obs"])
+    assert np.array_equal(rews, g[tag + "_r"]) and np.array_equal(dones, g[tag + "_d"])
+
+
+@pytest.mark.parametrize("tag", ["psrs", "followobs", "followact", "random"])
+@pytest.mark.parametrize("device_encoder", [True, False])
+def test_wrapper_cartpole_encoder_and_baselines_match_reference(ob, golden, tag, device_encoder):
+    from offsim4rl_b200.data import OfflineDataset, ProbDistribution
+    from offsim4rl_b200 import spaces
+    from offsim4rl_b200.encoders import CartpoleBoxEncoder
+    from offsim4rl_b200.evaluators import (PerStateRejectionSampling, FollowObservationOnly, FollowActionOnly,
+                                           ServeRandomTransitions)
+    g = golden("wrapper")
+    ds = OfflineDataset(observation_space=spaces.Box(low=-10, high=10, shape=(4,)), action_space=spaces.Discrete(2),
+                        action_dist_type=ProbDistribution.Discrete, observations=g["cp_obs"], actions=g["cp_a"],
+                        action_distributions=g["cp_p"], rewards=g["cp_r"], next_observations=g["cp_next"],
+                        terminals=g["cp_done"], steps=g["cp_steps"])
+    base = CartpoleBoxEncoder()
+    enc = base
+    if not device_encoder:
+        class HostEncoder:                      # a user-supplied encoder with only .encode (numpy in, ids out)
+            def encode(self, o):
+                return base.encode(o)
+        enc = HostEncoder()
+    cls = {"psrs": PerStateRejectionSampling, "followobs": FollowObservationOnly, "followact": FollowActionOnly,
+           "random": ServeRandomTransitions}[tag]
+    env = cls(ds, num_states=162, encoder=enc) if tag in ("psrs", "followobs") else cls(ds)
+    env.reset_sampler(seed=9)
+    env._impl.feed_uniforms(g["cp_U"])
+    o = env.reset()
+    assert np.array_equal(o, g[f"cp_{tag}_first"])
+    acts, nobs, dones, status = [], [], [], "exhausted"
+    try:
+        while o is not None:
+            res = env.step_dist(np.array([0.5, 0.5]))
+            if res[0] is None:
+                break
+            acts.append(res[0]); nobs.append(res[1]); dones.append(res[3])
+            o = res[1]
+            if res[3]:
+                o = env.reset()
+                if o is not None:
+                    nobs.append(o)
+    except KeyError:
+        status = "keyerror"
+    assert status == str(g[f"cp_{tag}_status"])
+    assert np.array_equal(acts, g[f"cp_{tag}_a"]) and np.array_equal(dones, g[f"cp_{tag}_d"])
+    assert np.array_equal(np.array(nobs, dtype=np.float32).reshape(-1, 4), g[f"cp_{tag}_obs"])
+    assert int(env._impl._sim.draws[0]) == int(g[f"cp_{tag}_draws"])
+
+
+def test_reference_test_per_state_rejection_and_baselines(ob):
+    """tests/test_per_state_rejection.py:7-20 and tests/test_trivial_baselines.py:8-31 of the reference."""
+    from offsim4rl_b200.data import OfflineDataset, ProbDistribution
+    from offsim4rl_b200 import spaces
+    from offsim4rl_b200.evaluators import (PerStateRejectionSampling, FollowObservationOnly, FollowActionOnly,
+                                           ServeRandomTransitions)
+    dataset = OfflineDataset(
+        observation_space=spaces.Discrete(25), action_space=spaces.Discrete(4), action_dist_type=ProbDistribution.Discrete,
+        observations=np.array([0, 5], dtype=np.int64), actions=np.array([0, 1], dtype=np.int64),
+        action_distributions=np.full((2, 4), fill_value=0.25, dtype=np.float32), rewards=np.array([0.0, 1.0], dtype=np.float32),
+        next_observations=np.array([5, 7], dtype=np.int64), terminals=np.array([False, True], dtype=bool))
+    uniform = np.full((4,), 0.25)
+    for cls in (PerStateRejectionSampling, FollowObservationOnly, FollowActionOnly, ServeRandomTransitions):
+        env = cls(dataset)
+        obs = env.reset()
+        assert obs is None or np.shape(obs) == tuple()
+        env.step_dist(uniform)
+        with pytest.raises(NotImplementedError):
+            env.step(0)
+
+
+def test_wrapper_validation_errors(ob):
+    from offsim4rl_b200.data import OfflineDataset, ProbDistribution
+    from offsim4rl_b200 import spaces
+    from offsim4rl_b200.encoders import CartpoleBoxEncoder
+    from offsim4rl_b200.evaluators import PerStateRejectionSampling
+    obs = np.zeros((3, 4), dtype=np.float32)
+    kw = dict(action_dist_type=ProbDistribution.Discrete, observations=obs, actions=np.zeros(3, dtype=np.int64),
+              action_distributions=np.full((3, 2), 0.5, dtype=np.float32), rewards=np.zeros(3, dtype=np.float32),
+              next_observations=obs, terminals=np.zeros(3, dtype=bool))
+    box = OfflineDataset(observation_space=spaces.Box(-1, 1, (4,)), action_space=spaces.Discrete(2), **kw)
+    with pytest.raises(ValueError, match="only supports discrete observation"):
+        PerStateRejectionSampling(box)                                           # per_state_rejection.py:16-17
+    with pytest.raises(ValueError, match="both need"):
+        PerStateRejectionSampling(box, num_states=162)                           # :19-20
+    cont = OfflineDataset(observation_space=spaces.Box(-1, 1, (4,)), action_space=spaces.Box(-1, 1, (1,)), **kw)
+    with pytest.raises(ValueError, match="discrete action"):
+        PerStateRejectionSampling(cont, num_states=162, encoder=CartpoleBoxEncoder())   # :22-25
+    with pytest.raises(ValueError, match="Missing required key"):
+        OfflineDataset(observation_space=spaces.Discrete(2), action_space=spaces.Discrete(2),
+                       action_dist_type=ProbDistribution.Discrete, observations=obs)
+
+
+def test_torch_distribution_is_accepted(ob, golden):
+    import torch
+    from offsim4rl_b200.evaluators import PerStateRejectionSampling
+    g = golden("wrapper")
+    env = PerStateRejectionSampling(_disc_dataset(ob, g))
+    env.reset_sampler(seed=2)
+    env._impl.feed_uniforms(g["disc_U"])
+    env.reset()
+    dist = torch.distributions.Categorical(probs=torch.tensor(g["disc_target"]))
+    a, o, r, d, info = env.step_dist(dist)
+    assert a == g["disc_old_a"][0] and o == g["disc_old_obs"][0]
