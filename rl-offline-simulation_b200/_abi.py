@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libols_b200.so")
+# OLS_B200_LIB overrides the library path (used to A/B differently tuned builds of the same ABI)
+LIB_PATH = os.environ.get("OLS_B200_LIB") or os.path.join(HERE, "libols_b200.so")
 
 ABI_VERSION = 1
 

@@ -20,7 +20,9 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 OBJ_DIR = os.path.join(os.path.dirname(HERE), "build", "obj")
 LIB_PATH = os.path.join(HERE, "libols_b200.so")
 
-NVCC_FLAGS = [
+EXTRA = os.environ.get("OLS_NVCC_EXTRA", "").split()      # e.g. -DOLS_MINB=3 for tuning experiments
+
+NVCC_FLAGS = EXTRA + [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",

@@ -216,7 +216,15 @@ __device__ __forceinline__ void load_row(const ols_log_t& log, int64_t i, RowDat
   d.r = __ldg(log.reward + i);
   d.zn = __ldg(log.z_next + i);
   d.sn = log.s_next ? __ldg(log.s_next + i) : d.zn;
-  d.meta = ols_pack_meta(__ldg(log.action + i), __ldg(log.terminal + i));
+  float mn = pv[0], mx = pv[0];
+#pragma unroll
+  for (int j = 1; j < 4 * NV; ++j)
+    if (j < nA) {
+      mn = fminf(mn, pv[j]);
+      mx = fmaxf(mx, pv[j]);
+    }
+  const int tame = (mn >= 9.094947e-13f) && (mx <= 1.0995116e12f);  // [2^-40, 2^40]; false for NaN
+  d.meta = ols_pack_meta(__ldg(log.action + i), __ldg(log.terminal + i), tame);
 }
 
 template <int NV>

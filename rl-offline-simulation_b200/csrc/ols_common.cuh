@@ -46,10 +46,12 @@ constexpr int OLS_MAX_ACTIONS = 16;
 static inline int ols_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // ------------------------------------------------------------------------------------------ records
-// meta word: bits 0..7 action, bit 8 terminal
-__host__ __device__ inline uint32_t ols_pack_meta(int action, int terminal) {
-  return (uint32_t)(action & 0xff) | ((terminal ? 1u : 0u) << 8);
+// meta word: bits 0..7 action, bit 8 terminal, bit 9 "tame": every logged probability of the record lies in
+// [2^-40, 2^40] (set at packing time; lets the accept pre-filter skip its per-pop range checks)
+__host__ __device__ inline uint32_t ols_pack_meta(int action, int terminal, int tame = 0) {
+  return (uint32_t)(action & 0xff) | ((terminal ? 1u : 0u) << 8) | ((tame ? 1u : 0u) << 9);
 }
+__host__ __device__ inline int ols_meta_tame(uint32_t m) { return (int)((m >> 9) & 1); }
 __host__ __device__ inline int ols_meta_action(uint32_t m) { return (int)(m & 0xff); }
 __host__ __device__ inline int ols_meta_terminal(uint32_t m) { return (int)((m >> 8) & 1); }
 
@@ -74,6 +76,38 @@ __host__ __device__ inline ols_u4 ols_philox4x32_10(ols_u4 ctr, uint32_t k0, uin
     ctr = n;
     k0 += W0;
     k1 += W1;
+  }
+  return ctr;
+}
+
+// The ten round keys of Philox4x32-10 depend on the seed only: the host computes them once per launch and
+// passes them as a kernel parameter, so the device reads them as constant-bank operands.
+struct ols_philox_keys {
+  uint32_t k0[10], k1[10];
+};
+inline ols_philox_keys ols_philox_make_keys(uint64_t seed) {
+  ols_philox_keys K;
+  uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+  for (int i = 0; i < 10; ++i) {
+    K.k0[i] = a;
+    K.k1[i] = b;
+    a += 0x9E3779B9u;
+    b += 0xBB67AE85u;
+  }
+  return K;
+}
+__device__ __forceinline__ ols_u4 ols_philox4x32_10_keyed(ols_u4 ctr, const ols_philox_keys& K) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint64_t p0 = (uint64_t)M0 * ctr.x;  // one IMAD.WIDE each
+    const uint64_t p1 = (uint64_t)M1 * ctr.z;
+    ols_u4 n;
+    n.x = (uint32_t)(p1 >> 32) ^ ctr.y ^ K.k0[i];
+    n.y = (uint32_t)p1;
+    n.z = (uint32_t)(p0 >> 32) ^ ctr.w ^ K.k1[i];
+    n.w = (uint32_t)p0;
+    ctr = n;
   }
   return ctr;
 }

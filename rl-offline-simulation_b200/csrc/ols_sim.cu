@@ -40,17 +40,12 @@ __global__ void __launch_bounds__(kThreads) reset_kernel(ols_queues_t q, ols_rep
   const int64_t n = R.n_replicas;
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
     if (mask && !mask[r]) continue;
-    Rep s;
-    blank_rep(s);
-    s.init_cursor = R.init_cursor[r];
-    s.cur_z = R.cur_z[r];
-    s.cur_s = R.cur_s[r];
-    s.status = R.status[r];
-    reset_one(q, R, r, s);
-    R.init_cursor[r] = s.init_cursor;
-    R.cur_z[r] = s.cur_z;
-    R.cur_s[r] = s.cur_s;
-    R.status[r] = s.status;
+    int ic = R.init_cursor[r], z = R.cur_z[r], s = R.cur_s[r];
+    const bool ok = reset_one(q, R, (uint64_t)(R.replica_id0 + r), ic, z, s);
+    R.init_cursor[r] = ic;
+    R.cur_z[r] = z;
+    R.cur_s[r] = s;
+    R.status[r] = ok ? OLS_RUNNING : OLS_INIT_EMPTY;
     R.ep_open[r] = 0;
   }
 }
@@ -76,15 +71,6 @@ int check_sim(const ols_queues_t* q, const ols_replicas_t* r, const char* who) {
 
 bool valid_lanes(int g) { return g == 1 || g == 2 || g == 4 || g == 8 || g == 16 || g == 32; }
 
-// Persistent grid: enough CTAs for every lane group, capped at 8 CTAs (2048 threads) per SM.
-int sim_grid(int64_t n_replicas, int lanes) {
-  int64_t warps = (n_replicas * lanes + 31) / 32;
-  int64_t blocks = (warps * 32 + kThreads - 1) / kThreads;
-  int64_t cap = (int64_t)OLS_SM_COUNT * 8;
-  if (blocks > cap) blocks = cap;
-  return (int)(blocks < 1 ? 1 : blocks);
-}
-
 inline int align16(int64_t x) { return (int)((x + 15) / 16 * 16); }
 
 // Shared-memory staging: each lane group of a CTA gets one slot for its replica's cursor table and,
@@ -93,7 +79,7 @@ StagePlan make_stage_plan(const ols_queues_t* q, const ols_run_t* c) {
   StagePlan p = {0, 0, 0};
   if (!c->stage_smem) return p;
   const int groups = kThreads / c->lanes;
-  const int64_t budget = 96 * 1024;
+  const int64_t budget = 96 * 1024 - (int64_t)sizeof(Cold) * groups;
   const int64_t cb = align16((int64_t)q->n_buckets * 4);
   const int64_t qb = (c->agent == OLS_AGENT_FIXED_PI)
                          ? 0
@@ -147,7 +133,7 @@ extern "C" int ols_step(const ols_queues_t* q, const ols_replicas_t* r, const ui
               OLS_ERR_INVALID, "ols_step: null p_new / output buffer");
   OLS_REQUIRE(p_stride == 0 || p_stride >= q->n_actions, OLS_ERR_INVALID, "ols_step: p_stride must be 0 or >= n_actions");
   OLS_REQUIRE(q->order && q->records, OLS_ERR_INVALID, "ols_step: queues not bucketed");
-  const int grid = sim_grid(r->n_replicas, lanes);
+  const int grid = (int)((r->n_replicas * lanes + kThreads - 1) / kThreads);  // one lane group per replica
   cudaError_t e;
   switch ((q->n_actions + 3) / 4) {
     case 1: e = ols_launch_step_nv1(*q, *r, mask, p_new, p_new_is_f64, p_stride, reject_mode, compute_mode, lanes, *out, grid, (cudaStream_t)stream); break;
@@ -184,7 +170,8 @@ extern "C" int ols_run(const ols_queues_t* q, const ols_replicas_t* r, const ols
   RunLaunch L;
   L.grid = (int)((r->n_replicas * c->lanes + kThreads - 1) / kThreads);  // one lane group per replica, no grid-stride loop
   L.plan = make_stage_plan(q, c);
-  L.smem = (size_t)L.plan.slot_bytes * (kThreads / c->lanes);
+  L.smem = (sizeof(Cold) + (size_t)L.plan.slot_bytes) * (kThreads / c->lanes);
+  L.keys = ols_philox_make_keys(r->seed);
   L.stream = (cudaStream_t)stream;
   int ppl = c->pops_per_lane;
   if (ppl == 0) ppl = (r->rng_mode == OLS_RNG_PCG64 || c->reject_mode == OLS_REJECT_ACCEPT_ALL) ? 1 : 2;
