@@ -179,7 +179,8 @@ typedef struct ols_run {
                                  when it fits; 0: operate on global memory                       */
   int32_t pops_per_lane;      /* records each lane examines per round: 1, 2, or 0 = auto (2 with
                                  Philox/fed uniforms, 1 with PCG64 replay)                       */
-  int32_t _pad;
+  int32_t prefetch;           /* rounds ahead whose records are prefetched into L2 (0 = off; useful for
+                                 long reject chains, i.e. lanes >= 16)                           */
   int64_t max_steps;          /* > 0: every replica stops after this many accepted transitions in
                                  THIS call and stays resumable (not in the reference)            */
   double gamma;

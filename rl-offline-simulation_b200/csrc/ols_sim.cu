@@ -56,6 +56,7 @@ int check_sim(const ols_queues_t* q, const ols_replicas_t* r, const char* who) {
               who, OLS_MAX_ACTIONS);
   OLS_REQUIRE(q->rec_bytes == ols_record_bytes(q->n_actions), OLS_ERR_INVALID, "%s: bad rec_bytes", who);
   OLS_REQUIRE(q->n_buckets >= 1 && q->offsets, OLS_ERR_INVALID, "%s: bad queues", who);
+  OLS_REQUIRE((uintptr_t)q->records % 32 == 0, OLS_ERR_INVALID, "%s: records must be 32-byte aligned", who);
   OLS_REQUIRE(r->n_replicas >= 0, OLS_ERR_INVALID, "%s: negative n_replicas", who);
   if (r->n_replicas == 0) return OLS_OK;
   OLS_REQUIRE(r->cursor && r->init_cursor && r->cur_z && r->cur_s && r->status && r->draws && r->ties && r->pops &&

@@ -196,6 +196,12 @@ __device__ __forceinline__ bool load_bucket(const ols_queues_t& q, const ols_rep
 // The exact float64 entries are only needed when the filter is undecided; they are re-derived there by
 // the caller-supplied functor (epsilon-greedy: from eps and a*, fixed policies: re-read from the table).
 
+__device__ __forceinline__ void load_record32(const float4* rp, float4& p, float4& tail) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(p.x), "=f"(p.y), "=f"(p.z), "=f"(p.w), "=f"(tail.x), "=f"(tail.y), "=f"(tail.z), "=f"(tail.w)
+               : "l"(rp));
+}
+
 // Return codes of pop_round besides the OLS_* statuses
 constexpr int kPopIdle = -1;      // the group did not take part in this round
 constexpr int kPopContinue = -2;  // every record examined was rejected; the queue is not exhausted yet
@@ -210,7 +216,7 @@ __device__ __forceinline__ int pop_round(const ols_queues_t& q, const ols_replic
                                          unsigned gmask, bool active, int64_t r, uint64_t rid, const Policy<4 * NV>& P,
                                          PnFn pn_fn, const ols_philox_keys& PK, int reject_mode, int compute_mode, Bucket& B,
                                          uint64_t& draws, uint32_t& n_pop, ols_u128& pcg_s, const ols_u128& pcg_inc,
-                                         float4& win_tail, int32_t& win_slot) {
+                                         float4& win_tail, int32_t& win_slot, int prefetch = 0) {
   constexpr int NA = 4 * NV;
   static_assert(RNG != RNGT_PCG64 || PPL == 1, "PCG64 replay is sequential per lane group: one pop per lane");
   typedef typename std::conditional<RNG == RNGT_PHILOX, float, double>::type ustore_t;
@@ -242,9 +248,29 @@ __device__ __forceinline__ int pop_round(const ols_queues_t& q, const ols_replic
       uint32_t pos = B.start + (uint32_t)B.cur + (uint32_t)k;
       if (pos >= (uint32_t)B.len) pos -= (uint32_t)B.len;
       const float4* rp = (const float4*)((const char*)q.records + (size_t)(B.lo + (int32_t)pos) * q.rec_bytes);
+      if (NV == 1) {
+        // a 4-action record is 32 bytes, 32-byte aligned: one 256-bit load (LDG.E.256, new with sm_100) instead of
+        // two 128-bit ones halves the L1 wavefronts of the gather
+        load_record32(rp, pv[i][0], tail[i]);
+      } else {
 #pragma unroll
-      for (int v = 0; v < NV; ++v) pv[i][v] = __ldg(rp + v);
-      tail[i] = __ldg(rp + NV);
+        for (int v = 0; v < NV; ++v) pv[i][v] = __ldg(rp + v);
+        tail[i] = __ldg(rp + NV);
+      }
+    }
+  }
+  // ---- long reject chains: pull the records this lane would examine `prefetch` rounds ahead into L2 now, so that
+  // those rounds' loads are L2 hits (no registers held, unlike a software-pipelined load)
+  if (prefetch > 0) {
+    const int kp = k0 + prefetch * G * PPL;
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) {
+      if (kp + i >= 0 && kp + i < remaining && active) {
+        uint32_t pos = B.start + (uint32_t)B.cur + (uint32_t)(kp + i);
+        if (pos >= (uint32_t)B.len) pos -= (uint32_t)B.len;
+        const char* rp = (const char*)q.records + (size_t)(B.lo + (int32_t)pos) * q.rec_bytes;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
+      }
     }
   }
   // ---- uniforms of this lane's pops
@@ -731,7 +757,7 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
     float4 tail = make_float4(0.f, 0.f, 0.f, 0.f);
     int32_t slot = -1;
     const int res = pop_round<NV, RNG, PPL>(q, R, G, sub, gbase, gmask, live, rr, rid, P, pn_fn, PK, cfg.reject_mode,
-                                            cfg.compute_mode, B, draws, n_pop, pcg_s, pcg_inc, tail, slot);
+                                            cfg.compute_mode, B, draws, n_pop, pcg_s, pcg_inc, tail, slot, cfg.prefetch);
     // ---- learner update and episode bookkeeping for the groups whose round ended the step
     if (live && res != kPopContinue) {
       cur_tab[B.b] = B.cur;  // every lane of the group stores the same value and later re-reads its own store

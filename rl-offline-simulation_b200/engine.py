@@ -208,7 +208,7 @@ class BatchedPSRS:
     def __init__(self, log: BucketedLog, n_replicas: int, rng: str = "philox", seed: Optional[int] = 0,
                  seeds=None, u_feed=None, tie_feed=None, reject: str = "default", ring: bool = False,
                  ring_seed: int = 0, replica_id0: int = 0, lanes: int = 4, pops_per_lane: int = 0,
-                 stage_smem: bool = True):
+                 stage_smem: bool = True, prefetch: int = -1):
         self.lib = abi.load()
         self.log = log
         dev = log.device
@@ -219,6 +219,7 @@ class BatchedPSRS:
         self.lanes = 1 if self.reject_mode == abi.REJECT_ACCEPT_ALL else int(lanes)
         self.pops_per_lane = int(pops_per_lane)     # 0 = auto (2 with Philox / fed uniforms)
         self.stage_smem = bool(stage_smem)          # stage cursor table (+Q) in shared memory when it fits
+        self.prefetch = int(prefetch)               # rounds ahead prefetched into L2 (-1 = auto: 1 when lanes >= 16)
         self.rng_mode = {"feed": abi.RNG_FEED, "pcg64": abi.RNG_PCG64, "philox": abi.RNG_PHILOX}[rng]
         if seed is None:
             seed = secrets.randbits(63)           # psrs.py:13 — default_rng(None) draws OS entropy
@@ -361,7 +362,8 @@ class BatchedPSRS:
                           pi_is_f64=pi_is_f64, reject_mode=self.reject_mode,
                           compute_mode=abi.COMPUTE_F32 if compute == "f32" else abi.COMPUTE_F64, lanes=self.lanes,
                           n_episodes=int(n_episodes), ep_cap=ep_cap, stage_smem=int(self.stage_smem),
-                          pops_per_lane=0 if self.rng_mode == abi.RNG_PCG64 else self.pops_per_lane, _pad=0,
+                          pops_per_lane=0 if self.rng_mode == abi.RNG_PCG64 else self.pops_per_lane,
+                          prefetch=self.prefetch if self.prefetch >= 0 else (1 if self.lanes >= 16 else 0),
                           max_steps=int(max_steps),
                           gamma=float(gamma), alpha=_ptr(a_t), epsilon=_ptr(e_t), pi=_ptr(pi_t), Q=_ptr(Q), Gs=_ptr(Gs),
                           lengths=_ptr(lengths), trace_row=_ptr(trace_row), td_error=_ptr(td), trace_cap=int(trace_cap))
