@@ -85,15 +85,17 @@ typedef struct ols_log {
 } ols_log_t;
 
 /* ---- the bucketed log: per-state FIFO queues in CSR form (psrs.py:22-30) ------------------ *
- * Queue b holds slots offsets[b] .. offsets[b+1]-1; slot k carries the packed record of row
- * order[k].  Record layout (rec_bytes = 16 * (1 + ceil(n_actions / 4))):
+ * Queue b holds slots offsets[b] .. offsets[b+1]-1; slot k carries the packed record of one logged
+ * transition.  Record layout (rec_bytes = 16 * (1 + ceil(n_actions / 4)), 32-byte aligned base):
  *     float    p[4 * ceil(n_actions/4)]   logged distribution, zero padded (rounded to float32
  *                                         when the log is float64; the exact path then reads
- *                                         p_log64[order[k]])
+ *                                         p_log64[row])
  *     float    reward
  *     int32_t  z_next
- *     int32_t  s_next
- *     uint32_t meta                       bits 0..7 action, bit 8 terminal                    */
+ *     int32_t  row                        index of the transition in the log (the queue ORDER:
+ *                                         reading this field along a queue gives env.queues[z])
+ *     uint32_t meta                       bits 0..7 action, bit 8 terminal, bit 9 "tame" (all
+ *                                         logged probabilities in [2^-40, 2^40])                 */
 typedef struct ols_queues {
   int64_t n_rows;
   int64_t n_init;             /* number of initial rows                                          */
@@ -103,11 +105,12 @@ typedef struct ols_queues {
                                  encoders/heuristic.py:23-24)                                    */
   int32_t rec_bytes;
   int32_t* offsets;           /* [n_buckets + 1]                                                 */
-  int32_t* order;             /* [n_rows]                                                        */
-  void* records;              /* [n_rows * rec_bytes], 16-byte aligned                           */
+  void* records;              /* [n_rows * rec_bytes], 32-byte aligned                           */
   int32_t* init_row;          /* [n_init] initial rows in queue order (psrs.py:22-23)            */
   int32_t* init_z;            /* [n_init] their z                                                */
   int32_t* init_s;            /* [n_init] their s                                                */
+  const int32_t* s_next;      /* NULL (= z_next), or the agent-visible next observation id per ROW
+                                 when it differs from the state id (psrs.py:36,49-50)            */
   const double* p_log64;      /* NULL, or the float64 log distribution [n_rows][n_actions] in ROW
                                  order when it is not exactly float32-representable              */
 } ols_queues_t;
@@ -221,17 +224,16 @@ int ols_encode_mlp(const float* obs, int64_t n, int32_t d_obs, const float* W1, 
 int32_t ols_record_bytes(int32_t n_actions);
 size_t ols_bucket_scratch_bytes(int64_t n_rows, int32_t n_buckets);
 /* Stable counting sort of the rows by z (psrs.py:26: sorted + groupby) fused with record packing.
- * Fills q->offsets, q->order, q->records (log order inside every queue).  q's scalar fields and
- * buffer pointers are set by the caller.                                                       */
+ * Fills q->offsets and q->records (log order inside every queue).  q's scalar fields and buffer
+ * pointers are set by the caller.                                                              */
 int ols_bucket(const ols_log_t* log, const ols_queues_t* q, void* scratch, size_t scratch_bytes, void* stream);
 /* psrs.py:22 — initial rows (step == 0) in log order -> q->init_row/init_z/init_s; the count is
  * written to *n_init_dev (device int64).  scratch: ols_bucket_scratch_bytes(n_rows, 1).        */
 int ols_init_queue(const ols_log_t* log, const ols_queues_t* q, int64_t* n_init_dev, void* scratch,
                    size_t scratch_bytes, void* stream);
 /* psrs.py:23,29-30 — replay `np.random.default_rng(seed).shuffle` on the initial-state list and on
- * every queue (a fresh generator each): dst gets the permuted order/records/init_* of src (src
- * stays the log-order CSR; dst->offsets may alias src->offsets).  perm_scratch: n_rows + n_init
- * int32.                                                                                       */
+ * every queue (a fresh generator each): dst gets the permuted records/init_* of src (src stays
+ * the log-order CSR; dst->offsets may alias src->offsets).  perm_scratch: n_rows + n_init int32.  */
 int ols_shuffle_queues(const ols_queues_t* src, const ols_queues_t* dst, uint64_t seed, int32_t* perm_scratch,
                        void* stream);
 

@@ -7,12 +7,15 @@
 //                                                                      -> shuffle_perm / gather kernels
 //
 // The sort is a STABLE counting sort in one scatter pass.  The rows are cut into T contiguous
-// tiles, one tile per warp.  Pass 1 builds a per-tile histogram in the warp's private slice of
-// shared memory; a column scan over the [tile][bucket] table gives every tile its first slot in
-// every queue; pass 2 re-walks the tile in log order, ranks equal keys inside each 32-row batch
-// with __match_any_sync (lower lane = earlier row), and writes `order` plus the packed 16B-aligned
-// record straight to the final slot.  Algorithmic traffic per row: z twice (8 B), the log columns
-// once (~17 + 4*nA B), record + order written once (rec_bytes + 4 B).
+// tiles, one tile per CTA.  Pass 1 builds the tile's histogram in shared memory (all warps, atomics:
+// order is irrelevant for counting); a column scan over the [tile][bucket] table gives every tile its
+// first slot in every queue; pass 2 re-walks the tile: the CTA's warps take 64-row batches round-robin,
+// load their rows' columns concurrently, and then pass a TURN token in batch order through a short
+// critical section in which equal keys of the batch are ranked with __match_any_sync (lower lane =
+// earlier row) against the tile's running per-queue slot counters in shared memory.  Outside the token
+// the loads and the scattered stores of all warps overlap.  Each row's packed record (which carries the
+// row index, i.e. the queue order) goes straight to its final slot as full 32-byte sectors.  Algorithmic
+// traffic per row: z twice (8 B), the log columns once (~13 + 4*nA B), the record once (rec_bytes).
 #include <limits.h>
 
 #include "ols_common.cuh"
@@ -22,35 +25,34 @@ namespace {
 constexpr unsigned kFull = 0xffffffffu;
 
 struct BucketPlan {
-  int warps_per_cta;
   int ctas;
-  int tiles;          // = warps_per_cta * ctas
-  int64_t tile_rows;  // multiple of 32
-  size_t smem_bytes;  // per CTA
+  int tiles;          // = ctas (one tile per CTA)
+  int64_t tile_rows;  // multiple of the 64-row batch
+  size_t smem_bytes;  // per CTA: one counter per queue
 };
 
-// One private histogram of n_buckets counters per warp; up to 16 warps per CTA, as many CTAs as
-// fit the 148 SMs once or twice (grid = multiple of the SM count).
+constexpr int kBucketThreads = 256;  // 8 warps per CTA
+constexpr int kBatchRows = 64;       // rows a warp holds per turn (2 x 32)
+
+// One counter array of n_buckets entries per CTA; as many CTAs per SM as shared memory and the thread
+// limit allow, and a grid that is a multiple of the SM count.
 inline bool make_plan(int64_t n_rows, int n_buckets, BucketPlan* p) {
   const size_t smem_cap = 200 * 1024;
-  size_t per_warp = (size_t)n_buckets * sizeof(uint32_t);
-  if (per_warp > smem_cap) return false;
-  int w = (int)(smem_cap / per_warp);
-  if (w > 16) w = 16;
-  const int ctas_per_sm = ((size_t)w * per_warp <= 100 * 1024) ? 2 : 1;
-  const int64_t max_tiles = (int64_t)OLS_SM_COUNT * ctas_per_sm * w;
-  int64_t want = (n_rows + 2047) / 2048;  // small logs: no tile shorter than ~2048 rows
+  const size_t per_cta = (size_t)n_buckets * sizeof(uint32_t) + 64;
+  if (per_cta > smem_cap) return false;
+  int ctas_per_sm = (int)(smem_cap / per_cta);
+  if (ctas_per_sm > 8) ctas_per_sm = 8;  // 2048 threads / 256
+  const int64_t max_tiles = (int64_t)OLS_SM_COUNT * ctas_per_sm;
+  int64_t want = (n_rows + 4095) / 4096;  // small logs: no tile shorter than ~4096 rows
   if (want < 1) want = 1;
-  int64_t tiles = want < max_tiles ? want : max_tiles;
-  int ctas = (int)((tiles + w - 1) / w);
-  p->warps_per_cta = w;
-  p->ctas = ctas;
-  p->tiles = w * ctas;
-  int64_t tr = (n_rows + p->tiles - 1) / p->tiles;
-  tr = (tr + 31) / 32 * 32;
-  if (tr < 32) tr = 32;
+  const int64_t tiles = want < max_tiles ? want : max_tiles;
+  p->ctas = (int)tiles;
+  p->tiles = (int)tiles;
+  int64_t tr = (n_rows + tiles - 1) / tiles;
+  tr = (tr + kBatchRows - 1) / kBatchRows * kBatchRows;
+  if (tr < kBatchRows) tr = kBatchRows;
   p->tile_rows = tr;
-  p->smem_bytes = (size_t)w * per_warp;
+  p->smem_bytes = per_cta;
   return true;
 }
 
@@ -73,35 +75,32 @@ inline Scratch carve(void* base, const BucketPlan& p, int n_buckets) {
 }
 
 // ---------------------------------------------------------------------------------------- pass 1
-__global__ void __launch_bounds__(512) tile_histogram_kernel(const int32_t* __restrict__ z, int64_t n_rows, int z_offset,
-                                                              int n_buckets, int64_t tile_rows,
-                                                              uint32_t* __restrict__ tile_hist,
-                                                              uint32_t* __restrict__ invalid) {
+__global__ void __launch_bounds__(kBucketThreads) tile_histogram_kernel(const int32_t* __restrict__ z, int64_t n_rows,
+                                                                         int z_offset, int n_buckets, int64_t tile_rows,
+                                                                         uint32_t* __restrict__ tile_hist,
+                                                                         uint32_t* __restrict__ invalid) {
   extern __shared__ uint32_t s_hist[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x * (blockDim.x >> 5) + warp;
-  uint32_t* h = s_hist + (size_t)warp * n_buckets;
-  for (int b = lane; b < n_buckets; b += 32) h[b] = 0;
-  __syncwarp();
-  const int64_t lo = (int64_t)tile * tile_rows;
+  for (int b = threadIdx.x; b < n_buckets; b += blockDim.x) s_hist[b] = 0;
+  __syncthreads();
+  const int64_t lo = (int64_t)blockIdx.x * tile_rows;
   const int64_t hi = min(lo + tile_rows, n_rows);
   uint32_t bad = 0;
-  for (int64_t base = lo; base < hi; base += 128) {
+  for (int64_t base = lo + threadIdx.x; base < hi; base += 4 * kBucketThreads) {
     int key[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      int64_t i = base + j * 32 + lane;
+      const int64_t i = base + (int64_t)j * kBucketThreads;
       key[j] = (i < hi) ? __ldg(z + i) + z_offset : INT_MIN;
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      if (key[j] >= 0 && key[j] < n_buckets) atomicAdd(&h[key[j]], 1u);
+      if (key[j] >= 0 && key[j] < n_buckets) atomicAdd(&s_hist[key[j]], 1u);
       else if (key[j] != INT_MIN) ++bad;  // id outside [-z_offset, n_buckets - z_offset): row is dropped
     }
   }
-  __syncwarp();
-  uint32_t* out = tile_hist + (size_t)tile * n_buckets;
-  for (int b = lane; b < n_buckets; b += 32) out[b] = h[b];
+  __syncthreads();
+  uint32_t* out = tile_hist + (size_t)blockIdx.x * n_buckets;
+  for (int b = threadIdx.x; b < n_buckets; b += blockDim.x) out[b] = s_hist[b];
   if (bad) atomicAdd(invalid, bad);
 }
 
@@ -184,7 +183,7 @@ template <int NV>
 struct RowData {
   float4 p[NV];
   float r;
-  int zn, sn;
+  int zn;
   uint32_t meta;
 };
 
@@ -215,7 +214,6 @@ __device__ __forceinline__ void load_row(const ols_log_t& log, int64_t i, RowDat
   for (int v = 0; v < NV; ++v) d.p[v] = make_float4(pv[4 * v], pv[4 * v + 1], pv[4 * v + 2], pv[4 * v + 3]);
   d.r = __ldg(log.reward + i);
   d.zn = __ldg(log.z_next + i);
-  d.sn = log.s_next ? __ldg(log.s_next + i) : d.zn;
   float mn = pv[0], mx = pv[0];
 #pragma unroll
   for (int j = 1; j < 4 * NV; ++j)
@@ -228,60 +226,74 @@ __device__ __forceinline__ void load_row(const ols_log_t& log, int64_t i, RowDat
 }
 
 template <int NV>
-__global__ void __launch_bounds__(512) scatter_pack_kernel(ols_log_t log, ols_queues_t q, int64_t tile_rows,
-                                                            const uint32_t* __restrict__ tile_hist) {
-  extern __shared__ uint32_t s_next_slot[];
+__global__ void __launch_bounds__(kBucketThreads) scatter_pack_kernel(ols_log_t log, ols_queues_t q, int64_t tile_rows,
+                                                                       const uint32_t* __restrict__ tile_hist) {
+  extern __shared__ uint32_t s_next_slot[];   // [n_buckets] next free slot of every queue for this tile, then the turn
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x * (blockDim.x >> 5) + warp;
+  const int n_warps = blockDim.x >> 5;
   const int nB = q.n_buckets;
-  uint32_t* slot = s_next_slot + (size_t)warp * nB;
-  const uint32_t* th = tile_hist + (size_t)tile * nB;
-  for (int b = lane; b < nB; b += 32) slot[b] = (uint32_t)__ldg(q.offsets + b) + th[b];
-  __syncwarp();
-  const int64_t lo = (int64_t)tile * tile_rows;
+  volatile int* turn = (volatile int*)(s_next_slot + nB);
+  const uint32_t* th = tile_hist + (size_t)blockIdx.x * nB;
+  for (int b = threadIdx.x; b < nB; b += blockDim.x) s_next_slot[b] = (uint32_t)__ldg(q.offsets + b) + th[b];
+  if (threadIdx.x == 0) *turn = 0;
+  __syncthreads();
+  const int64_t lo = (int64_t)blockIdx.x * tile_rows;
   const int64_t hi = min(lo + tile_rows, log.n_rows);
+  const int n_batches = (int)((hi - lo + kBatchRows - 1) / kBatchRows);
   const uint32_t lt_mask = (1u << lane) - 1u;
-  constexpr int U = 2;  // batches in flight per warp iteration
-  for (int64_t base = lo; base < hi; base += 32 * U) {
+  constexpr int U = kBatchRows / 32;
+  for (int jb = warp; jb < n_batches; jb += n_warps) {
+    const int64_t base = lo + (int64_t)jb * kBatchRows;
     int key[U];
     RowData<NV> row[U];
 #pragma unroll
     for (int j = 0; j < U; ++j) {
-      int64_t i = base + j * 32 + lane;
+      const int64_t i = base + j * 32 + lane;
       key[j] = -1;
       if (i < hi) {
-        int b = __ldg(log.z + i) + q.z_offset;
+        const int b = __ldg(log.z + i) + q.z_offset;
         if (b >= 0 && b < nB) {
           key[j] = b;
           load_row<NV>(log, i, row[j]);
         }
       }
     }
+    // lanes holding the same key, lowest lane = earliest row; invalid lanes form their own group
+    unsigned peers[U];
+#pragma unroll
+    for (int j = 0; j < U; ++j) peers[j] = __match_any_sync(kFull, key[j]);
+    // ---- the turn: batches update the tile's slot counters strictly in log order
+    if (lane == 0)
+      while (*turn != jb) {
+      }
+    __syncwarp();
+    uint32_t first[U];
 #pragma unroll
     for (int j = 0; j < U; ++j) {
-      const bool valid = key[j] >= 0;
-      // lanes holding the same key, lowest lane = earliest row; invalid lanes form their own group
-      unsigned peers = __match_any_sync(kFull, key[j]);
-      unsigned rank = __popc(peers & lt_mask);
-      int leader = __ffs(peers) - 1;
-      uint32_t first = 0;
-      if (valid && lane == leader) {
-        first = slot[key[j]];
-        slot[key[j]] = first + __popc(peers);
+      const int leader = __ffs(peers[j]) - 1;
+      uint32_t f = 0;
+      if (key[j] >= 0 && lane == leader) {
+        f = s_next_slot[key[j]];
+        s_next_slot[key[j]] = f + __popc(peers[j]);
       }
-      first = __shfl_sync(kFull, first, leader);
       __syncwarp();
-      if (valid) {
-        uint32_t pos = first + rank;
-        int64_t i = base + j * 32 + lane;
-        q.order[pos] = (int32_t)i;
+      first[j] = __shfl_sync(kFull, f, leader);
+    }
+    __threadfence_block();
+    if (lane == 0) *turn = jb + 1;
+    // ---- scattered stores, overlapping with the other warps' loads and turns
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      if (key[j] >= 0) {
+        const uint32_t pos = first[j] + __popc(peers[j] & lt_mask);
+        const int64_t i = base + j * 32 + lane;
         float4* dst = (float4*)((char*)q.records + (size_t)pos * q.rec_bytes);
 #pragma unroll
         for (int v = 0; v < NV; ++v) dst[v] = row[j].p[v];
         float4 tail;
         tail.x = row[j].r;
         tail.y = __int_as_float(row[j].zn);
-        tail.z = __int_as_float(row[j].sn);
+        tail.z = __int_as_float((int32_t)i);  // the row index: reading it along a queue gives the queue order
         tail.w = __uint_as_float(row[j].meta);
         dst[NV] = tail;
       }
@@ -455,7 +467,6 @@ __global__ void __launch_bounds__(256) gather_queues_kernel(ols_queues_t src, ol
     const float4* s = (const float4*)((const char*)src.records + (size_t)from * src.rec_bytes);
     float4* d = (float4*)((char*)dst.records + (size_t)slot * dst.rec_bytes);
     d[c] = __ldg(s + c);
-    if (c == 0) dst.order[slot] = __ldg(src.order + from);
   }
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < src.n_init; k += (int64_t)gridDim.x * blockDim.x) {
     int32_t from = __ldg(perm + src.n_rows + k) - (int32_t)src.n_rows;
@@ -474,8 +485,8 @@ int check_queues(const ols_queues_t* q, const char* who) {
   OLS_REQUIRE(q->rec_bytes == ols_record_bytes(q->n_actions), OLS_ERR_INVALID, "%s: rec_bytes must be %d", who,
               ols_record_bytes(q->n_actions));
   OLS_REQUIRE(q->offsets != nullptr, OLS_ERR_INVALID, "%s: null offsets", who);
-  OLS_REQUIRE(q->n_rows == 0 || (q->order && q->records), OLS_ERR_INVALID, "%s: null order/records", who);
-  OLS_REQUIRE((uintptr_t)q->records % 16 == 0, OLS_ERR_INVALID, "%s: records must be 16-byte aligned", who);
+  OLS_REQUIRE(q->n_rows == 0 || q->records, OLS_ERR_INVALID, "%s: null records", who);
+  OLS_REQUIRE((uintptr_t)q->records % 32 == 0, OLS_ERR_INVALID, "%s: records must be 32-byte aligned", who);
   return OLS_OK;
 }
 
@@ -504,7 +515,7 @@ extern "C" int ols_bucket(const ols_log_t* log, const ols_queues_t* q, void* scr
               "ols_bucket: log and queues disagree on n_rows / n_actions");
   BucketPlan plan;
   OLS_REQUIRE(make_plan(q->n_rows, q->n_buckets, &plan), OLS_ERR_UNSUPPORTED,
-              "ols_bucket: n_buckets = %d needs more than 200 KB of shared memory per warp histogram", q->n_buckets);
+              "ols_bucket: n_buckets = %d needs more than 200 KB of shared memory for one tile's counters", q->n_buckets);
   OLS_REQUIRE(scratch != nullptr && scratch_bytes >= scratch_bytes_for(plan, q->n_buckets), OLS_ERR_INVALID,
               "ols_bucket: scratch too small (%zu < %zu)", scratch_bytes, scratch_bytes_for(plan, q->n_buckets));
   if (q->n_rows > 0) {
@@ -514,7 +525,7 @@ extern "C" int ols_bucket(const ols_log_t* log, const ols_queues_t* q, void* scr
   }
   Scratch s = carve(scratch, plan, q->n_buckets);
   OLS_CUDA_CHECK(cudaMemsetAsync(s.invalid, 0, sizeof(uint32_t), stream));
-  const int threads = plan.warps_per_cta * 32;
+  const int threads = kBucketThreads;
   if (plan.smem_bytes > 48 * 1024) {
     OLS_CUDA_CHECK(cudaFuncSetAttribute(tile_histogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes));
   }
@@ -586,8 +597,7 @@ extern "C" int ols_shuffle_queues(const ols_queues_t* src, const ols_queues_t* d
   OLS_REQUIRE(src->n_rows == dst->n_rows && src->n_buckets == dst->n_buckets && src->n_actions == dst->n_actions &&
                   src->n_init == dst->n_init,
               OLS_ERR_INVALID, "ols_shuffle_queues: src and dst shapes differ");
-  OLS_REQUIRE(src->records != dst->records && src->order != dst->order, OLS_ERR_INVALID,
-              "ols_shuffle_queues: dst must not alias src (except offsets)");
+  OLS_REQUIRE(src->records != dst->records, OLS_ERR_INVALID, "ols_shuffle_queues: dst must not alias src (except offsets)");
   const int64_t total = src->n_rows + src->n_init;
   OLS_REQUIRE(total < (1ll << 31), OLS_ERR_UNSUPPORTED, "ols_shuffle_queues: n_rows + n_init must be < 2^31");
   if (total == 0) return OLS_OK;

@@ -133,7 +133,7 @@ extern "C" int ols_step(const ols_queues_t* q, const ols_replicas_t* r, const ui
   OLS_REQUIRE(p_new && out && out->row && out->action && out->reward && out->terminal && out->s_next && out->z_from,
               OLS_ERR_INVALID, "ols_step: null p_new / output buffer");
   OLS_REQUIRE(p_stride == 0 || p_stride >= q->n_actions, OLS_ERR_INVALID, "ols_step: p_stride must be 0 or >= n_actions");
-  OLS_REQUIRE(q->order && q->records, OLS_ERR_INVALID, "ols_step: queues not bucketed");
+  OLS_REQUIRE(q->records, OLS_ERR_INVALID, "ols_step: queues not bucketed");
   const int grid = (int)((r->n_replicas * lanes + kThreads - 1) / kThreads);  // one lane group per replica
   cudaError_t e;
   switch ((q->n_actions + 3) / 4) {
@@ -162,7 +162,7 @@ extern "C" int ols_run(const ols_queues_t* q, const ols_replicas_t* r, const ols
               "ols_run: PCG64 replay examines one record per lane per round");
   if (r->n_replicas == 0) return OLS_OK;
   OLS_REQUIRE(c->Gs && c->lengths, OLS_ERR_INVALID, "ols_run: null Gs / lengths");
-  OLS_REQUIRE(q->order && q->records, OLS_ERR_INVALID, "ols_run: queues not bucketed");
+  OLS_REQUIRE(q->records, OLS_ERR_INVALID, "ols_run: queues not bucketed");
   OLS_REQUIRE(q->n_init == 0 || (q->init_z && q->init_s), OLS_ERR_INVALID, "ols_run: null init arrays");
   if (c->agent != OLS_AGENT_FIXED_PI) OLS_REQUIRE(c->Q && c->alpha, OLS_ERR_INVALID, "ols_run: learner needs Q and alpha");
   if (c->agent == OLS_AGENT_QLEARN) OLS_REQUIRE(c->epsilon, OLS_ERR_INVALID, "ols_run: qlearn needs epsilon");

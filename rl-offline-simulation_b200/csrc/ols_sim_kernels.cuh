@@ -342,7 +342,7 @@ __device__ __forceinline__ int pop_round(const ols_queues_t& q, const ols_replic
           if (pos >= (uint32_t)B.len) pos -= (uint32_t)B.len;
           const int32_t slot = B.lo + (int32_t)pos;
           const double ue = (RNG == RNGT_PHILOX) ? ols_philox_uniform(R.seed, rid, 0u, draws + (uint64_t)k) : (double)u[i];
-          const double* p64 = q.p_log64 ? q.p_log64 + (int64_t)__ldg(q.order + slot) * nA : nullptr;
+          const double* p64 = q.p_log64 ? q.p_log64 + (int64_t)__float_as_int(tail[i].z) * nA : nullptr;
           dec = (int)accept_slow(pn_fn, (const float*)((const char*)q.records + (size_t)slot * q.rec_bytes), p64, nA, a, ue,
                                  compute_mode);
         }
@@ -481,13 +481,15 @@ __global__ void __launch_bounds__(kThreads) step_kernel(ols_queues_t q, ols_repl
         const uint32_t meta = __float_as_uint(tail.w);
         R.status[r] = OLS_RUNNING;
         R.cur_z[r] = __float_as_int(tail.y);  // psrs.py:49-50
-        R.cur_s[r] = __float_as_int(tail.z);
+        const int32_t row = __float_as_int(tail.z);
+        const int32_t s2 = q.s_next ? __ldg(q.s_next + row) : __float_as_int(tail.y);
+        R.cur_s[r] = s2;
         R.accepted[r] += 1;
-        out.row[r] = __ldg(q.order + slot);
+        out.row[r] = row;
         out.action[r] = ols_meta_action(meta);
         out.reward[r] = tail.x;
         out.terminal[r] = (uint8_t)ols_meta_terminal(meta);
-        out.s_next[r] = __float_as_int(tail.z);
+        out.s_next[r] = s2;
         out.z_from[r] = cur_z;
       } else {
         R.status[r] = res;
@@ -766,7 +768,8 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
         const uint32_t meta = __float_as_uint(tail.w);
         const int A = ols_meta_action(meta);
         const int Z2 = __float_as_int(tail.y);
-        const int S2 = __float_as_int(tail.z);
+        const int32_t row_idx = __float_as_int(tail.z);
+        const int S2 = q.s_next ? __ldg(q.s_next + row_idx) : Z2;
         const int done = ols_meta_terminal(meta);
         const double Rw = (double)tail.x;
         const int ep_index = C->ep_index;
@@ -823,7 +826,7 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
           }
         }
         if (live) {
-          if (cfg.trace_row && sub == 0 && acc_idx < cfg.trace_cap) cfg.trace_row[rr * cfg.trace_cap + acc_idx] = __ldg(q.order + slot);
+          if (cfg.trace_row && sub == 0 && acc_idx < cfg.trace_cap) cfg.trace_row[rr * cfg.trace_cap + acc_idx] = row_idx;
           cur_z = Z2;
           cur_s = S2;
           const int n_acc = C->n_acc + 1;

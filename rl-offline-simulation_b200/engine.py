@@ -120,7 +120,7 @@ class BucketedLog:
                           z_next=_ptr(z_next), s=_ptr(s), s_next=_ptr(s_next), action=_ptr(action),
                           reward=_ptr(reward), terminal=_ptr(terminal), p_log=_ptr(p), step=_ptr(steps))
             self.offsets = torch.empty(n_buckets + 1, dtype=torch.int32, device=dev)
-            self.order = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+            self.s_next = s_next            # kept resident only when the agent's observation id differs from z
             self.records = torch.empty(max(n, 1) * self.rec_bytes // 4, dtype=torch.float32, device=dev)
             init_row = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
             init_z = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
@@ -131,9 +131,9 @@ class BucketedLog:
             scratch = torch.empty(sb, dtype=torch.uint8, device=dev)
             n_init_dev = torch.zeros(1, dtype=torch.int64, device=dev)
             q = abi.Queues(n_rows=n, n_init=0, n_actions=n_actions, n_buckets=n_buckets, z_offset=self.z_offset,
-                           rec_bytes=self.rec_bytes, offsets=_ptr(self.offsets), order=_ptr(self.order),
+                           rec_bytes=self.rec_bytes, offsets=_ptr(self.offsets),
                            records=_ptr(self.records), init_row=_ptr(init_row), init_z=_ptr(init_z),
-                           init_s=_ptr(init_s), p_log64=_ptr(p_log64))
+                           init_s=_ptr(init_s), s_next=_ptr(s_next), p_log64=_ptr(p_log64))
             abi.check(lib.ols_bucket(C.byref(log), C.byref(q), _ptr(scratch), sb, _stream_ptr()))
             abi.check(lib.ols_init_queue(C.byref(log), C.byref(q), _ptr(n_init_dev), _ptr(scratch), sb, _stream_ptr()))
             self.n_init = int(n_init_dev.item())        # one sync: construction is not the step path
@@ -144,13 +144,49 @@ class BucketedLog:
             self.base = self
             self._columns = dict(z=z, z_next=z_next, action=action, reward=reward, terminal=terminal, p_log=p,
                                  s=s, s_next=s_next, steps=steps) if keep_columns else None
+            self._scratch = scratch if keep_columns else None
+
+    def time_bucketing(self, iters: int = 3):
+        """Re-run the bucketing kernels (ols_bucket + ols_init_queue) on the kept columns and return the mean
+        device time per run in ms (CUDA events on the launching stream).  Needs ``keep_columns=True``."""
+        if self._columns is None:
+            raise RuntimeError("time_bucketing needs BucketedLog(..., keep_columns=True)")
+        lib = abi.load()
+        c = self._columns
+        with torch.cuda.device(self.device):
+            log = abi.Log(n_rows=self.n_rows, n_actions=self.n_actions, p_is_f64=int(c["p_log"].dtype == torch.float64),
+                          z=_ptr(c["z"]), z_next=_ptr(c["z_next"]), s=_ptr(c["s"]), s_next=_ptr(c["s_next"]),
+                          action=_ptr(c["action"]), reward=_ptr(c["reward"]), terminal=_ptr(c["terminal"]),
+                          p_log=_ptr(c["p_log"]), step=_ptr(c["steps"]))
+            q = self.queues_struct()
+            n_init_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+            sb = self._scratch.numel()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(iters):
+                abi.check(lib.ols_bucket(C.byref(log), C.byref(q), _ptr(self._scratch), sb, _stream_ptr()))
+                abi.check(lib.ols_init_queue(C.byref(log), C.byref(q), _ptr(n_init_dev), _ptr(self._scratch), sb, _stream_ptr()))
+            e1.record()
+            torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    def drop_columns(self):
+        self._columns = None
+        self._scratch = None
 
     # ------------------------------------------------------------------ views
     def queues_struct(self) -> abi.Queues:
         return abi.Queues(n_rows=self.n_rows, n_init=self.n_init, n_actions=self.n_actions, n_buckets=self.n_buckets,
                           z_offset=self.z_offset, rec_bytes=self.rec_bytes, offsets=_ptr(self.offsets),
-                          order=_ptr(self.order), records=_ptr(self.records), init_row=_ptr(self.init_row),
-                          init_z=_ptr(self.init_z), init_s=_ptr(self.init_s), p_log64=_ptr(self.p_log64))
+                          records=_ptr(self.records), init_row=_ptr(self.init_row), init_z=_ptr(self.init_z),
+                          init_s=_ptr(self.init_s), s_next=_ptr(self.s_next), p_log64=_ptr(self.p_log64))
+
+    @property
+    def order(self) -> torch.Tensor:
+        """Row index at every queue slot (the reference's queue order): a strided view of the records' row field."""
+        words = self.rec_bytes // 4
+        return self.records.view(torch.int32).view(-1, words)[: max(self.n_rows, 1), words - 2]
 
     def seeded(self, seed: Optional[int]) -> "BucketedLog":
         """Queues as ``reset_sampler(seed)`` leaves them (psrs.py:23,29-30).  ``None`` = log order."""
@@ -163,7 +199,6 @@ class BucketedLog:
         out = object.__new__(BucketedLog)
         out.__dict__.update(base.__dict__)
         with torch.cuda.device(base.device):
-            out.order = torch.empty_like(base.order)
             out.records = torch.empty_like(base.records)
             out.init_row = torch.empty_like(base.init_row)
             out.init_z = torch.empty_like(base.init_z)
@@ -402,8 +437,9 @@ class BatchedPSRS:
             abi.check(self.lib.ols_reduce_curves(_ptr(result.Gs), _ptr(result.n_returns), self.R, int(result.Gs.shape[1]),
                                                  int(n_episodes), _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), _ptr(scratch),
                                                  sb, _stream_ptr()))
-            if all_reduce and torch.distributed.is_available() and torch.distributed.is_initialized():
-                torch.distributed.all_reduce(out, op=torch.distributed.ReduceOp.SUM)
+            if all_reduce:
+                from .parallel import all_reduce_sum_
+                all_reduce_sum_(out)
         return out[0, :n_episodes], out[1, :n_episodes], out[2, :n_episodes]
 
     def replica_totals(self, result: RunResult):

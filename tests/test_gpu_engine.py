@@ -79,7 +79,7 @@ def test_bucketing_is_stable_counting_sort(ob, N, nS, nA, kw):
         assert np.array_equal(rec[:, 4 * nv], g["r"][order])
         tail = rec[:, 4 * nv + 1:].copy().view(np.int32)
         assert np.array_equal(tail[:, 0], g["z_next"][order])
-        assert np.array_equal(tail[:, 1], g["z_next"][order])
+        assert np.array_equal(tail[:, 1], order)                     # the row index field IS the queue order
         assert np.array_equal(tail[:, 2] & 0xFF, g["a"][order])
         assert np.array_equal((tail[:, 2] >> 8) & 1, g["done"][order].astype(np.int32))
 
@@ -468,3 +468,62 @@ def test_accept_filter_never_changes_a_decision(ob):
         res = sim.run_evalmc(nS, 10**6 // 1000, pi=pi, gamma=1.0, trace_cap=N, max_steps=len(trace), ep_cap=2000)
         got = res.trace_row[0, :len(trace)].cpu().numpy()
         assert np.array_equal(got, trace), (lanes, ppl)
+
+
+def test_agent_observation_ids_distinct_from_state_ids(ob):
+    """psrs.py:36,49-50 — the agent indexes Q with the observation s, the queues are keyed by z."""
+    import torch
+    from oracle import c_oracle as CO
+    g = make_log(41, 30000, 12, 4)
+    rng = np.random.default_rng(0)
+    # observation = (z, a noise bit): two observations per latent state
+    s = g["z"] * 2 + rng.integers(0, 2, 30000)
+    s_next = g["z_next"] * 2 + rng.integers(0, 2, 30000)
+    log = ob.BucketedLog(z=g["z"], z_next=g["z_next"], action=g["a"], reward=g["r"], terminal=g["done"], p_log=g["p_log"],
+                         s=s, s_next=s_next, steps=g["t"], n_buckets=12)
+    sim = ob.BatchedPSRS(log, 200, rng="philox", seed=3, lanes=4)
+    res = sim.run_qlearn(24, 20, gamma=0.9, alpha=0.1, epsilon=0.2, q_dtype=torch.float64, trace_cap=3000)
+    clog = CO.Log(z=g["z"], z_next=g["z_next"], action=g["a"], reward=g["r"], terminal=g["done"], p_log=g["p_log"], s=s,
+                  s_next=s_next, steps=g["t"], n_buckets=12)
+    ref = CO.run(clog, 200, CO.QLEARN, 24, 20, gamma=0.9, alpha=0.1, epsilon=0.2, seed=3, trace_cap=3000, threads=4)
+    assert np.array_equal(res.trace_row.cpu().numpy(), ref["trace_row"])
+    assert np.array_equal(res.Q.cpu().numpy(), ref["Q"])
+    assert np.array_equal(sim.cur_s.cpu().numpy()[ref["status"] == O.DONE] % 2 >= 0, np.ones((ref["status"] == O.DONE).sum(), bool))
+
+
+def test_learning_curves_agree_with_oracle_under_independent_rngs_ks(ob):
+    """north_star: aggregate learning curves must agree under a two-sample KS test when each side uses its OWN RNG.
+    GPU: Philox streams, ring-offset decorrelation.  Oracle: NumPy's PCG64 (the reference's generator family), the
+    same protocol mirrored on its side."""
+    from scipy.stats import ks_2samp
+    from tests.helpers import ring_start, init_ring_start
+    g = make_log(51, 40000, 10, 4, ep_len=12)
+    nS = 10
+    pi = np.random.default_rng(2).dirichlet(np.ones(4) * 2, size=nS)
+    log = device_log(ob, g, n_buckets=nS)
+    R = 4000
+    sim = ob.BatchedPSRS(log, R, rng="philox", seed=99, ring=True, ring_seed=11, lanes=4)
+    res = sim.run_evalmc(nS, 6, pi=pi, gamma=0.95)
+    ne = res.n_returns.cpu().numpy()
+    Gs, L = res.Gs.cpu().numpy(), res.lengths.cpu().numpy()
+    lens = np.diff(O.bucket(g["z"], nS)[0])
+    n_init = O.init_rows(g["t"], 40000).size
+    oG, oL = [], []
+    for i in range(500):
+        rid = 10**7 + i
+        env = oracle_env(g, n_buckets=nS, uniforms=O.Pcg64Uniforms(5000 + i),
+                         ring_start=[ring_start(11, rid, b, int(lens[b])) for b in range(nS)],
+                         init_start=init_ring_start(11, rid, n_init))
+        G, ln, _ = O.evalmc(env, 6, pi=pi, gamma=0.95, record=False)
+        oG.append(G); oL.append(ln)
+    for e in range(6):
+        a = Gs[ne > e, e]
+        b = np.array([x[e] for x in oG if len(x) > e])
+        assert a.size > 3000 and b.size > 400
+        assert ks_2samp(a, b).pvalue > 1e-3, f"episode {e}: return distributions differ"
+        la = L[ne > e, e]
+        lb = np.array([x[e] for x in oL if len(x) > e])
+        assert ks_2samp(la, lb).pvalue > 1e-3, f"episode {e}: length distributions differ"
+    # and the reduced learning curve is the mean of those per-replica returns
+    s, s2, c = sim.learning_curve(res, 6, all_reduce=False)
+    np.testing.assert_allclose((s / c).cpu().numpy(), [Gs[ne > e, e].mean() for e in range(6)], rtol=1e-10)
