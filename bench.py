@@ -39,6 +39,10 @@ WORKLOADS = {
     "c2": dict(rows=1_000_000, states=162, actions=2, replicas=10_000, budget=2_000, delta=None, lanes=2,
                desc="cartpole-shaped: 1M-transition log, 162 states, 2 actions, eps-greedy Q-learning, 10k replicas"),
 }
+# DRAM bytes (read + write) per accepted transition of the fused run kernel, from the committed `ncu --set full`
+# captures (profiles/r01c_ncu_full_run_kernel_v5_*.txt): dram__bytes_read.sum + dram__bytes_write.sum divided by the
+# accepted transitions of the captured launch.  Used to report `roofline.traffic` per launch.
+NCU_DRAM_BYTES_PER_ACCEPTED = {"c4": (24.510792e9 + 2.574961e9) / 3.75e7, "c5": (78.320005e9 + 1.573043e9) / 3.2e6}
 EPS, ALPHA, GAMMA = 0.1, 0.1, 0.99
 EP_CAP = 512
 
@@ -373,7 +377,11 @@ def main():
                            N * rec_bytes / 1e9, R * nS * 4 / 1e9, (R * nS * nA * 4 / 1e9) if qlearn else 0.0)},
             "pops_per_s": pops / secs,
             "roofline": {"bound": "hbm", "kernel": "run_kernel (fused PSRS step + agent update)", "achieved": gather_gbs, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": gather_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": gather_gbs / hbm_peak,
+                         "traffic": (NCU_DRAM_BYTES_PER_ACCEPTED[args.workload] * float(sim.accepted.sum())
+                                     if args.workload in NCU_DRAM_BYTES_PER_ACCEPTED else None),
+                         "traffic_note": "DRAM read+write bytes per launch = ncu bytes per accepted transition (profiles/r01c_*) x accepted per launch",
+                         "algorithmic_bytes_per_launch": my_pops / max(1, args.steps) * rec_bytes, "peak_source": peak_src,
                          "algorithmic_bytes_per_pop": rec_bytes, "agent_state_GBps": agent_gbs, "kernel_ms": float(run_ms)},
             "bucketing": {"rows": N, "ms": bucket_ms, "GBps": bucket_bytes / bucket_ms / 1e6, "frac": bucket_bytes / bucket_ms / 1e6 / hbm_peak,
                           "note": "ols_bucket + ols_init_queue kernels; bytes = z twice + order + log columns + packed record per row"},
