@@ -87,7 +87,7 @@ typedef struct ols_log {
 /* ---- the bucketed log: per-state FIFO queues in CSR form (psrs.py:22-30) ------------------ *
  * Queue b holds slots offsets[b] .. offsets[b+1]-1; slot k carries the packed record of one logged
  * transition.  Record layout (rec_bytes = 16 * (1 + ceil(n_actions / 4)), 32-byte aligned base):
- *     float    p[4 * ceil(n_actions/4)]   logged distribution, zero padded (rounded to float32
+ *     float    p[4 * ceil(n_actions/4)]   logged distribution, padded with 1.0 (rounded to float32
  *                                         when the log is float64; the exact path then reads
  *                                         p_log64[row])
  *     float    reward

@@ -51,19 +51,23 @@ static double philox_uniform(uint64_t seed, uint64_t stream, uint32_t which, uin
   return (double)(v >> 11) * (1.0 / 9007199254740992.0);
 }
 
-static uint64_t mix64(uint64_t x) {
-  x += 0x9E3779B97F4A7C15ull;
-  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-  return x ^ (x >> 31);
+/* ring offsets (replica decorrelation): 32-bit murmur3-finaliser hashing, as documented in DESIGN.md §6 */
+static uint32_t fmix32(uint32_t h) {
+  h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
 }
+static uint32_t ring_replica_hash(uint64_t ring_seed, uint64_t replica) {
+  uint32_t h = fmix32((uint32_t)(replica >> 32));
+  h = fmix32((uint32_t)replica ^ h);
+  h = fmix32((uint32_t)(ring_seed >> 32) ^ h);
+  return fmix32((uint32_t)ring_seed ^ h);
+}
+static uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static uint32_t ring_start(uint64_t ring_seed, uint64_t replica, uint32_t bucket, uint32_t len) {
-  uint64_t h = mix64(mix64(ring_seed ^ (replica * 0xD1342543DE82EF95ull)) + bucket);
-  return (uint32_t)(((h >> 32) * (uint64_t)len) >> 32);
+  return mulhi32(fmix32(ring_replica_hash(ring_seed, replica) ^ ((bucket + 1u) * 0x9E3779B1u)), len);
 }
 static int64_t init_ring_start(uint64_t ring_seed, uint64_t replica, int64_t n_init) {
-  uint64_t h = mix64(ring_seed ^ mix64(replica + 0x51ED270B1ull));
-  return (int64_t)(((h >> 32) * (uint64_t)n_init) >> 32);
+  return (int64_t)mulhi32(fmix32(ring_replica_hash(ring_seed, replica) ^ 0x85EBCA6Bu), (uint32_t)n_init);
 }
 
 /* ------------------------------------------------------------------------------------------ bucketing */

@@ -192,7 +192,7 @@ __device__ __forceinline__ void load_row(const ols_log_t& log, int64_t i, RowDat
   const int nA = log.n_actions;
   float pv[4 * NV];
 #pragma unroll
-  for (int j = 0; j < 4 * NV; ++j) pv[j] = 0.0f;
+  for (int j = 0; j < 4 * NV; ++j) pv[j] = 1.0f;  // padding entries hold 1 (see accept_filter)
   if (log.p_is_f64) {
     const double* p = (const double*)log.p_log + i * nA;
 #pragma unroll

@@ -115,6 +115,20 @@ __device__ __forceinline__ ols_u4 ols_philox4x32_10_keyed(ols_u4 ctr, const ols_
 // 53-bit uniform in [0,1) from 64 random bits — the same mapping NumPy's Generator.random() uses.
 __host__ __device__ inline double ols_u64_to_unit(uint64_t v) { return (double)(v >> 11) * (1.0 / 9007199254740992.0); }
 
+// ols_philox_uniform (below) with host-precomputed round keys
+__device__ __forceinline__ double ols_philox_uniform_keyed(const ols_philox_keys& K, uint64_t stream_id, uint32_t which,
+                                                           uint64_t d) {
+  ols_u4 c;
+  const uint64_t blk = d >> 1;
+  c.x = (uint32_t)blk;
+  c.y = (uint32_t)(blk >> 32);
+  c.z = (uint32_t)stream_id;
+  c.w = (uint32_t)(stream_id >> 32) ^ (which << 28);
+  const ols_u4 o = ols_philox4x32_10_keyed(c, K);
+  const uint64_t v = (d & 1) ? (((uint64_t)o.w << 32) | o.z) : (((uint64_t)o.y << 32) | o.x);
+  return ols_u64_to_unit(v);
+}
+
 // draw `d` of the stream (seed, stream_id, which): one Philox block yields two doubles
 __host__ __device__ inline double ols_philox_uniform(uint64_t seed, uint64_t stream_id, uint32_t which, uint64_t d) {
   ols_u4 c;
@@ -128,16 +142,31 @@ __host__ __device__ inline double ols_philox_uniform(uint64_t seed, uint64_t str
   return ols_u64_to_unit(v);
 }
 
-// splitmix64 finaliser: hashing (seed, replica, bucket) into ring offsets
-__host__ __device__ inline uint64_t ols_mix64(uint64_t x) {
-  x += 0x9E3779B97F4A7C15ull;
-  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-  return x ^ (x >> 31);
+// Ring offsets (replica decorrelation, not in the reference): 32-bit murmur3 finaliser hashing.
+//   h_rep   = fmix32(seed_lo ^ fmix32(seed_hi ^ fmix32(rid_lo ^ fmix32(rid_hi))))        once per replica
+//   queue b : start = mulhi32(fmix32(h_rep ^ ((b + 1) * 0x9E3779B1)), len_b)             uniform in [0, len_b)
+//   init    : start = mulhi32(fmix32(h_rep ^ 0x85EBCA6B), n_init)
+// (restated in oracle/ols_oracle.c and tests/helpers.py)
+__host__ __device__ inline uint32_t ols_fmix32(uint32_t h) {
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
 }
-__host__ __device__ inline uint32_t ols_ring_start(uint64_t ring_seed, uint64_t replica, uint32_t bucket, uint32_t len) {
-  uint64_t h = ols_mix64(ols_mix64(ring_seed ^ (replica * 0xD1342543DE82EF95ull)) + bucket);
-  return (uint32_t)(((h >> 32) * (uint64_t)len) >> 32);  // multiply-shift: uniform in [0, len)
+__host__ __device__ inline uint32_t ols_ring_replica_hash(uint64_t ring_seed, uint64_t replica) {
+  uint32_t h = ols_fmix32((uint32_t)(replica >> 32));
+  h = ols_fmix32((uint32_t)replica ^ h);
+  h = ols_fmix32((uint32_t)(ring_seed >> 32) ^ h);
+  return ols_fmix32((uint32_t)ring_seed ^ h);
+}
+__host__ __device__ inline uint32_t ols_mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+__host__ __device__ inline uint32_t ols_ring_start(uint32_t h_rep, uint32_t bucket, uint32_t len) {
+  return ols_mulhi32(ols_fmix32(h_rep ^ ((bucket + 1u) * 0x9E3779B1u)), len);
+}
+__host__ __device__ inline uint32_t ols_ring_init_start(uint32_t h_rep, uint32_t n_init) {
+  return ols_mulhi32(ols_fmix32(h_rep ^ 0x85EBCA6Bu), n_init);
 }
 
 // ------------------------------------------------------------------------------------------ PCG64 (NumPy)

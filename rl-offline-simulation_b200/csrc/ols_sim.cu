@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(kThreads) reset_kernel(ols_queues_t q, ols_rep
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
     if (mask && !mask[r]) continue;
     int ic = R.init_cursor[r], z = R.cur_z[r], s = R.cur_s[r];
-    const bool ok = reset_one(q, R, (uint64_t)(R.replica_id0 + r), ic, z, s);
+    const bool ok = reset_one(q, R, R.ring_mode ? ols_ring_replica_hash(R.ring_seed, (uint64_t)(R.replica_id0 + r)) : 0u, ic, z, s);
     R.init_cursor[r] = ic;
     R.cur_z[r] = z;
     R.cur_s[r] = s;

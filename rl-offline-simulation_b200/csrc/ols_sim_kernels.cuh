@@ -37,7 +37,8 @@ constexpr int kThreads = 256;
 #define OLS_MINB 4
 #endif
 
-enum { RNGT_FEED = OLS_RNG_FEED, RNGT_PCG64 = OLS_RNG_PCG64, RNGT_PHILOX = OLS_RNG_PHILOX };
+// RNGT_NONE: the accept-all baselines (trivial_baselines.py:8-10,22-24) draw no uniform at all
+enum { RNGT_FEED = OLS_RNG_FEED, RNGT_PCG64 = OLS_RNG_PCG64, RNGT_PHILOX = OLS_RNG_PHILOX, RNGT_NONE = 3 };
 
 struct Lane {
   int lane, G, sub, gbase;
@@ -109,23 +110,21 @@ __device__ __forceinline__ float rcp_approx(float x) {
 }
 
 template <int NA>
-__device__ __forceinline__ int accept_filter(const Policy<NA>& P, const float (&plf)[NA], int nA, int a, float uf, bool tame) {
+__device__ __forceinline__ int accept_filter(const Policy<NA>& P, const float (&plf)[NA], int a, float uf, bool guards) {
+  // padding entries (j >= n_actions) hold p = 1 in the record and ipn = +inf in the policy: t_j = +inf never wins the min
   float t = plf[0] * P.ipn[0];
   float inv_m = t, ta = t;
 #pragma unroll
   for (int j = 1; j < NA; ++j) {
-    if (j < nA) {
-      t = plf[j] * P.ipn[j];
-      inv_m = fminf(inv_m, t);
-      ta = (j == a) ? t : ta;
-    }
+    t = plf[j] * P.ipn[j];
+    inv_m = fminf(inv_m, t);
+    ta = (j == a) ? t : ta;
   }
   const float thr = inv_m * rcp_approx(ta);
   int dec = 2;
   if (uf > thr * (1.0f + 1.52587890625e-5f)) dec = 0;  // 2^-16 band
   if (uf < thr * (1.0f - 1.52587890625e-5f)) dec = 1;
-  // u below 2^-60 (incl. 0) is not resolved in float32: with thr = 0 the exact rule accepts only u == 0
-  return (tame && P.ok && uf >= 8.6736174e-19f) ? dec : 2;
+  return guards ? dec : 2;
 }
 
 template <int NA, typename PnFn>
@@ -139,7 +138,7 @@ __device__ __forceinline__ void finish_policy(Policy<NA>& P, const PnFn& pn_fn, 
       ok = ok && (pj == 0.f || (pj >= 9.094947e-13f && pj <= 1.0f));
       mx = fmaxf(mx, pj);
     }
-    P.ipn[j] = (pj == 0.f) ? __int_as_float(0x7f800000) : __frcp_rn(pj);
+    P.ipn[j] = (pj == 0.f) ? __int_as_float(0x7f800000) : __frcp_rn(pj);  // +inf for pi = 0 and for padding entries
   }
   P.ok = ok && (mx > 0.f);
 }
@@ -147,13 +146,12 @@ __device__ __forceinline__ void finish_policy(Policy<NA>& P, const PnFn& pn_fn, 
 // ------------------------------------------------------------------------------------------ replica state
 // psrs.py:32-37 — pop the next initial (z, s); the ring start (if enabled) rotates the shared list.
 // Returns false (INIT_EMPTY) when the list is exhausted.
-__device__ __forceinline__ bool reset_one(const ols_queues_t& q, const ols_replicas_t& R, uint64_t rid, int& init_cursor,
+__device__ __forceinline__ bool reset_one(const ols_queues_t& q, const ols_replicas_t& R, uint32_t h_rep, int& init_cursor,
                                           int& cur_z, int& cur_s) {
   if ((int64_t)init_cursor >= q.n_init) return false;
   int64_t pos = init_cursor;
   if (R.ring_mode) {
-    uint64_t h = ols_mix64(R.ring_seed ^ ols_mix64(rid + 0x51ED270B1ull));
-    pos += (int64_t)(((h >> 32) * (uint64_t)q.n_init) >> 32);
+    pos += (int64_t)ols_ring_init_start(h_rep, (uint32_t)q.n_init);
     if (pos >= q.n_init) pos -= q.n_init;
   }
   cur_z = __ldg(q.init_z + pos);
@@ -171,7 +169,7 @@ struct Bucket {
 };
 
 // psrs.py:44 — `self.queues[z]`: a z that was never logged as a from-state has no queue (KeyError).
-__device__ __forceinline__ bool load_bucket(const ols_queues_t& q, const ols_replicas_t& R, uint64_t rid, const int32_t* cur_tab,
+__device__ __forceinline__ bool load_bucket(const ols_queues_t& q, const ols_replicas_t& R, uint32_t h_rep, const int32_t* cur_tab,
                                             int z, Bucket& B) {
   B.b = z + q.z_offset;
   B.lo = B.len = B.cur = 0;
@@ -187,7 +185,7 @@ __device__ __forceinline__ bool load_bucket(const ols_queues_t& q, const ols_rep
     return false;
   }
   B.cur = cur_tab[B.b];
-  if (R.ring_mode) B.start = ols_ring_start(R.ring_seed, rid, (uint32_t)B.b, (uint32_t)B.len);
+  if (R.ring_mode) B.start = ols_ring_start(h_rep, (uint32_t)B.b, (uint32_t)B.len);
   return true;
 }
 
@@ -208,20 +206,23 @@ constexpr int kPopContinue = -2;  // every record examined was rejected; the que
 
 // ONE pop round, warp-convergent (every lane of the warp calls it; `active` is group-uniform).  Lane groups
 // are decoupled: each executes its own round against its own bucket, and the caller loops.  Outcomes per
-// group: OLS_RUNNING = a record was accepted (its tail and CSR slot are returned), kPopContinue,
+// group: OLS_RUNNING = a record was accepted (its tail is returned; tail.z is the log row), kPopContinue,
 // OLS_QUEUE_EMPTY (psrs.py:44-45, detected when a round starts on a drained queue), OLS_FEED_EMPTY.
 // B.cur, draws, n_pop (and the PCG64 state) advance by the records consumed.
 template <int NV, int RNG, int PPL, typename PnFn>
 __device__ __forceinline__ int pop_round(const ols_queues_t& q, const ols_replicas_t& R, int G, int sub, int gbase,
                                          unsigned gmask, bool active, int64_t r, uint64_t rid, const Policy<4 * NV>& P,
-                                         PnFn pn_fn, const ols_philox_keys& PK, int reject_mode, int compute_mode, Bucket& B,
-                                         uint64_t& draws, uint32_t& n_pop, ols_u128& pcg_s, const ols_u128& pcg_inc,
-                                         float4& win_tail, int32_t& win_slot, int prefetch = 0) {
+                                         PnFn pn_fn, const ols_philox_keys& PK, int compute_mode, Bucket& B, uint64_t& draws,
+                                         uint32_t& n_pop, ols_u128& pcg_s, const ols_u128& pcg_inc, float4& win_tail,
+                                         int prefetch = 0) {
   constexpr int NA = 4 * NV;
+  constexpr int kRec = 16 * (NV + 1);  // record bytes
+  constexpr bool accept_all = (RNG == RNGT_NONE);
+  constexpr bool paired = (RNG == RNGT_PHILOX && PPL == 2);  // one Philox block serves the lane's two pops
   static_assert(RNG != RNGT_PCG64 || PPL == 1, "PCG64 replay is sequential per lane group: one pop per lane");
+  static_assert(!accept_all || PPL == 1, "accept-all examines one record per round");
   typedef typename std::conditional<RNG == RNGT_PHILOX, float, double>::type ustore_t;
   const int nA = q.n_actions;
-  const bool accept_all = (reject_mode == OLS_REJECT_ACCEPT_ALL);
   int result = active ? kPopContinue : kPopIdle;
 
   const int remaining = B.len - B.cur;
@@ -229,25 +230,25 @@ __device__ __forceinline__ int pop_round(const ols_queues_t& q, const ols_replic
     result = OLS_QUEUE_EMPTY;
     active = false;
   }
-  // Philox yields two uniforms per block: with PPL == 2 the round is aligned to an even draw index and
-  // the slot before `draws` (if draws is odd) is masked out, so each lane needs exactly one block.
-  const int align = (RNG == RNGT_PHILOX && PPL == 2 && !accept_all) ? (int)(draws & 1) : 0;
-  int n_eval = active ? min(G * PPL - align, remaining) : 0;
-  if (accept_all) n_eval = min(n_eval, 1);
-  const int k0 = sub * PPL - align;  // queue offset (from the cursor) of this lane's first pop
+  // Philox yields two uniforms per block: a paired round is aligned to an even draw index and the slot before
+  // `draws` (if draws is odd) is masked out, so each lane needs exactly one block.
+  const int align = paired ? (int)(draws & 1) : 0;
+  const int n_eval = active ? min(accept_all ? 1 : G * PPL - align, remaining) : 0;
+  const int k0 = sub * PPL - align;  // queue offset (from the cursor) of this lane's first pop; -1 = masked slot
 
   // ---- issue all record loads of the round first
   float4 pv[PPL][NV], tail[PPL];
+  bool valid[PPL];
 #pragma unroll
   for (int i = 0; i < PPL; ++i) {
-    const int k = k0 + i;
+    valid[i] = (unsigned)(k0 + i) < (unsigned)n_eval;  // 0 <= k < n_eval
     tail[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int v = 0; v < NV; ++v) pv[i][v] = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (k >= 0 && k < n_eval) {
-      uint32_t pos = B.start + (uint32_t)B.cur + (uint32_t)k;
+    if (valid[i]) {
+      uint32_t pos = B.start + (uint32_t)(B.cur + k0 + i);
       if (pos >= (uint32_t)B.len) pos -= (uint32_t)B.len;
-      const float4* rp = (const float4*)((const char*)q.records + (size_t)(B.lo + (int32_t)pos) * q.rec_bytes);
+      const float4* rp = (const float4*)((const char*)q.records + (size_t)(uint32_t)(B.lo + (int32_t)pos) * kRec);
       if (NV == 1) {
         // a 4-action record is 32 bytes, 32-byte aligned: one 256-bit load (LDG.E.256, new with sm_100) instead of
         // two 128-bit ones halves the L1 wavefronts of the gather
@@ -259,60 +260,64 @@ __device__ __forceinline__ int pop_round(const ols_queues_t& q, const ols_replic
       }
     }
   }
-  // ---- long reject chains: pull the records this lane would examine `prefetch` rounds ahead into L2 now, so that
-  // those rounds' loads are L2 hits (no registers held, unlike a software-pipelined load)
-  if (prefetch > 0) {
+  // ---- long reject chains: pull the records this lane would examine `prefetch` rounds ahead into L2
+  if (prefetch > 0 && active) {
     const int kp = k0 + prefetch * G * PPL;
 #pragma unroll
     for (int i = 0; i < PPL; ++i) {
-      if (kp + i >= 0 && kp + i < remaining && active) {
-        uint32_t pos = B.start + (uint32_t)B.cur + (uint32_t)(kp + i);
+      if ((unsigned)(kp + i) < (unsigned)remaining) {
+        uint32_t pos = B.start + (uint32_t)(B.cur + kp + i);
         if (pos >= (uint32_t)B.len) pos -= (uint32_t)B.len;
-        const char* rp = (const char*)q.records + (size_t)(B.lo + (int32_t)pos) * q.rec_bytes;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)q.records + (size_t)(uint32_t)(B.lo + (int32_t)pos) * kRec));
       }
     }
   }
-  // ---- uniforms of this lane's pops
+  // ---- uniforms of this lane's pops: ustore_t is a float image for Philox (the exact double is re-derived on the
+  // slow path), the exact double otherwise
   ustore_t u[PPL];
-  bool lack[PPL];
+  bool lack[PPL], tiny[PPL];
 #pragma unroll
   for (int i = 0; i < PPL; ++i) {
     u[i] = (ustore_t)0;
-    lack[i] = false;
+    lack[i] = tiny[i] = false;
   }
   ols_u128 stepped = pcg_s;
-  if (!accept_all) {
-    if (RNG == RNGT_PHILOX && PPL == 2) {
-      if (k0 + 1 >= 0 && k0 < n_eval) {
-        const uint64_t blk = ((draws - (uint64_t)align) >> 1) + (uint64_t)sub;
-        ols_u4 c;
-        c.x = (uint32_t)blk;
-        c.y = (uint32_t)(blk >> 32);
-        c.z = (uint32_t)rid;
-        c.w = (uint32_t)(rid >> 32);
-        const ols_u4 o = ols_philox4x32_10_keyed(c, PK);
-        // float image of the 53-bit uniform (relative error 2^-24); the exact double is re-derived on the slow path
-        u[0] = (ustore_t)(__ull2float_rn((((uint64_t)o.y << 32) | o.x) >> 11) * 1.1102230246251565e-16f);
-        u[PPL - 1] = (ustore_t)(__ull2float_rn((((uint64_t)o.w << 32) | o.z) >> 11) * 1.1102230246251565e-16f);
-      }
-    } else {
+  if (paired) {
+    if (valid[0] || valid[1]) {
+      const uint64_t blk = ((draws - (uint64_t)align) >> 1) + (uint64_t)sub;
+      ols_u4 c;
+      c.x = (uint32_t)blk;
+      c.y = (uint32_t)(blk >> 32);
+      c.z = (uint32_t)rid;
+      c.w = (uint32_t)(rid >> 32);
+      const ols_u4 o = ols_philox4x32_10_keyed(c, PK);
+      // float image of u from its top 32 bits: |error| <= 2^-32 + 2^-24 u, i.e. < 2^-19 relative once u >= 2^-12;
+      // the rare smaller draws (2.4e-4) are converted from all 53 bits instead
+      float f0 = __uint2float_rn(o.y) * 2.3283064365386963e-10f, f1 = __uint2float_rn(o.w) * 2.3283064365386963e-10f;
+      if (o.y < (1u << 20)) f0 = __ull2float_rn((((uint64_t)o.y << 32) | o.x) >> 11) * 1.1102230246251565e-16f;
+      if (o.w < (1u << 20)) f1 = __ull2float_rn((((uint64_t)o.w << 32) | o.z) >> 11) * 1.1102230246251565e-16f;
+      u[0] = (ustore_t)f0;
+      u[PPL - 1] = (ustore_t)f1;
+      tiny[0] = !(f0 >= 8.6736174e-19f);  // u < 2^-60 (incl. 0): not resolved in float32
+      tiny[PPL - 1] = !(f1 >= 8.6736174e-19f);
+    }
+  } else if (!accept_all) {
 #pragma unroll
-      for (int i = 0; i < PPL; ++i) {
+    for (int i = 0; i < PPL; ++i) {
+      if (valid[i]) {
         const int k = k0 + i;
-        if (k >= 0 && k < n_eval) {
-          const uint64_t d = draws + (uint64_t)k;
-          if (RNG == RNGT_FEED) {
-            if ((int64_t)d < R.u_feed_len) u[i] = (ustore_t)__ldg(R.u_feed + r * R.u_stride + (int64_t)d);
-            else lack[i] = true;
-          } else if (RNG == RNGT_PCG64) {
-            // PCG64 always runs with PPL == 1: pop k needs the group's generator stepped k + 1 times
-            for (int t = 0; t <= k; ++t) stepped = ols_pcg_step(stepped, pcg_inc);
-            u[i] = (ustore_t)ols_u64_to_unit(ols_pcg_output(stepped));
-          } else {
-            u[i] = (ustore_t)(float)ols_philox_uniform(R.seed, rid, 0u, d);
-          }
+        const uint64_t d = draws + (uint64_t)k;
+        if (RNG == RNGT_FEED) {
+          if ((int64_t)d < R.u_feed_len) u[i] = (ustore_t)__ldg(R.u_feed + r * R.u_stride + (int64_t)d);
+          else lack[i] = true;
+        } else if (RNG == RNGT_PCG64) {
+          // PCG64 always runs with PPL == 1: pop k needs the group's generator stepped k + 1 times
+          for (int t = 0; t <= k; ++t) stepped = ols_pcg_step(stepped, pcg_inc);
+          u[i] = (ustore_t)ols_u64_to_unit(ols_pcg_output(stepped));
+        } else {
+          u[i] = (ustore_t)(float)ols_philox_uniform_keyed(PK, rid, 0u, d);
         }
+        tiny[i] = !((float)u[i] >= 8.6736174e-19f);  // u < 2^-60 (incl. 0): not resolved by the float32 filter
       }
     }
   }
@@ -320,43 +325,59 @@ __device__ __forceinline__ int pop_round(const ols_queues_t& q, const ols_replic
   bool acc[PPL];
 #pragma unroll
   for (int i = 0; i < PPL; ++i) {
-    const int k = k0 + i;
     acc[i] = false;
-    if (k >= 0 && k < n_eval && !lack[i]) {
-      if (accept_all) {
-        acc[i] = true;  // trivial_baselines.py:8-10: no uniform is drawn
-      } else {
-        const uint32_t meta = __float_as_uint(tail[i].w);
-        const int a = ols_meta_action(meta);
-        float plf[NA];
+    if (accept_all) {
+      acc[i] = valid[i];  // trivial_baselines.py:8-10: no uniform is drawn
+    } else if (valid[i] && !lack[i]) {
+      const uint32_t meta = __float_as_uint(tail[i].w);
+      const int a = ols_meta_action(meta);
+      float plf[NA];
 #pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          plf[4 * v + 0] = pv[i][v].x;
-          plf[4 * v + 1] = pv[i][v].y;
-          plf[4 * v + 2] = pv[i][v].z;
-          plf[4 * v + 3] = pv[i][v].w;
-        }
-        int dec = accept_filter<NA>(P, plf, nA, a, (float)u[i], ols_meta_tame(meta) != 0);
-        if (dec == 2) {
-          uint32_t pos = B.start + (uint32_t)B.cur + (uint32_t)k;
-          if (pos >= (uint32_t)B.len) pos -= (uint32_t)B.len;
-          const int32_t slot = B.lo + (int32_t)pos;
-          const double ue = (RNG == RNGT_PHILOX) ? ols_philox_uniform(R.seed, rid, 0u, draws + (uint64_t)k) : (double)u[i];
-          const double* p64 = q.p_log64 ? q.p_log64 + (int64_t)__float_as_int(tail[i].z) * nA : nullptr;
-          dec = (int)accept_slow(pn_fn, (const float*)((const char*)q.records + (size_t)slot * q.rec_bytes), p64, nA, a, ue,
-                                 compute_mode);
-        }
-        acc[i] = (dec == 1);
+      for (int v = 0; v < NV; ++v) {
+        plf[4 * v + 0] = pv[i][v].x;
+        plf[4 * v + 1] = pv[i][v].y;
+        plf[4 * v + 2] = pv[i][v].z;
+        plf[4 * v + 3] = pv[i][v].w;
       }
+      int dec = accept_filter<NA>(P, plf, a, (float)u[i], P.ok && !tiny[i] && ols_meta_tame(meta) != 0);
+      if (dec == 2) {
+        const int k = k0 + i;
+        uint32_t pos = B.start + (uint32_t)(B.cur + k);
+        if (pos >= (uint32_t)B.len) pos -= (uint32_t)B.len;
+        const double ue = (RNG == RNGT_PHILOX) ? ols_philox_uniform_keyed(PK, rid, 0u, draws + (uint64_t)k) : (double)u[i];
+        const double* p64 = q.p_log64 ? q.p_log64 + (int64_t)__float_as_int(tail[i].z) * nA : nullptr;
+        dec = (int)accept_slow(pn_fn, (const float*)((const char*)q.records + (size_t)(uint32_t)(B.lo + (int32_t)pos) * kRec),
+                               p64, nA, a, ue, compute_mode);
+      }
+      acc[i] = (dec == 1);
     }
   }
   // ---- first accepting pop of each group, in queue order
   int first_acc = 1 << 20, first_lack = 1 << 20;
+#ifdef OLS_EXP_OLDBALLOT
+  if (PPL == 2) {
 #pragma unroll
-  for (int i = 0; i < PPL; ++i) {
-    const unsigned ba = (__ballot_sync(kFull, acc[i]) >> gbase) & gmask;
-    if (ba) first_acc = min(first_acc, (__ffs(ba) - 1) * PPL + i - align);
-    if (RNG == RNGT_FEED) {
+    for (int i = 0; i < PPL; ++i) {
+      const unsigned ba = (__ballot_sync(kFull, acc[i]) >> gbase) & gmask;
+      if (ba) first_acc = min(first_acc, (__ffs(ba) - 1) * PPL + i - align);
+    }
+  } else {
+#else
+  if (PPL == 2) {
+    const unsigned g_any = (__ballot_sync(kFull, acc[0] || acc[PPL - 1]) >> gbase) & gmask;
+    const unsigned g_a0 = (__ballot_sync(kFull, acc[0]) >> gbase) & gmask;
+    if (g_any) {
+      const int w = __ffs(g_any) - 1;
+      first_acc = 2 * w + (((g_a0 >> w) & 1u) ? 0 : 1) - align;
+    }
+  } else {
+#endif
+    const unsigned ba = (__ballot_sync(kFull, acc[0]) >> gbase) & gmask;
+    if (ba) first_acc = __ffs(ba) - 1;
+  }
+  if (RNG == RNGT_FEED) {
+#pragma unroll
+    for (int i = 0; i < PPL; ++i) {
       const unsigned bl = (__ballot_sync(kFull, lack[i]) >> gbase) & gmask;
       if (bl) first_lack = min(first_lack, (__ffs(bl) - 1) * PPL + i - align);
     }
@@ -378,9 +399,7 @@ __device__ __forceinline__ int pop_round(const ols_queues_t& q, const ols_replic
   const int wk = (first_acc < (1 << 20)) ? first_acc + align : 0;
   const int src = gbase + wk / PPL;
   float4 sel = tail[0];
-#pragma unroll
-  for (int i = 1; i < PPL; ++i)
-    if (wk % PPL == i) sel = tail[i];
+  if (PPL == 2 && (wk & 1)) sel = tail[PPL - 1];
   sel.x = __shfl_sync(kFull, sel.x, src);
   sel.y = __shfl_sync(kFull, sel.y, src);
   sel.z = __shfl_sync(kFull, sel.z, src);
@@ -391,15 +410,12 @@ __device__ __forceinline__ int pop_round(const ols_queues_t& q, const ols_replic
     const int adv_src = gbase + (consumed > 0 ? consumed - 1 : 0);
     const uint64_t nh = __shfl_sync(kFull, stepped.hi, adv_src);
     const uint64_t nl = __shfl_sync(kFull, stepped.lo, adv_src);
-    if (consumed > 0 && !accept_all) {
+    if (consumed > 0) {
       pcg_s.hi = nh;
       pcg_s.lo = nl;
     }
   }
   if (took) {
-    uint32_t pos = B.start + (uint32_t)B.cur + (uint32_t)first_acc;
-    if (pos >= (uint32_t)B.len) pos -= (uint32_t)B.len;
-    win_slot = B.lo + (int32_t)pos;
     win_tail = sel;
     result = OLS_RUNNING;
   }
@@ -413,8 +429,7 @@ __device__ __forceinline__ int pop_round(const ols_queues_t& q, const ols_replic
 template <int NV, int RNG>
 __global__ void __launch_bounds__(kThreads) step_kernel(ols_queues_t q, ols_replicas_t R, const uint8_t* mask,
                                                          const void* p_new, int p_new_is_f64, int64_t p_stride,
-                                                         int reject_mode, int compute_mode, int G, ols_step_out_t out,
-                                                         ols_philox_keys PK) {
+                                                         int compute_mode, int G, ols_step_out_t out, ols_philox_keys PK) {
   constexpr int NA = 4 * NV;
   const Lane L = make_lane(G);
   const int nA = q.n_actions;
@@ -453,16 +468,15 @@ __global__ void __launch_bounds__(kThreads) step_kernel(ols_queues_t q, ols_repl
   B.lo = B.len = B.cur = 0;
   B.start = 0;
   int res = kPopIdle;
-  if (active && !load_bucket(q, R, rid, cur_tab, cur_z, B)) {
+  if (active && !load_bucket(q, R, ols_ring_replica_hash(R.ring_seed, rid), cur_tab, cur_z, B)) {
     res = OLS_NO_QUEUE;
     active = false;
   }
   uint32_t n_pop = 0;
   float4 tail = make_float4(0.f, 0.f, 0.f, 0.f);
-  int32_t slot = -1;
   while (__any_sync(kFull, active)) {
-    const int rc = pop_round<NV, RNG, 1>(q, R, L.G, L.sub, L.gbase, L.gmask, active, rr, rid, P, pn_fn, PK, reject_mode,
-                                         compute_mode, B, draws, n_pop, pcg_s, pcg_inc, tail, slot);
+    const int rc = pop_round<NV, RNG, 1>(q, R, L.G, L.sub, L.gbase, L.gmask, active, rr, rid, P, pn_fn, PK, compute_mode, B,
+                                         draws, n_pop, pcg_s, pcg_inc, tail);
     if (active && rc != kPopContinue) {
       res = rc;
       active = false;
@@ -560,6 +574,7 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
   const bool exists = r < R.n_replicas;
   const int64_t rr = exists ? r : 0;
   const uint64_t rid = (uint64_t)(R.replica_id0 + rr);
+  const uint32_t h_rep = R.ring_mode ? ols_ring_replica_hash(R.ring_seed, rid) : 0u;
   const int group = threadIdx.x / G;
   volatile Cold* C = (volatile Cold*)s_mem + group;
   unsigned char* my_slot = s_mem + sizeof(Cold) * (kThreads / G) + (size_t)group * plan.slot_bytes;
@@ -631,168 +646,185 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
   for (int j = 0; j < NA; ++j) P.ipn[j] = 1.f;
   P.ok = false;
 
+  // Lanes of one group execute the step code redundantly and keep shared state (the Cold block, the cursor table,
+  // the Q table) in memory they all write.  The programming model does not promise that they run in lockstep, so
+  // every block below is phased: all reads of shared state -> __syncwarp(gm) -> all writes (identical values from
+  // every lane) -> __syncwarp(gm).  gm is the group's own lane mask.
+  const unsigned gm = gmask << gbase;
+
   while (__any_sync(kFull, live)) {
     if (live && need_step) {
       need_step = false;
+      // ---------------- phase 1: reads
+      const int ep_open0 = C->ep_open, ep_index0 = C->ep_index;
+      int ic = C->init_cursor;
+      const unsigned long long ties0 = C->ties;
+      const int eps_episode0 = C->eps_episode;
+      int new_status = -1;       // >= 0: terminate with this status
+      bool started = false;      // a new episode starts here
       // ---- episode start: psrs.py:149-156 / 205-212 / 246-253
-      if (!C->ep_open) {
-        int ic = C->init_cursor;
-        if (C->ep_index >= cfg.n_episodes) {
-          C->status = OLS_DONE;
-          live = false;
-        } else if (!reset_one(q, R, rid, ic, cur_z, cur_s)) {
-          C->status = OLS_INIT_EMPTY;  // terminate without appending (psrs.py:153-155)
-          live = false;
+      if (!ep_open0) {
+        if (ep_index0 >= cfg.n_episodes) {
+          new_status = OLS_DONE;
+        } else if (!reset_one(q, R, h_rep, ic, cur_z, cur_s)) {
+          new_status = OLS_INIT_EMPTY;  // terminate without appending (psrs.py:153-155)
         } else {
-          C->init_cursor = ic;
-          C->status = OLS_RUNNING;
-          C->ep_open = 1;
-          C->ep_t = 0;
-          C->ep_G = 0.0;
-          C->ep_disc = 1.0;
+          started = true;
           row_valid = false;
           bucket_valid = false;
         }
       }
-      if (live && (cur_s < 0 || cur_s >= nS)) {  // IndexError on Q[S] / pi[S] in the reference
-        C->status = OLS_NO_QUEUE;
-        live = false;
-      }
-      if (live && !bucket_valid && !load_bucket(q, R, rid, cur_tab, cur_z, B)) {
-        C->status = OLS_NO_QUEUE;  // KeyError in the reference (psrs.py:44); no partial episode is appended
-        live = false;
-      }
+      if (new_status < 0 && (cur_s < 0 || cur_s >= nS)) new_status = OLS_NO_QUEUE;  // IndexError on Q[S] / pi[S]
+      if (new_status < 0 && !bucket_valid && !load_bucket(q, R, h_rep, cur_tab, cur_z, B))
+        new_status = OLS_NO_QUEUE;  // KeyError in the reference (psrs.py:44); no partial episode is appended
       // ---- the agent's action distribution for the current state
-      if (AGENT == OLS_AGENT_QLEARN && live) {
+      bool used_tie = false;
+      float ib = 0.f, it = 0.f;
+      int pn_ok = 0;
+      bool new_eps = false;
+      if (AGENT == OLS_AGENT_QLEARN && new_status < 0) {
         // tabular.py:24-32 epsilon_greedy_policy on the single row Q[[S], :] (psrs.py:158)
         if (!row_valid) {
 #pragma unroll
-          for (int j = 0; j < NA; ++j)
-            if (j < nA) row[j] = Qr[(int64_t)cur_s * nA + j];
+          for (int j = 0; j < NA; ++j) row[j] = (j < nA) ? Qr[(int64_t)cur_s * nA + j] : -INFINITY;  // padding never wins
         }
         QT mx = row[0];
 #pragma unroll
-        for (int j = 1; j < NA; ++j)
-          if (j < nA && row[j] > mx) mx = row[j];
-        int ncand = 0;
+        for (int j = 1; j < NA; ++j) mx = (row[j] > mx) ? row[j] : mx;
+        unsigned cand = 0;  // bit j set: action j attains the maximum
 #pragma unroll
-        for (int j = 0; j < NA; ++j)
-          if (j < nA && row[j] == mx) ++ncand;
-        int pick = 0;
+        for (int j = 0; j < NA; ++j) cand |= (row[j] == mx) ? (1u << j) : 0u;
+        const int ncand = __popc(cand);
         if (ncand > 1) {  // tabular.py:4-5 _random_argmax: a draw is consumed only on ties
-          const unsigned long long ties = C->ties;
           double v = 0.0;
           bool have = true;
           if (R.tie_mode == OLS_RNG_FEED) {
-            if ((int64_t)ties < R.tie_feed_len) v = __ldg(R.tie_feed + rr * R.tie_stride + (int64_t)ties);
+            if ((int64_t)ties0 < R.tie_feed_len) v = __ldg(R.tie_feed + rr * R.tie_stride + (int64_t)ties0);
             else have = false;
           } else {
-            v = ols_philox_uniform(R.seed, rid, 1u, ties);
+            v = ols_philox_uniform_keyed(PK, rid, 1u, ties0);
           }
           if (!have) {
-            C->status = OLS_FEED_EMPTY;
-            live = false;
+            new_status = OLS_FEED_EMPTY;
           } else {
-            C->ties = ties + 1;
-            pick = min(ncand - 1, (int)(v * (double)ncand));
+            used_tie = true;
+            const int pick = min(ncand - 1, (int)(v * (double)ncand));
+            for (int t = 0; t < pick; ++t) cand &= cand - 1;  // drop the `pick` lowest candidates
           }
         }
-        int seen = 0;
-        a_star = 0;
-#pragma unroll
-        for (int j = 0; j < NA; ++j)
-          if (j < nA && row[j] == mx) {
-            if (seen == pick) a_star = j;
-            ++seen;
-          }
-      }
-      // ---- the float image of pi(.|S) the pre-filter works with
-      if (live) {
-        if (AGENT == OLS_AGENT_QLEARN) {
-          // epsilon-greedy has two distinct probabilities per episode (tabular.py:27,30): their float reciprocals
-          // and the guard bit are cached in the Cold block when an episode's epsilon is first used
-          const int ep = C->ep_index;
-          if (C->eps_episode != ep) {
-            const double eps = __ldg(cfg.epsilon + ep);
-            const double based = __ddiv_rn(eps, (double)nA);
-            const float base = (float)based, top = (float)__dadd_rn(__dsub_rn(1.0, eps), based);
-            const bool okb = (base == 0.f) || (base >= 9.094947e-13f && base <= 1.0f);
-            const bool okt = (top == 0.f) || (top >= 9.094947e-13f && top <= 1.0f);
-            C->ipn_base = (base == 0.f) ? __int_as_float(0x7f800000) : __frcp_rn(base);
-            C->ipn_top = (top == 0.f) ? __int_as_float(0x7f800000) : __frcp_rn(top);
-            C->pn_ok = (okb && okt && (base > 0.f || top > 0.f)) ? 1 : 0;
-            C->eps_episode = ep;
-          }
-          const float ib = C->ipn_base, it = C->ipn_top;
-#pragma unroll
-          for (int j = 0; j < NA; ++j) P.ipn[j] = (j == a_star) ? it : ib;
-          P.ok = C->pn_ok != 0;
+        a_star = __ffs(cand) - 1;
+        // epsilon-greedy has two distinct probabilities per episode (tabular.py:27,30): their float reciprocals and
+        // the guard bit are cached in the Cold block when an episode's epsilon is first used
+        if (eps_episode0 != ep_index0) {
+          new_eps = true;
+          const double eps = __ldg(cfg.epsilon + ep_index0);
+          const double based = __ddiv_rn(eps, (double)nA);
+          const float base = (float)based, top = (float)__dadd_rn(__dsub_rn(1.0, eps), based);
+          const bool okb = (base == 0.f) || (base >= 9.094947e-13f && base <= 1.0f);
+          const bool okt = (top == 0.f) || (top >= 9.094947e-13f && top <= 1.0f);
+          ib = (base == 0.f) ? __int_as_float(0x7f800000) : __frcp_rn(base);
+          it = (top == 0.f) ? __int_as_float(0x7f800000) : __frcp_rn(top);
+          pn_ok = (okb && okt && (base > 0.f || top > 0.f)) ? 1 : 0;
         } else {
-          const void* pi_tab = cfg.pi;
-          const int is64 = cfg.pi_is_f64;
-          const int64_t off = (int64_t)cur_s * nA;
-          finish_policy<NA>(P, [=](int j) -> double {
-            return is64 ? __ldg((const double*)pi_tab + off + j) : (double)__ldg((const float*)pi_tab + off + j);
-          }, nA);
+          ib = C->ipn_base;
+          it = C->ipn_top;
+          pn_ok = C->pn_ok;
         }
+#pragma unroll
+        for (int j = 0; j < NA; ++j) P.ipn[j] = (j >= nA) ? __int_as_float(0x7f800000) : ((j == a_star) ? it : ib);
+        P.ok = pn_ok != 0;
+      } else if (new_status < 0) {
+        const void* pi_tab = cfg.pi;
+        const int is64 = cfg.pi_is_f64;
+        const int64_t off = (int64_t)cur_s * nA;
+        finish_policy<NA>(P, [=](int j) -> double {
+          return is64 ? __ldg((const double*)pi_tab + off + j) : (double)__ldg((const float*)pi_tab + off + j);
+        }, nA);
       }
+      __syncwarp(gm);
+      // ---------------- phase 2: writes
+      if (started) {
+        C->init_cursor = ic;
+        C->status = OLS_RUNNING;
+        C->ep_open = 1;
+        C->ep_t = 0;
+        C->ep_G = 0.0;
+        C->ep_disc = 1.0;
+      }
+      if (used_tie) C->ties = ties0 + 1;
+      if (new_eps) {
+        C->ipn_base = ib;
+        C->ipn_top = it;
+        C->pn_ok = pn_ok;
+        C->eps_episode = ep_index0;
+      }
+      if (new_status >= 0) {
+        C->status = new_status;
+        live = false;
+      }
+      __syncwarp(gm);
     }
-    // exact float64 pi(.|S): re-derived from (eps, a*) or re-read from the table wherever it is needed
-    const int a_now = a_star;
-    const double* eps_ptr = (AGENT == OLS_AGENT_QLEARN) ? cfg.epsilon + (live ? C->ep_index : 0) : nullptr;
-    const int S_now = live ? cur_s : 0;
-    const void* pi_row = (AGENT == OLS_AGENT_QLEARN) ? nullptr
-                         : (cfg.pi_is_f64 ? (const void*)((const double*)cfg.pi + (int64_t)S_now * nA)
-                                          : (const void*)((const float*)cfg.pi + (int64_t)S_now * nA));
+    // exact float64 pi(.|S) for the cold path: re-derived from (eps, a*) or re-read from the table when needed
+    const int a_now = a_star, S_now = cur_s;
+    const double* eps_tab = cfg.epsilon;
+    const void* pi_tab = cfg.pi;
     const int pi_is_f64 = cfg.pi_is_f64;
     auto pn_fn = [=](int j) -> double {
       if (AGENT == OLS_AGENT_QLEARN) {
-        const double eps = __ldg(eps_ptr);
+        const double eps = __ldg(eps_tab + C->ep_index);
         const double base = __ddiv_rn(eps, (double)nA);           // ones * eps / nA          (tabular.py:27)
         const double top = __dadd_rn(__dsub_rn(1.0, eps), base);  // 1 - eps + eps / nA       (tabular.py:30)
         return (j == a_now) ? top : base;
       }
       // psrs.py:214,255 — p = pi[S]
-      return pi_is_f64 ? __ldg((const double*)pi_row + j) : (double)__ldg((const float*)pi_row + j);
+      const int64_t off = (int64_t)S_now * nA + j;
+      return pi_is_f64 ? __ldg((const double*)pi_tab + off) : (double)__ldg((const float*)pi_tab + off);
     };
     // ---- env.step(p), one round of it: psrs.py:39-57
     float4 tail = make_float4(0.f, 0.f, 0.f, 0.f);
-    int32_t slot = -1;
-    const int res = pop_round<NV, RNG, PPL>(q, R, G, sub, gbase, gmask, live, rr, rid, P, pn_fn, PK, cfg.reject_mode,
-                                            cfg.compute_mode, B, draws, n_pop, pcg_s, pcg_inc, tail, slot, cfg.prefetch);
+    const int res = pop_round<NV, RNG, PPL>(q, R, G, sub, gbase, gmask, live, rr, rid, P, pn_fn, PK, cfg.compute_mode, B, draws,
+                                            n_pop, pcg_s, pcg_inc, tail, cfg.prefetch);
     // ---- learner update and episode bookkeeping for the groups whose round ended the step
     if (live && res != kPopContinue) {
-      cur_tab[B.b] = B.cur;  // every lane of the group stores the same value and later re-reads its own store
-      if (res == OLS_RUNNING) {
-        const int S = cur_s;
-        const uint32_t meta = __float_as_uint(tail.w);
-        const int A = ols_meta_action(meta);
-        const int Z2 = __float_as_int(tail.y);
-        const int32_t row_idx = __float_as_int(tail.z);
-        const int S2 = q.s_next ? __ldg(q.s_next + row_idx) : Z2;
-        const int done = ols_meta_terminal(meta);
-        const double Rw = (double)tail.x;
-        const int ep_index = C->ep_index;
-        const long long acc_idx = (long long)C->accepted0 + C->n_acc;
-        // the next state is known: fetch its queue head now, ahead of the learner's own memory traffic
-        const bool next_ok = done ? false : load_bucket(q, R, rid, cur_tab, Z2, B);
+      // ---------------- phase 1: reads of shared state, loads, arithmetic
+      const int ep_index = C->ep_index, lc = C->ep_len_count, t_old = C->ep_t, n_acc_old = C->n_acc;
+      const double G_old = C->ep_G, disc = C->ep_disc;
+      const long long acc_idx = (long long)C->accepted0 + n_acc_old;
+      const int b_done = B.b, cur_done = B.cur;  // the queue just popped from and its new cursor
+      int new_status = -1;
+      bool accepted = (res == OLS_RUNNING), q_write = false, close_ep = false, append_G = false;
+      const int S = cur_s;
+      const uint32_t meta = __float_as_uint(tail.w);
+      const int A = ols_meta_action(meta);
+      const int Z2 = __float_as_int(tail.y);
+      const int32_t row_idx = __float_as_int(tail.z);
+      const int done = ols_meta_terminal(meta);
+      const double Rw = (double)tail.x;
+      int S2 = 0;
+      QT qn = (QT)0, td = (QT)0;
+      double G_new = G_old;
+      int t_new = t_old;
+      if (accepted) {
+        S2 = q.s_next ? __ldg(q.s_next + row_idx) : Z2;
+        // the next state is known: fetch its queue head now, ahead of the learner's own memory traffic.  (The cursor
+        // of the queue just popped is still the old one in memory; a self-loop patches it from the register.)
+        const bool next_ok = done ? false : load_bucket(q, R, h_rep, cur_tab, Z2, B);
+        if (next_ok && B.b == b_done) B.cur = cur_done;
         bucket_valid = next_ok;
         need_step = true;
         if (AGENT != OLS_AGENT_FIXED_PI) {
           if (S2 < 0 || S2 >= nS) {
-            C->status = OLS_NO_QUEUE;
-            live = false;
+            new_status = OLS_NO_QUEUE;
           } else {
             const double alpha = __ldg(cfg.alpha + ep_index);
             QT nrow[NA];
 #pragma unroll
-            for (int j = 0; j < NA; ++j) nrow[j] = (j < nA) ? Qr[(int64_t)S2 * nA + j] : (QT)0;
+            for (int j = 0; j < NA; ++j) nrow[j] = (j < nA) ? Qr[(int64_t)S2 * nA + j] : -INFINITY;
             QT boot;
             if (AGENT == OLS_AGENT_QLEARN) {
               boot = nrow[0];  // Q[S_].max()
 #pragma unroll
-              for (int j = 1; j < NA; ++j)
-                if (j < nA && nrow[j] > boot) boot = nrow[j];
+              for (int j = 1; j < NA; ++j) boot = (nrow[j] > boot) ? nrow[j] : boot;
             } else {
               double acc = 0.0;  // Q[S_] @ pi[S_]
 #pragma unroll
@@ -813,10 +845,9 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
             } else {
               qsa = Qr[(int64_t)S * nA + A];
             }
-            const QT td = QMath<QT>::td((QT)Rw, (QT)cfg.gamma, boot, qsa);
-            const QT qn = QMath<QT>::upd(qsa, (QT)alpha, td);
-            Qr[(int64_t)S * nA + A] = qn;  // all lanes of the group store the same value (see cursor)
-            if (sub == 0 && cfg.td_error && acc_idx < cfg.trace_cap) cfg.td_error[rr * cfg.trace_cap + acc_idx] = (double)td;
+            td = QMath<QT>::td((QT)Rw, (QT)cfg.gamma, boot, qsa);
+            qn = QMath<QT>::upd(qsa, (QT)alpha, td);
+            q_write = true;
             if (AGENT == OLS_AGENT_QLEARN) {
               // the bootstrap row becomes the next step's policy row (patched if S' == S)
 #pragma unroll
@@ -825,50 +856,58 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
             }
           }
         }
-        if (live) {
-          if (cfg.trace_row && sub == 0 && acc_idx < cfg.trace_cap) cfg.trace_row[rr * cfg.trace_cap + acc_idx] = row_idx;
-          cur_z = Z2;
-          cur_s = S2;
-          const int n_acc = C->n_acc + 1;
-          C->n_acc = n_acc;
-          const double disc = C->ep_disc;
-          const double G_new = __dadd_rn(C->ep_G, __dmul_rn(disc, Rw));  // G + gamma**t * R   (psrs.py:171)
-          C->ep_G = G_new;
-          C->ep_disc = __dmul_rn(disc, cfg.gamma);
-          const int t_new = C->ep_t + 1;
-          C->ep_t = t_new;
+        if (new_status < 0) {
+          G_new = __dadd_rn(G_old, __dmul_rn(disc, Rw));  // G + gamma**t * R   (psrs.py:171)
+          t_new = t_old + 1;
           if (done) {  // psrs.py:176-178 / 265-269
-            const int lc = C->ep_len_count;
-            if (sub == 0) {
-              if (ep_index < cfg.ep_cap) cfg.Gs[rr * (int64_t)cfg.ep_cap + ep_index] = G_new;
-              if (lc < cfg.ep_cap) cfg.lengths[rr * (int64_t)cfg.ep_cap + lc] = t_new;
-            }
-            C->ep_index = ep_index + 1;
-            C->ep_len_count = lc + 1;
-            C->ep_open = 0;
+            close_ep = true;
+            append_G = true;
           } else if (!next_ok) {
-            // the next state has no queue: the reference raises KeyError on its next step (psrs.py:44)
-            C->status = OLS_NO_QUEUE;
-            live = false;
+            new_status = OLS_NO_QUEUE;  // the next state has no queue: KeyError on the reference's next step (psrs.py:44)
           }
-          if (cfg.max_steps > 0 && (int64_t)n_acc >= cfg.max_steps) live = false;  // budget: stays resumable
         }
       } else {
-        // exhaustion in mid-episode (psrs.py:160-162): qlearn/expSARSA still append the partial
-        // return (:177-178), evalMC appends only the length (:265-269)
-        C->status = res;
-        live = false;
+        // exhaustion in mid-episode (psrs.py:160-162): qlearn/expSARSA still append the partial return (:177-178),
+        // evalMC appends only the length (:265-269)
+        new_status = res;
         if (res == OLS_QUEUE_EMPTY) {
-          const int ep_index = C->ep_index, lc = C->ep_len_count;
-          if (sub == 0) {
-            if (lc < cfg.ep_cap) cfg.lengths[rr * (int64_t)cfg.ep_cap + lc] = C->ep_t;
-            if (AGENT != OLS_AGENT_FIXED_PI && ep_index < cfg.ep_cap) cfg.Gs[rr * (int64_t)cfg.ep_cap + ep_index] = C->ep_G;
-          }
-          C->ep_len_count = lc + 1;
-          if (AGENT != OLS_AGENT_FIXED_PI) C->ep_index = ep_index + 1;
-          C->ep_open = 0;
+          close_ep = true;
+          append_G = (AGENT != OLS_AGENT_FIXED_PI);
         }
       }
+      __syncwarp(gm);
+      // ---------------- phase 2: writes (every lane of the group writes the same values)
+      if (b_done >= 0) cur_tab[b_done] = cur_done;
+      // an accepted transition is committed unless the learner found its next observation out of range
+      const bool commit = accepted && !(AGENT != OLS_AGENT_FIXED_PI && !q_write);
+      if (commit) {
+        if (q_write) {
+          Qr[(int64_t)S * nA + A] = qn;
+          if (sub == 0 && cfg.td_error && acc_idx < cfg.trace_cap) cfg.td_error[rr * cfg.trace_cap + acc_idx] = (double)td;
+        }
+        if (cfg.trace_row && sub == 0 && acc_idx < cfg.trace_cap) cfg.trace_row[rr * cfg.trace_cap + acc_idx] = row_idx;
+        cur_z = Z2;
+        cur_s = S2;
+        C->n_acc = n_acc_old + 1;
+        C->ep_G = G_new;
+        C->ep_disc = __dmul_rn(disc, cfg.gamma);
+        C->ep_t = t_new;
+        if (cfg.max_steps > 0 && (int64_t)(n_acc_old + 1) >= cfg.max_steps) live = false;  // budget: stays resumable
+      }
+      if (close_ep) {
+        if (sub == 0) {
+          if (append_G && ep_index < cfg.ep_cap) cfg.Gs[rr * (int64_t)cfg.ep_cap + ep_index] = G_new;
+          if (lc < cfg.ep_cap) cfg.lengths[rr * (int64_t)cfg.ep_cap + lc] = t_new;
+        }
+        if (append_G) C->ep_index = ep_index + 1;
+        C->ep_len_count = lc + 1;
+        C->ep_open = 0;
+      }
+      if (new_status >= 0) {
+        C->status = new_status;
+        live = false;
+      }
+      __syncwarp(gm);
     }
   }
   // ---- write the staged tables back
@@ -926,7 +965,8 @@ inline cudaError_t launch_run_rng(const ols_queues_t& q, const ols_replicas_t& r
     }                                                                                                                  \
     k<<<L.grid, kThreads, L.smem, L.stream>>>(q, r, c, L.plan, L.keys);                                                        \
   } while (0)
-  if (r.rng_mode == OLS_RNG_PCG64) OLS_GO(RNGT_PCG64, 1);
+  if (c.reject_mode == OLS_REJECT_ACCEPT_ALL) OLS_GO(RNGT_NONE, 1);
+  else if (r.rng_mode == OLS_RNG_PCG64) OLS_GO(RNGT_PCG64, 1);
   else if (r.rng_mode == OLS_RNG_FEED) { if (ppl == 2) OLS_GO(RNGT_FEED, 2); else OLS_GO(RNGT_FEED, 1); }
   else { if (ppl == 2) OLS_GO(RNGT_PHILOX, 2); else OLS_GO(RNGT_PHILOX, 1); }
 #undef OLS_GO
@@ -949,9 +989,10 @@ inline cudaError_t launch_step_nv(const ols_queues_t& q, const ols_replicas_t& r
                                   int p_new_is_f64, int64_t p_stride, int reject_mode, int compute_mode, int lanes,
                                   const ols_step_out_t& out, int grid, cudaStream_t stream) {
 #define OLS_GO(RNG) \
-  step_kernel<NV, RNG><<<grid, kThreads, 0, stream>>>(q, r, mask, p_new, p_new_is_f64, p_stride, reject_mode, compute_mode, lanes, out, \
+  step_kernel<NV, RNG><<<grid, kThreads, 0, stream>>>(q, r, mask, p_new, p_new_is_f64, p_stride, compute_mode, lanes, out, \
                                                       ols_philox_make_keys(r.seed))
-  if (r.rng_mode == OLS_RNG_PCG64) OLS_GO(RNGT_PCG64);
+  if (reject_mode == OLS_REJECT_ACCEPT_ALL) OLS_GO(RNGT_NONE);
+  else if (r.rng_mode == OLS_RNG_PCG64) OLS_GO(RNGT_PCG64);
   else if (r.rng_mode == OLS_RNG_FEED) OLS_GO(RNGT_FEED);
   else OLS_GO(RNGT_PHILOX);
 #undef OLS_GO

@@ -254,7 +254,7 @@ class BatchedPSRS:
         self.lanes = 1 if self.reject_mode == abi.REJECT_ACCEPT_ALL else int(lanes)
         self.pops_per_lane = int(pops_per_lane)     # 0 = auto (2 with Philox / fed uniforms)
         self.stage_smem = bool(stage_smem)          # stage cursor table (+Q) in shared memory when it fits
-        self.prefetch = int(prefetch)               # rounds ahead prefetched into L2 (-1 = auto: 1 when lanes >= 16)
+        self.prefetch = int(prefetch)               # rounds ahead prefetched into L2 (<= 0: off; measured neutral on B200)
         self.rng_mode = {"feed": abi.RNG_FEED, "pcg64": abi.RNG_PCG64, "philox": abi.RNG_PHILOX}[rng]
         if seed is None:
             seed = secrets.randbits(63)           # psrs.py:13 — default_rng(None) draws OS entropy
@@ -398,7 +398,7 @@ class BatchedPSRS:
                           compute_mode=abi.COMPUTE_F32 if compute == "f32" else abi.COMPUTE_F64, lanes=self.lanes,
                           n_episodes=int(n_episodes), ep_cap=ep_cap, stage_smem=int(self.stage_smem),
                           pops_per_lane=0 if self.rng_mode == abi.RNG_PCG64 else self.pops_per_lane,
-                          prefetch=self.prefetch if self.prefetch >= 0 else (1 if self.lanes >= 16 else 0),
+                          prefetch=max(self.prefetch, 0),
                           max_steps=int(max_steps),
                           gamma=float(gamma), alpha=_ptr(a_t), epsilon=_ptr(e_t), pi=_ptr(pi_t), Q=_ptr(Q), Gs=_ptr(Gs),
                           lengths=_ptr(lengths), trace_row=_ptr(trace_row), td_error=_ptr(td), trace_cap=int(trace_cap))

@@ -24,18 +24,26 @@ def philox_uniform(seed, stream, which, d):
     return (v >> 11) * (1.0 / 9007199254740992.0)
 
 
-def mix64(x):
-    x = (x + 0x9E3779B97F4A7C15) & M64
-    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & M64
-    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & M64
-    return x ^ (x >> 31)
+def fmix32(h):
+    h ^= h >> 16
+    h = (h * 0x85EBCA6B) & M32
+    h ^= h >> 13
+    h = (h * 0xC2B2AE35) & M32
+    h ^= h >> 16
+    return h
+
+
+def ring_replica_hash(ring_seed, replica):
+    h = fmix32((replica >> 32) & M32)
+    h = fmix32((replica & M32) ^ h)
+    h = fmix32(((ring_seed >> 32) & M32) ^ h)
+    return fmix32((ring_seed & M32) ^ h)
 
 
 def ring_start(ring_seed, replica, bucket, length):
-    h = mix64((mix64(ring_seed ^ ((replica * 0xD1342543DE82EF95) & M64)) + bucket) & M64)
-    return ((h >> 32) * length) >> 32
+    h = fmix32(ring_replica_hash(ring_seed, replica) ^ (((bucket + 1) * 0x9E3779B1) & M32))
+    return (h * length) >> 32
 
 
 def init_ring_start(ring_seed, replica, n_init):
-    h = mix64(ring_seed ^ mix64((replica + 0x51ED270B1) & M64))
-    return ((h >> 32) * n_init) >> 32
+    return (fmix32(ring_replica_hash(ring_seed, replica) ^ 0x85EBCA6B) * n_init) >> 32

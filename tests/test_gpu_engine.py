@@ -75,7 +75,7 @@ def test_bucketing_is_stable_counting_sort(ob, N, nS, nA, kw):
         nv = (nA + 3) // 4
         rec = log.records.cpu().numpy().reshape(N, 4 * nv + 4)
         assert np.array_equal(rec[:, :nA], g["p_log"][order])
-        assert np.all(rec[:, nA:4 * nv] == 0)
+        assert np.all(rec[:, nA:4 * nv] == 1)                        # padding entries hold 1.0
         assert np.array_equal(rec[:, 4 * nv], g["r"][order])
         tail = rec[:, 4 * nv + 1:].copy().view(np.int32)
         assert np.array_equal(tail[:, 0], g["z_next"][order])
