@@ -250,6 +250,12 @@ int ols_reset(const ols_queues_t* q, const ols_replicas_t* r, const uint8_t* mas
 int ols_step(const ols_queues_t* q, const ols_replicas_t* r, const uint8_t* mask, const void* p_new,
              int32_t p_new_is_f64, int64_t p_stride, int32_t reject_mode, int32_t compute_mode, int32_t lanes,
              const ols_step_out_t* out, void* stream);
+/* queue_evaluator.py:121-131 `QueueEvaluator_impl.step(a)`: queues keyed by (z, a), no rejection — every RUNNING
+ * replica with mask[r] != 0 pops the head of queue (cur_z, action[r]).  The queues must have been bucketed on the
+ * combined key (z + z_offset) * n_actions + a, i.e. q->n_buckets = n_state_keys * n_actions (queue_evaluator.py:107).
+ * OLS_NO_QUEUE = the reference's KeyError for a (z, a) pair that was never logged.                            */
+int ols_step_action(const ols_queues_t* q, const ols_replicas_t* r, const uint8_t* mask, const int32_t* action,
+                    const ols_step_out_t* out, void* stream);
 /* psrs.py:119-271 `qlearn_psrs` / `expSARSA_psrs` / `evalMC_psrs`, one independent run per replica,
  * fused with the agent update and the per-episode return evaluator.                            */
 int ols_run(const ols_queues_t* q, const ols_replicas_t* r, const ols_run_t* run, void* stream);

@@ -222,6 +222,48 @@ class OraclePSRS:
         return row
 
 
+class OracleQueueEvaluator:
+    """evaluators/queue_evaluator.py:90-131 — queues keyed by ``(z, a)`` (:107), the agent's own action picks the queue
+    (:125-127), no rejection.  ``step`` returns the row index, None on an empty queue, KeyError for an unlogged pair."""
+
+    def __init__(self, z, z_next, s, s_next, action, steps=None, n_state_keys=None, n_actions=None, z_offset=0, seed=None):
+        self.z, self.z_next = np.asarray(z), np.asarray(z_next)
+        self.s, self.s_next = np.asarray(s), np.asarray(s_next)
+        self.action = np.asarray(action).astype(np.int64)
+        n = self.z.shape[0]
+        self.nA, self.z_offset = n_actions, z_offset
+        key = (self.z.astype(np.int64) + z_offset) * n_actions + self.action
+        self.offsets, self.order = bucket(key, n_state_keys * n_actions, 0)
+        self.init = init_rows(steps, n)
+        if seed is not None:
+            self.order, self.init = apply_seed(self.offsets, self.order, self.init, seed)     # :104,110-111
+        self.cursor = np.zeros(n_state_keys * n_actions, dtype=np.int64)
+        self.init_cursor = 0
+        self.cur_z = self.cur_s = None
+
+    def reset(self):                                                                              # :113-119
+        if self.init_cursor >= self.init.size:
+            self.cur_s = None
+            return None
+        row = int(self.init[self.init_cursor])
+        self.init_cursor += 1
+        self.cur_z, self.cur_s = int(self.z[row]), self.s[row]
+        return self.cur_s
+
+    def step(self, a):                                                                            # :121-131
+        b = (self.cur_z + self.z_offset) * self.nA + int(a)
+        lo, hi = int(self.offsets[b]), int(self.offsets[b + 1])
+        if hi == lo:
+            raise KeyError((self.cur_z, int(a)))
+        c = int(self.cursor[b])
+        if c >= hi - lo:
+            return None
+        row = int(self.order[lo + c])
+        self.cursor[b] = c + 1
+        self.cur_s, self.cur_z = self.s_next[row], int(self.z_next[row])
+        return row
+
+
 # --------------------------------------------------------------------------- tabular policies
 def epsilon_greedy_row(q_row, epsilon, ties):
     """agents/tabular.py:24-32 for a single row: ``eps/nA`` everywhere, ``1-eps+eps/nA`` at a

@@ -121,29 +121,44 @@ extern "C" int ols_reset(const ols_queues_t* q, const ols_replicas_t* r, const u
   return OLS_OK;
 }
 
-extern "C" int ols_step(const ols_queues_t* q, const ols_replicas_t* r, const uint8_t* mask, const void* p_new,
-                        int32_t p_new_is_f64, int64_t p_stride, int32_t reject_mode, int32_t compute_mode, int32_t lanes,
-                        const ols_step_out_t* out, void* stream) {
-  int rc = check_sim(q, r, "ols_step");
+static int step_impl(const ols_queues_t* q, const ols_replicas_t* r, const uint8_t* mask, const void* p_new, int32_t p_new_is_f64,
+                     int64_t p_stride, int32_t reject_mode, int32_t compute_mode, int32_t lanes, const ols_step_out_t* out,
+                     const int32_t* act, void* stream, const char* who) {
+  int rc = check_sim(q, r, who);
   if (rc) return rc;
-  OLS_REQUIRE(valid_lanes(lanes), OLS_ERR_INVALID, "ols_step: lanes must be 1, 2, 4, 8, 16 or 32");
-  OLS_REQUIRE(reject_mode == OLS_REJECT_DEFAULT || reject_mode == OLS_REJECT_ACCEPT_ALL, OLS_ERR_INVALID, "ols_step: bad reject_mode");
-  OLS_REQUIRE(compute_mode == OLS_COMPUTE_F64 || compute_mode == OLS_COMPUTE_F32, OLS_ERR_INVALID, "ols_step: bad compute_mode");
+  OLS_REQUIRE(valid_lanes(lanes), OLS_ERR_INVALID, "%s: lanes must be 1, 2, 4, 8, 16 or 32", who);
+  OLS_REQUIRE(reject_mode == OLS_REJECT_DEFAULT || reject_mode == OLS_REJECT_ACCEPT_ALL, OLS_ERR_INVALID, "%s: bad reject_mode", who);
+  OLS_REQUIRE(compute_mode == OLS_COMPUTE_F64 || compute_mode == OLS_COMPUTE_F32, OLS_ERR_INVALID, "%s: bad compute_mode", who);
   if (r->n_replicas == 0) return OLS_OK;
-  OLS_REQUIRE(p_new && out && out->row && out->action && out->reward && out->terminal && out->s_next && out->z_from,
-              OLS_ERR_INVALID, "ols_step: null p_new / output buffer");
-  OLS_REQUIRE(p_stride == 0 || p_stride >= q->n_actions, OLS_ERR_INVALID, "ols_step: p_stride must be 0 or >= n_actions");
-  OLS_REQUIRE(q->records, OLS_ERR_INVALID, "ols_step: queues not bucketed");
+  OLS_REQUIRE((p_new || act) && out && out->row && out->action && out->reward && out->terminal && out->s_next && out->z_from,
+              OLS_ERR_INVALID, "%s: null input / output buffer", who);
+  OLS_REQUIRE(p_stride == 0 || p_stride >= q->n_actions, OLS_ERR_INVALID, "%s: p_stride must be 0 or >= n_actions", who);
+  OLS_REQUIRE(q->records, OLS_ERR_INVALID, "%s: queues not bucketed", who);
   const int grid = (int)((r->n_replicas * lanes + kThreads - 1) / kThreads);  // one lane group per replica
   cudaError_t e;
   switch ((q->n_actions + 3) / 4) {
-    case 1: e = ols_launch_step_nv1(*q, *r, mask, p_new, p_new_is_f64, p_stride, reject_mode, compute_mode, lanes, *out, grid, (cudaStream_t)stream); break;
-    case 2: e = ols_launch_step_nv2(*q, *r, mask, p_new, p_new_is_f64, p_stride, reject_mode, compute_mode, lanes, *out, grid, (cudaStream_t)stream); break;
-    case 3: e = ols_launch_step_nv3(*q, *r, mask, p_new, p_new_is_f64, p_stride, reject_mode, compute_mode, lanes, *out, grid, (cudaStream_t)stream); break;
-    default: e = ols_launch_step_nv4(*q, *r, mask, p_new, p_new_is_f64, p_stride, reject_mode, compute_mode, lanes, *out, grid, (cudaStream_t)stream); break;
+    case 1: e = ols_launch_step_nv1(*q, *r, mask, p_new, p_new_is_f64, p_stride, reject_mode, compute_mode, lanes, *out, grid, (cudaStream_t)stream, act); break;
+    case 2: e = ols_launch_step_nv2(*q, *r, mask, p_new, p_new_is_f64, p_stride, reject_mode, compute_mode, lanes, *out, grid, (cudaStream_t)stream, act); break;
+    case 3: e = ols_launch_step_nv3(*q, *r, mask, p_new, p_new_is_f64, p_stride, reject_mode, compute_mode, lanes, *out, grid, (cudaStream_t)stream, act); break;
+    default: e = ols_launch_step_nv4(*q, *r, mask, p_new, p_new_is_f64, p_stride, reject_mode, compute_mode, lanes, *out, grid, (cudaStream_t)stream, act); break;
   }
-  OLS_REQUIRE(e == cudaSuccess, OLS_ERR_CUDA, "ols_step: launch failed: %s", cudaGetErrorString(e));
+  OLS_REQUIRE(e == cudaSuccess, OLS_ERR_CUDA, "%s: launch failed: %s", who, cudaGetErrorString(e));
   return OLS_OK;
+}
+
+extern "C" int ols_step(const ols_queues_t* q, const ols_replicas_t* r, const uint8_t* mask, const void* p_new,
+                        int32_t p_new_is_f64, int64_t p_stride, int32_t reject_mode, int32_t compute_mode, int32_t lanes,
+                        const ols_step_out_t* out, void* stream) {
+  OLS_REQUIRE(p_new != nullptr || (r && r->n_replicas == 0), OLS_ERR_INVALID, "ols_step: null p_new");
+  return step_impl(q, r, mask, p_new, p_new_is_f64, p_stride, reject_mode, compute_mode, lanes, out, nullptr, stream, "ols_step");
+}
+
+extern "C" int ols_step_action(const ols_queues_t* q, const ols_replicas_t* r, const uint8_t* mask, const int32_t* action,
+                               const ols_step_out_t* out, void* stream) {
+  OLS_REQUIRE(action != nullptr || (r && r->n_replicas == 0), OLS_ERR_INVALID, "ols_step_action: null action");
+  OLS_REQUIRE(q && q->n_buckets % (q->n_actions > 0 ? q->n_actions : 1) == 0, OLS_ERR_INVALID,
+              "ols_step_action: queues must be keyed by (z, a): n_buckets = n_state_keys * n_actions");
+  return step_impl(q, r, mask, nullptr, 0, 0, OLS_REJECT_ACCEPT_ALL, OLS_COMPUTE_F64, 1, out, action, stream, "ols_step_action");
 }
 
 extern "C" int ols_run(const ols_queues_t* q, const ols_replicas_t* r, const ols_run_t* c, void* stream) {

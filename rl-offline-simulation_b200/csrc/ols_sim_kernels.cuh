@@ -429,7 +429,8 @@ __device__ __forceinline__ int pop_round(const ols_queues_t& q, const ols_replic
 template <int NV, int RNG>
 __global__ void __launch_bounds__(kThreads) step_kernel(ols_queues_t q, ols_replicas_t R, const uint8_t* mask,
                                                          const void* p_new, int p_new_is_f64, int64_t p_stride,
-                                                         int compute_mode, int G, ols_step_out_t out, ols_philox_keys PK) {
+                                                         int compute_mode, int G, ols_step_out_t out, ols_philox_keys PK,
+                                                         const int32_t* act) {
   constexpr int NA = 4 * NV;
   const Lane L = make_lane(G);
   const int nA = q.n_actions;
@@ -468,7 +469,11 @@ __global__ void __launch_bounds__(kThreads) step_kernel(ols_queues_t q, ols_repl
   B.lo = B.len = B.cur = 0;
   B.start = 0;
   int res = kPopIdle;
-  if (active && !load_bucket(q, R, ols_ring_replica_hash(R.ring_seed, rid), cur_tab, cur_z, B)) {
+  // queue_evaluator.py:107,125 — queues keyed by (z, a): the key is (z + z_offset) * n_actions + a, and the agent's
+  // own action picks the queue (act != NULL); otherwise the state alone does
+  const int key_z = act ? ((cur_z + q.z_offset) * q.n_actions + (exists ? __ldg(act + rr) : 0) - q.z_offset) : cur_z;
+  const bool act_ok = !act || ((unsigned)__ldg(act + rr) < (unsigned)q.n_actions);
+  if (active && (!act_ok || !load_bucket(q, R, ols_ring_replica_hash(R.ring_seed, rid), cur_tab, key_z, B))) {
     res = OLS_NO_QUEUE;
     active = false;
   }
@@ -987,10 +992,10 @@ inline cudaError_t launch_run_nv(const ols_queues_t& q, const ols_replicas_t& r,
 template <int NV>
 inline cudaError_t launch_step_nv(const ols_queues_t& q, const ols_replicas_t& r, const uint8_t* mask, const void* p_new,
                                   int p_new_is_f64, int64_t p_stride, int reject_mode, int compute_mode, int lanes,
-                                  const ols_step_out_t& out, int grid, cudaStream_t stream) {
+                                  const ols_step_out_t& out, int grid, cudaStream_t stream, const int32_t* act) {
 #define OLS_GO(RNG) \
   step_kernel<NV, RNG><<<grid, kThreads, 0, stream>>>(q, r, mask, p_new, p_new_is_f64, p_stride, compute_mode, lanes, out, \
-                                                      ols_philox_make_keys(r.seed))
+                                                      ols_philox_make_keys(r.seed), act)
   if (reject_mode == OLS_REJECT_ACCEPT_ALL) OLS_GO(RNGT_NONE);
   else if (r.rng_mode == OLS_RNG_PCG64) OLS_GO(RNGT_PCG64);
   else if (r.rng_mode == OLS_RNG_FEED) OLS_GO(RNGT_FEED);
@@ -1008,7 +1013,7 @@ cudaError_t ols_launch_run_nv3(const ols_queues_t&, const ols_replicas_t&, const
 cudaError_t ols_launch_run_nv4(const ols_queues_t&, const ols_replicas_t&, const ols_run_t&, const ols_sim::RunLaunch&, int ppl);
 #define OLS_STEP_ARGS                                                                                                      \
   const ols_queues_t &q, const ols_replicas_t &r, const uint8_t *mask, const void *p_new, int p_new_is_f64, int64_t p_stride, \
-      int reject_mode, int compute_mode, int lanes, const ols_step_out_t &out, int grid, cudaStream_t stream
+      int reject_mode, int compute_mode, int lanes, const ols_step_out_t &out, int grid, cudaStream_t stream, const int32_t *act
 cudaError_t ols_launch_step_nv1(OLS_STEP_ARGS);
 cudaError_t ols_launch_step_nv2(OLS_STEP_ARGS);
 cudaError_t ols_launch_step_nv3(OLS_STEP_ARGS);

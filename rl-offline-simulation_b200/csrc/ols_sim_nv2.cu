@@ -9,5 +9,5 @@ cudaError_t ols_launch_run_nv2(const ols_queues_t& q, const ols_replicas_t& r, c
 
 cudaError_t ols_launch_step_nv2(OLS_STEP_ARGS) {
   return ols_sim::launch_step_nv<2>(q, r, mask, p_new, p_new_is_f64, p_stride, reject_mode, compute_mode, lanes, out, grid,
-                                    stream);
+                                    stream, act);
 }

@@ -60,7 +60,7 @@ class BucketedLog:
     """
 
     def __init__(self, z, z_next, action, reward, terminal, p_log, s=None, s_next=None, steps=None,
-                 n_buckets=None, z_offset=None, device=None, keep_columns=False):
+                 n_buckets=None, z_offset=None, device=None, keep_columns=False, key_by_action=False):
         dev = _require_cuda(device)
         self.device = dev
         lib = abi.load()
@@ -109,6 +109,14 @@ class BucketedLog:
                 n_buckets = hi + z_offset + 1
             n_buckets = max(int(n_buckets), hi + z_offset + 1, 1)
 
+            # queue_evaluator.py:107 — QueueEvaluator keys its queues by (z, a): bucket on (z + z_offset) * nA + a
+            self.key_by_action = bool(key_by_action)
+            self.n_state_keys = n_buckets
+            z_key, key_offset = z, int(z_offset)
+            if key_by_action:
+                z_key = (z + int(z_offset)) * n_actions + action
+                key_offset = 0
+                n_buckets = n_buckets * n_actions
             self.n_rows, self.n_actions = n, n_actions
             self.n_buckets, self.z_offset = n_buckets, int(z_offset)
             self.rec_bytes = int(lib.ols_record_bytes(n_actions))
@@ -130,11 +138,14 @@ class BucketedLog:
                 raise ValueError(f"n_buckets = {n_buckets} is beyond what one bucketing pass supports")
             scratch = torch.empty(sb, dtype=torch.uint8, device=dev)
             n_init_dev = torch.zeros(1, dtype=torch.int64, device=dev)
-            q = abi.Queues(n_rows=n, n_init=0, n_actions=n_actions, n_buckets=n_buckets, z_offset=self.z_offset,
+            log_key = abi.Log(n_rows=n, n_actions=n_actions, p_is_f64=int(p.dtype == torch.float64), z=_ptr(z_key),
+                              z_next=_ptr(z_next), s=_ptr(s), s_next=_ptr(s_next), action=_ptr(action),
+                              reward=_ptr(reward), terminal=_ptr(terminal), p_log=_ptr(p), step=_ptr(steps))
+            q = abi.Queues(n_rows=n, n_init=0, n_actions=n_actions, n_buckets=n_buckets, z_offset=key_offset,
                            rec_bytes=self.rec_bytes, offsets=_ptr(self.offsets),
                            records=_ptr(self.records), init_row=_ptr(init_row), init_z=_ptr(init_z),
                            init_s=_ptr(init_s), s_next=_ptr(s_next), p_log64=_ptr(p_log64))
-            abi.check(lib.ols_bucket(C.byref(log), C.byref(q), _ptr(scratch), sb, _stream_ptr()))
+            abi.check(lib.ols_bucket(C.byref(log_key), C.byref(q), _ptr(scratch), sb, _stream_ptr()))
             abi.check(lib.ols_init_queue(C.byref(log), C.byref(q), _ptr(n_init_dev), _ptr(scratch), sb, _stream_ptr()))
             self.n_init = int(n_init_dev.item())        # one sync: construction is not the step path
             self.init_row = init_row[: max(self.n_init, 1)]
@@ -142,7 +153,7 @@ class BucketedLog:
             self.init_s = init_s[: max(self.n_init, 1)]
             self.seed = None
             self.base = self
-            self._columns = dict(z=z, z_next=z_next, action=action, reward=reward, terminal=terminal, p_log=p,
+            self._columns = dict(z=z_key, z_next=z_next, action=action, reward=reward, terminal=terminal, p_log=p,
                                  s=s, s_next=s_next, steps=steps) if keep_columns else None
             self._scratch = scratch if keep_columns else None
 
@@ -210,9 +221,9 @@ class BucketedLog:
         out.base = base
         return out
 
-    def queue_rows(self, z: int) -> torch.Tensor:
-        """Row indices of queue ``z`` in queue order (the reference's ``env.queues[z]``)."""
-        b = z + self.z_offset
+    def queue_rows(self, z: int, a: Optional[int] = None) -> torch.Tensor:
+        """Row indices of queue ``z`` (or ``(z, a)``) in queue order (the reference's ``env.queues[z]``)."""
+        b = (z + self.z_offset) * self.n_actions + a if self.key_by_action else z + self.z_offset
         lo, hi = int(self.offsets[b].item()), int(self.offsets[b + 1].item())
         return self.order[lo:hi]
 
@@ -349,6 +360,25 @@ class BatchedPSRS:
                               terminal=_ptr(self.out_terminal), s_next=_ptr(self.out_s_next), z_from=_ptr(self.out_z_from))
             abi.check(self.lib.ols_step(C.byref(q), C.byref(r), _ptr(m), _ptr(p), int(p.dtype == torch.float64), stride,
                                         self.reject_mode, cm, self.lanes, C.byref(out), _stream_ptr()))
+        return dict(row=self.out_row, action=self.out_action, reward=self.out_reward, terminal=self.out_terminal,
+                    s_next=self.out_s_next, z_from=self.out_z_from, status=self.status)
+
+    def step_action(self, actions, mask=None):
+        """queue_evaluator.py:121-131 for every RUNNING replica: pop the head of queue ``(z, actions[r])`` — no
+        rejection.  Needs a log bucketed with ``key_by_action=True``.  Returns the same dict as :meth:`step`."""
+        if not self.log.key_by_action:
+            raise ValueError("step_action needs BucketedLog(..., key_by_action=True)")
+        with torch.cuda.device(self.device):
+            a = _as_tensor(actions, self.device, torch.int32)
+            if a.dim() == 0:
+                a = a.expand(self.R).contiguous()
+            if a.shape[0] != self.R:
+                raise ValueError("actions must hold one action per replica")
+            m = None if mask is None else _as_tensor(mask, self.device, torch.uint8)
+            q, r = self.log.queues_struct(), self.replicas_struct()
+            out = abi.StepOut(row=_ptr(self.out_row), action=_ptr(self.out_action), reward=_ptr(self.out_reward),
+                              terminal=_ptr(self.out_terminal), s_next=_ptr(self.out_s_next), z_from=_ptr(self.out_z_from))
+            abi.check(self.lib.ols_step_action(C.byref(q), C.byref(r), _ptr(m), _ptr(a), C.byref(out), _stream_ptr()))
         return dict(row=self.out_row, action=self.out_action, reward=self.out_reward, terminal=self.out_terminal,
                     s_next=self.out_s_next, z_from=self.out_z_from, status=self.status)
 

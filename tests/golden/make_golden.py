@@ -485,6 +485,46 @@ def case_gridworld():
     save("gridworld", **out)
 
 
+def case_queue_evaluator():
+    """QueueEvaluator_impl (queues keyed by (z, a), no rejection) driven by a fixed action sequence."""
+    from offsim4rl.evaluators.queue_evaluator import QueueEvaluator_impl
+    rng = np.random.default_rng(31)
+    N, nS, nA = 500, 6, 3
+    log = make_log(rng, N, nS, nA)
+    out = {k: v for k, v in log.items()}
+    acts = rng.integers(0, nA, size=4 * N)
+    out["acts"] = acts
+    for seed in (0, 4):
+        rows, id2row = legacy_tuples(log)
+        rows = [(s, a, r, s_, d, p, {**info, "next_z": info["z_next"]}) for s, a, r, s_, d, p, info in rows]
+        env = QueueEvaluator_impl(rows, nS=nS, nA=nA)
+        env.reset_sampler(seed=seed)
+        order, offsets = [], [0]
+        for z in range(nS):
+            for a in range(nA):
+                qq = env.queues.get((z, a), [])
+                order.extend(id2row[id(e[7])] for e in qq)
+                offsets.append(offsets[-1] + len(qq))
+        out[f"order_{seed}"], out[f"offsets_{seed}"] = np.array(order), np.array(offsets)
+        trace, resets, k, status = [], [], 0, "exhausted"
+        s = env.reset()
+        resets.append(s)
+        try:
+            while s is not None:
+                s, r, done, info = env.step(acts[k]); k += 1
+                if s is None:
+                    break
+                trace.append(id2row[id(info["p"])])
+                if done:
+                    s = env.reset()
+                    resets.append(-1 if s is None else s)
+        except KeyError:
+            status = "keyerror"
+        out[f"trace_{seed}"], out[f"resets_{seed}"] = np.array(trace, dtype=np.int64), np.array(resets, dtype=np.int64)
+        out[f"status_{seed}"], out[f"nacts_{seed}"] = np.array(status), np.array(k)
+    save("queue_evaluator", **out)
+
+
 if __name__ == "__main__":
     case_seeded_walk()
     case_drivers()
@@ -492,3 +532,4 @@ if __name__ == "__main__":
     case_wrapper()
     case_encoders()
     case_gridworld()
+    case_queue_evaluator()

@@ -298,3 +298,86 @@ def test_torch_distribution_is_accepted(ob, golden):
     dist = torch.distributions.Categorical(probs=torch.tensor(g["disc_target"]))
     a, o, r, d, info = env.step_dist(dist)
     assert a == g["disc_old_a"][0] and o == g["disc_old_obs"][0]
+
+
+# ----------------------------------------------------------------------------- QueueEvaluator
+@pytest.mark.parametrize("seed", [0, 4])
+def test_queue_evaluator_matches_reference(ob, golden, seed):
+    from offsim4rl_b200.evaluators.queue_evaluator import QueueEvaluator_impl
+    g = golden("queue_evaluator")
+    rows = [(int(g["z"][i]), g["a"][i], g["r"][i], int(g["z_next"][i]), bool(g["done"][i]), g["p_log"][i],
+             {"z": int(g["z"][i]), "next_z": int(g["z_next"][i]), "t": int(g["t"][i])}) for i in range(len(g["z"]))]
+    env = QueueEvaluator_impl(rows, nS=6, nA=3)
+    env.reset_sampler(seed=seed)
+    assert np.array_equal(env._cur.offsets.cpu().numpy(), g[f"offsets_{seed}"])
+    assert np.array_equal(env._cur.order.cpu().numpy(), g[f"order_{seed}"])          # queue_evaluator.py:107,110-111
+    expect = g[f"trace_{seed}"]
+    n, resets, k, status = 0, [], 0, "exhausted"
+    s = env.reset()
+    resets.append(s)
+    try:
+        while s is not None:
+            s, r, done, info = env.step(g["acts"][k]); k += 1
+            if s is None:
+                break
+            row = int(expect[n]); n += 1
+            assert s == g["z_next"][row] and r == g["r"][row] and done == g["done"][row]
+            assert info["z"] == g["z"][row] and info["next_z"] == g["z_next"][row] and info["a"] == g["a"][row]
+            if done:
+                s = env.reset()
+                resets.append(-1 if s is None else s)
+    except KeyError:
+        status = "keyerror"
+    assert n == expect.size and np.array_equal(np.array(resets, dtype=np.int64), g[f"resets_{seed}"])
+    assert status == str(g[f"status_{seed}"]) and k == int(g[f"nacts_{seed}"])
+
+
+def test_batched_queue_evaluator_and_dataset_front_end(ob, golden):
+    import torch
+    from oracle import psrs_oracle as O
+    from offsim4rl_b200.data import OfflineDataset, ProbDistribution
+    from offsim4rl_b200 import spaces
+    from offsim4rl_b200.evaluators import QueueEvaluator
+    g = golden("queue_evaluator")
+    # batched: R replicas, each with its own action sequence, against independent oracle instances (log order)
+    R = 16
+    rng = np.random.default_rng(0)
+    log = ob.BucketedLog(z=g["z"], z_next=g["z_next"], action=g["a"], reward=g["r"], terminal=g["done"], p_log=g["p_log"],
+                         steps=g["t"], n_buckets=6, key_by_action=True)
+    sim = ob.BatchedPSRS(log, R, reject="accept_all")
+    envs = [O.OracleQueueEvaluator(z=g["z"], z_next=g["z_next"], s=g["z"], s_next=g["z_next"], action=g["a"], steps=g["t"],
+                                   n_state_keys=6, n_actions=3) for _ in range(R)]
+    sim.reset()
+    for e in envs:
+        e.reset()
+    alive = np.ones(R, dtype=bool)
+    for it in range(60):
+        acts = rng.integers(0, 3, R)
+        out = sim.step_action(acts, mask=alive.astype(np.uint8))
+        rows = out["row"].cpu().numpy()
+        for r, e in enumerate(envs):
+            if not alive[r]:
+                continue
+            try:
+                row = e.step(acts[r])
+            except KeyError:
+                row = None
+                assert int(out["status"][r]) == O.NO_QUEUE
+            if row is None:
+                assert rows[r] == -1
+                alive[r] = False
+            else:
+                assert rows[r] == row
+    # dataset front end (queue_evaluator.py:8-88)
+    ds = OfflineDataset(observation_space=spaces.Discrete(6), action_space=spaces.Discrete(3),
+                        action_dist_type=ProbDistribution.Discrete, observations=g["z"], actions=g["a"],
+                        action_distributions=g["p_log"], rewards=g["r"], next_observations=g["z_next"], terminals=g["done"],
+                        steps=g["t"])
+    qe = QueueEvaluator(ds)
+    qe.reset_sampler(seed=0)
+    obs = qe.reset()
+    assert obs == g["resets_0"][0]
+    nxt, r, done, info = qe.step(int(g["acts"][0]))
+    assert nxt == g["z_next"][g["trace_0"][0]]
+    a, nxt, r, done, info = qe.step_dist(torch.distributions.Categorical(probs=torch.tensor([0.0, 1.0, 0.0])))
+    assert a == 1

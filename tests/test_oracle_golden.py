@@ -169,3 +169,29 @@ def test_reference_gridworld_scenario(golden):
         counts.append(n)
     assert np.array_equal(counts, g["steps_simulated_by_seed"])
     assert min(counts) > 40
+
+
+# --------------------------------------------------------------------------- QueueEvaluator
+@pytest.mark.parametrize("seed", [0, 4])
+def test_queue_evaluator_oracle_matches_reference(golden, seed):
+    g = golden("queue_evaluator")
+    env = O.OracleQueueEvaluator(z=g["z"], z_next=g["z_next"], s=g["z"], s_next=g["z_next"], action=g["a"], steps=g["t"],
+                                 n_state_keys=6, n_actions=3, seed=seed)
+    assert np.array_equal(env.offsets, g[f"offsets_{seed}"]) and np.array_equal(env.order, g[f"order_{seed}"])
+    trace, resets, k, status = [], [], 0, "exhausted"
+    s = env.reset()
+    resets.append(s)
+    try:
+        while s is not None:
+            row = env.step(g["acts"][k]); k += 1
+            if row is None:
+                break
+            trace.append(row)
+            s = env.cur_s
+            if g["done"][row]:
+                s = env.reset()
+                resets.append(-1 if s is None else s)
+    except KeyError:
+        status = "keyerror"
+    assert np.array_equal(trace, g[f"trace_{seed}"]) and np.array_equal(np.array(resets, dtype=np.int64), g[f"resets_{seed}"])
+    assert status == str(g[f"status_{seed}"]) and k == int(g[f"nacts_{seed}"])
