@@ -256,6 +256,17 @@ int ols_step(const ols_queues_t* q, const ols_replicas_t* r, const uint8_t* mask
  * OLS_NO_QUEUE = the reference's KeyError for a (z, a) pair that was never logged.                            */
 int ols_step_action(const ols_queues_t* q, const ols_replicas_t* r, const uint8_t* mask, const int32_t* action,
                     const ols_step_out_t* out, void* stream);
+/* psrs.py:99-117 `PSRS_Exo.step`: observations split into an endogenous state s and an exogenous state x; the log is
+ * bucketed twice (qs keyed by s, qx keyed by x, both over the same rows; the x-queue record's z_next field holds x').
+ * One pop consumes the head of both queues; the accept rule runs on the s-record; the step returns s' of the accepted
+ * s-record (out->s_next) and x' of the x-record popped with it (out_x_next).  r->cursor / r->cur_z are the s-side
+ * cursor table and current s; cursor_x [n_replicas][qx->n_buckets] and cur_x [n_replicas] the x side.            */
+int ols_step_exo(const ols_queues_t* qs, const ols_queues_t* qx, const ols_replicas_t* r, int32_t* cursor_x, int32_t* cur_x,
+                 const uint8_t* mask, const void* p_new, int32_t p_new_is_f64, int64_t p_stride, int32_t compute_mode,
+                 int32_t lanes, const ols_step_out_t* out, int32_t* out_x_next, void* stream);
+/* psrs.py:92 (PSRS_Exo.reset), queue_evaluator.py:114 — `rejection_sampling_rng = default_rng(seed)` again: re-seed the
+ * PCG64 state of the replicas with mask[r] != 0 from seeds[r] (NULL = r->seed) and restart their draw counters.     */
+int ols_reseed(const ols_replicas_t* r, const uint64_t* seeds, const uint8_t* mask, void* stream);
 /* psrs.py:119-271 `qlearn_psrs` / `expSARSA_psrs` / `evalMC_psrs`, one independent run per replica,
  * fused with the agent update and the per-episode return evaluator.                            */
 int ols_run(const ols_queues_t* q, const ols_replicas_t* r, const ols_run_t* run, void* stream);

@@ -222,6 +222,53 @@ class OraclePSRS:
         return row
 
 
+class OraclePSRSExo:
+    """evaluators/psrs.py:59-117 — endogenous queues keyed by s, exogenous queues keyed by x, popped in lock-step;
+    ``reset(seed)`` re-creates the rejection generator (psrs.py:92).  ``step`` returns ``(row_s, x_next)`` or None."""
+
+    def __init__(self, s, x, s_next, x_next, action, p_log, steps, n_s, n_x, seed=None):
+        self.s, self.x, self.s_next, self.x_next = (np.asarray(v) for v in (s, x, s_next, x_next))
+        self.action, self.p_log = np.asarray(action), np.asarray(p_log)
+        n = self.s.shape[0]
+        self.off_s, self.ord_s = bucket(self.s, n_s)
+        self.off_x, self.ord_x = bucket(self.x, n_x)
+        self.init = init_rows(steps, n)
+        if seed is not None:
+            self.ord_s, self.init = apply_seed(self.off_s, self.ord_s, self.init, seed)         # psrs.py:79,86-87
+            self.ord_x, _ = apply_seed(self.off_x, self.ord_x, np.zeros(0, dtype=np.int64), seed)  # psrs.py:88-89
+        self.cur_s_tab = np.zeros(n_s, dtype=np.int64)
+        self.cur_x_tab = np.zeros(n_x, dtype=np.int64)
+        self.init_cursor = 0
+        self.cs = self.cx = None
+        self.rng = None
+
+    def reset(self, seed):                                                                       # psrs.py:91-97
+        self.rng = Pcg64Uniforms(seed)
+        if self.init_cursor >= self.init.size:
+            return None
+        row = int(self.init[self.init_cursor])
+        self.init_cursor += 1
+        self.cs, self.cx = int(self.s[row]), int(self.x[row])
+        return row
+
+    def step(self, p_new):                                                                       # psrs.py:99-117
+        bs, bx = self.cs, self.cx
+        if self.off_s[bs + 1] == self.off_s[bs] or self.off_x[bx + 1] == self.off_x[bx]:
+            raise KeyError((bs, bx))
+        while True:
+            cs, cx = int(self.cur_s_tab[bs]), int(self.cur_x_tab[bx])
+            if cs >= self.off_s[bs + 1] - self.off_s[bs] or cx >= self.off_x[bx + 1] - self.off_x[bx]:
+                return None
+            row_s = int(self.ord_s[self.off_s[bs] + cs])
+            row_x = int(self.ord_x[self.off_x[bx] + cx])
+            self.cur_s_tab[bs] += 1
+            self.cur_x_tab[bx] += 1
+            if not rejects(self.rng.random(), p_new, self.p_log[row_s], self.action[row_s]):
+                break
+        self.cs, self.cx = int(self.s_next[row_s]), int(self.x_next[row_x])
+        return row_s, self.cx
+
+
 class OracleQueueEvaluator:
     """evaluators/queue_evaluator.py:90-131 — queues keyed by ``(z, a)`` (:107), the agent's own action picks the queue
     (:125-127), no rejection.  ``step`` returns the row index, None on an empty queue, KeyError for an unlogged pair."""

@@ -81,6 +81,9 @@ SIGNATURES = {
     "ols_step": (C.c_int, [C.POINTER(Queues), C.POINTER(Replicas), p, p, i32, i64, i32, i32, i32,
                            C.POINTER(StepOut), p]),
     "ols_step_action": (C.c_int, [C.POINTER(Queues), C.POINTER(Replicas), p, p, C.POINTER(StepOut), p]),
+    "ols_step_exo": (C.c_int, [C.POINTER(Queues), C.POINTER(Queues), C.POINTER(Replicas), p, p, p, p, i32, i64, i32, i32,
+                               C.POINTER(StepOut), p, p]),
+    "ols_reseed": (C.c_int, [C.POINTER(Replicas), p, p, p]),
     "ols_run": (C.c_int, [C.POINTER(Queues), C.POINTER(Replicas), C.POINTER(Run), p]),
     "ols_curve_scratch_bytes": (C.c_size_t, [i64, i32]),
     "ols_reduce_curves": (C.c_int, [p, p, i64, i32, i32, p, p, p, p, C.c_size_t, p]),

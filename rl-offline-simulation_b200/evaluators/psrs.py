@@ -182,6 +182,108 @@ class PSRS(object):
         self.s = None if st == abi.INIT_EMPTY else int(self._sim.cur_s[0])
 
 
+class PSRS_Exo(object):
+    """Rejection sampler with an exogenous state (reference: psrs.py:59-117).
+
+    An observation ``o`` splits into an endogenous state ``s`` and an exogenous state ``x`` (``o_split_func``); the
+    log is bucketed by ``s`` and, independently, by ``x``; one pop consumes the head of both queues and the usual
+    accept rule runs on the s-record; the next observation is ``o_combine_func(s', x')``.  ``s`` and ``x`` must be
+    integers.  ``buffer`` rows are ``(o, a, r, o', done, p, info)`` with ``info['t']``.
+    """
+
+    def __init__(self, buffer, nO=25, nA=5, o_split_func=lambda o: (o, 0), o_combine_func=lambda s, x: s, device=None):
+        rows = list(buffer)
+        n = len(rows)
+        self.nS = self.nO = nO
+        self.nA = nA
+        self.o_split_func, self.o_combine_func = o_split_func, o_combine_func
+        split = [o_split_func(r[0]) for r in rows]
+        split_next = [o_split_func(r[3]) for r in rows]
+        s = np.array([int(a) for a, _ in split], dtype=np.int64)
+        x = np.array([int(b) for _, b in split], dtype=np.int64)
+        s2 = np.array([int(a) for a, _ in split_next], dtype=np.int64)
+        x2 = np.array([int(b) for _, b in split_next], dtype=np.int64)
+        self._o_rows = [r[0] for r in rows]
+        self._x = x
+        self._action = np.array([r[1] for r in rows])
+        self._reward = np.array([r[2] for r in rows])
+        self._terminal = np.array([bool(r[4]) for r in rows])
+        self._p_log = np.stack([np.asarray(r[5]) for r in rows]) if n else np.zeros((0, nA), dtype=np.float32)
+        t = np.fromiter((r[6]["t"] for r in rows), dtype=np.int64, count=n)
+        common = dict(action=self._action, reward=self._reward, terminal=self._terminal, p_log=self._p_log, steps=t, device=device)
+        self._log_s = BucketedLog(z=s, z_next=s2, **common)      # psrs.py:82
+        self._log_x = BucketedLog(z=x, z_next=x2, **common)      # psrs.py:83
+        self._sim = None
+        self.o = self.s = None
+        self.reset_sampler()
+        self.reset()
+
+    def reset_sampler(self, seed=None):                                     # psrs.py:77-89
+        if seed is None:
+            seed = secrets.randbits(63)
+        self._cur_s, self._cur_x = self._log_s.seeded(int(seed)), self._log_x.seeded(int(seed))
+        self._init_rows_host = self._cur_s.init_row[: self._cur_s.n_init].cpu().numpy()
+        if self._sim is None:
+            self._sim = BatchedPSRS(self._cur_s, 1, rng="pcg64", seed=int(seed), lanes=4)
+            dev = self._sim.device
+            self._cursor_x = torch.zeros((1, self._log_x.n_buckets), dtype=torch.int32, device=dev)
+            self._x_state = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._out_x = torch.zeros(1, dtype=torch.int32, device=dev)
+        else:
+            self._sim.restart(self._cur_s)
+            self._cursor_x.zero_()
+            if self.o is not None:
+                s_now, x_now = self.o_split_func(self.o)
+                self._sim.cur_z.fill_(int(s_now))
+                self._x_state.fill_(int(x_now))
+                self._sim.status.fill_(abi.RUNNING)
+        self._n_resets = 0
+
+    def reset(self, seed=None):                                             # psrs.py:91-97
+        import ctypes as C
+        from ..engine import _ptr, _stream_ptr
+        if seed is None:
+            seed = secrets.randbits(63)
+        sim = self._sim
+        sim.seed = int(seed)
+        with torch.cuda.device(sim.device):
+            r = sim.replicas_struct()
+            abi.check(sim.lib.ols_reseed(C.byref(r), _ptr(None), _ptr(None), _stream_ptr()))   # default_rng(seed) again
+        _, status = sim.reset()
+        if int(status[0]) != abi.RUNNING:
+            self.s = None
+            return None
+        row = int(self._init_rows_host[self._n_resets])
+        self._n_resets += 1
+        self.o = self._o_rows[row]
+        self._x_state.fill_(int(self._x[row]))
+        return self.o
+
+    def step(self, p_new):                                                  # psrs.py:99-117
+        import ctypes as C
+        from ..engine import _as_tensor, _ptr, _stream_ptr
+        sim = self._sim
+        with torch.cuda.device(sim.device):
+            p = _as_tensor(np.asarray(p_new), sim.device)
+            if p.dtype not in (torch.float32, torch.float64):
+                p = p.to(torch.float64)
+            compute = abi.COMPUTE_F32 if (p.dtype == torch.float32 and self._log_s.p_source_f32) else abi.COMPUTE_F64
+            qs, qx, r = self._cur_s.queues_struct(), self._cur_x.queues_struct(), sim.replicas_struct()
+            out = abi.StepOut(row=_ptr(sim.out_row), action=_ptr(sim.out_action), reward=_ptr(sim.out_reward),
+                              terminal=_ptr(sim.out_terminal), s_next=_ptr(sim.out_s_next), z_from=_ptr(sim.out_z_from))
+            abi.check(sim.lib.ols_step_exo(C.byref(qs), C.byref(qx), C.byref(r), _ptr(self._cursor_x), _ptr(self._x_state),
+                                           _ptr(None), _ptr(p), int(p.dtype == torch.float64), 0, compute, sim.lanes,
+                                           C.byref(out), _ptr(self._out_x), _stream_ptr()))
+        row = int(sim.out_row[0])
+        if row < 0:
+            if int(sim.status[0]) == abi.NO_QUEUE:
+                raise KeyError(self.o_split_func(self.o))
+            return None, None, None, None
+        s_from = int(sim.out_z_from[0])
+        self.o = self.o_combine_func(int(sim.out_s_next[0]), int(self._out_x[0]))
+        return self.o, self._reward[row], self._terminal[row], {"s": s_from, "a": self._action[row], "p": self._p_log[row]}
+
+
 # --------------------------------------------------------------------------------------------------- drivers
 def _schedule(x):
     return x if callable(x) else (lambda episode: x)

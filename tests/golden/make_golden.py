@@ -525,6 +525,50 @@ def case_queue_evaluator():
     save("queue_evaluator", **out)
 
 
+def case_psrs_exo():
+    """PSRS_Exo (psrs.py:59-117): o = 3*s + x, split/combine by divmod; the reference's own generator, re-seeded by
+    reset(seed=episode)."""
+    rng = np.random.default_rng(41)
+    N, nS, nX, nA = 600, 5, 3, 3
+    log = make_log(rng, N, nS, nA, ep_len=6)
+    x = rng.integers(0, nX, N)
+    x_next = rng.integers(0, nX, N)
+    o, o_next = log["z"] * nX + x, log["z_next"] * nX + x_next
+    out = {k: v for k, v in log.items()}
+    out.update(x=x, x_next=x_next)
+    p_new = np.array([0.5, 0.2, 0.3])
+    out["p_new"] = p_new
+    rows, id2row = [], {}
+    for i in range(N):
+        p = np.array(log["p_log"][i], copy=True)
+        id2row[id(p)] = i
+        rows.append((int(o[i]), int(log["a"][i]), log["r"][i], int(o_next[i]), bool(log["done"][i]), p, {"t": int(log["t"][i])}))
+    env = ref_psrs.PSRS_Exo(rows, nO=nS * nX, nA=nA, o_split_func=lambda v: divmod(v, nX), o_combine_func=lambda s, xx: s * nX + xx)
+    # the reference deep-copies the buffer (psrs.py:65): recover rows through the copied p_log objects
+    id2row = {id(e[5]): i for i, e in enumerate(env.raw_buffer)}
+    for seed in (1, 6):
+        env.reset_sampler(seed=seed)
+        trace, obs, episode, status = [], [], 0, "exhausted"
+        ob = env.reset(seed=episode)
+        obs.append(-1 if ob is None else ob)
+        try:
+            while ob is not None:
+                ob, r, done, info = env.step(p_new)
+                if ob is None:
+                    break
+                trace.append(id2row[id(info["p"])])
+                obs.append(ob)
+                if done:
+                    episode += 1
+                    ob = env.reset(seed=episode)
+                    obs.append(-1 if ob is None else ob)
+        except KeyError:
+            status = "keyerror"
+        out[f"trace_{seed}"], out[f"obs_{seed}"] = np.array(trace, dtype=np.int64), np.array(obs, dtype=np.int64)
+        out[f"status_{seed}"] = np.array(status)
+    save("psrs_exo", **out)
+
+
 if __name__ == "__main__":
     case_seeded_walk()
     case_drivers()
@@ -533,3 +577,4 @@ if __name__ == "__main__":
     case_encoders()
     case_gridworld()
     case_queue_evaluator()
+    case_psrs_exo()

@@ -381,3 +381,33 @@ def test_batched_queue_evaluator_and_dataset_front_end(ob, golden):
     assert nxt == g["z_next"][g["trace_0"][0]]
     a, nxt, r, done, info = qe.step_dist(torch.distributions.Categorical(probs=torch.tensor([0.0, 1.0, 0.0])))
     assert a == 1
+
+
+# ----------------------------------------------------------------------------- PSRS_Exo
+@pytest.mark.parametrize("seed", [1, 6])
+def test_psrs_exo_matches_reference(ob, golden, seed):
+    """Two queue families popped in lock-step, the generator re-seeded by reset(seed=episode): same observations
+    and accepted rows as the reference's PSRS_Exo running on its own NumPy generator."""
+    from offsim4rl_b200.evaluators.psrs import PSRS_Exo
+    g = golden("psrs_exo")
+    nX, N = 3, len(g["z"])
+    o, o_next = g["z"] * nX + g["x"], g["z_next"] * nX + g["x_next"]
+    rows = [(int(o[i]), int(g["a"][i]), g["r"][i], int(o_next[i]), bool(g["done"][i]), g["p_log"][i], {"t": int(g["t"][i])})
+            for i in range(N)]
+    env = PSRS_Exo(rows, nO=15, nA=3, o_split_func=lambda v: divmod(v, nX), o_combine_func=lambda s, x: s * nX + x)
+    env.reset_sampler(seed=seed)
+    expect, obs, n, episode = g[f"trace_{seed}"], [], 0, 0
+    ob_ = env.reset(seed=episode)
+    obs.append(-1 if ob_ is None else ob_)
+    while ob_ is not None:
+        ob_, r, done, info = env.step(g["p_new"])
+        if ob_ is None:
+            break
+        row = int(expect[n]); n += 1
+        assert r == g["r"][row] and done == g["done"][row] and info["a"] == g["a"][row] and info["s"] == g["z"][row]
+        obs.append(ob_)
+        if done:
+            episode += 1
+            ob_ = env.reset(seed=episode)
+            obs.append(-1 if ob_ is None else ob_)
+    assert n == expect.size and np.array_equal(np.array(obs, dtype=np.int64), g[f"obs_{seed}"])

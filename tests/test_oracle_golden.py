@@ -195,3 +195,28 @@ def test_queue_evaluator_oracle_matches_reference(golden, seed):
         status = "keyerror"
     assert np.array_equal(trace, g[f"trace_{seed}"]) and np.array_equal(np.array(resets, dtype=np.int64), g[f"resets_{seed}"])
     assert status == str(g[f"status_{seed}"]) and k == int(g[f"nacts_{seed}"])
+
+
+# --------------------------------------------------------------------------- PSRS_Exo
+@pytest.mark.parametrize("seed", [1, 6])
+def test_psrs_exo_oracle_matches_reference(golden, seed):
+    g = golden("psrs_exo")
+    nX = 3
+    env = O.OraclePSRSExo(s=g["z"], x=g["x"], s_next=g["z_next"], x_next=g["x_next"], action=g["a"], p_log=g["p_log"],
+                          steps=g["t"], n_s=5, n_x=nX, seed=seed)
+    trace, obs, episode = [], [], 0
+    row = env.reset(episode)
+    obs.append(-1 if row is None else int(g["z"][row]) * nX + int(g["x"][row]))
+    while row is not None:
+        res = env.step(g["p_new"])
+        if res is None:
+            break
+        row_s, x_next = res
+        trace.append(row_s)
+        obs.append(int(g["z_next"][row_s]) * nX + x_next)
+        row = row_s
+        if g["done"][row_s]:
+            episode += 1
+            row = env.reset(episode)
+            obs.append(-1 if row is None else int(g["z"][row]) * nX + int(g["x"][row]))
+    assert np.array_equal(trace, g[f"trace_{seed}"]) and np.array_equal(obs, g[f"obs_{seed}"])
