@@ -199,6 +199,7 @@ def main():
     ap.add_argument("--budget", type=int, help="accepted transitions per replica per step")
     ap.add_argument("--lanes", type=int)
     ap.add_argument("--prefetch", type=int, default=-1)
+    ap.add_argument("--ppl", type=int, default=0, help="records per lane per round (0 = auto)")
     ap.add_argument("--no-ring", action="store_true", help="all replicas consume the queues from slot 0 (L2-resident gather)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--skip-cpu", action="store_true")
@@ -249,7 +250,7 @@ def main():
     log.drop_columns()
     rec_bytes = log.rec_bytes
     bucket_bytes = N * (12 + 17 + 4 * nA + rec_bytes)   # z twice + order, log columns once, record written once
-    sim = ob.BatchedPSRS(log, R, rng="philox", seed=1234, ring=not args.no_ring, ring_seed=99, replica_id0=rank * R, lanes=wl["lanes"], prefetch=args.prefetch)
+    sim = ob.BatchedPSRS(log, R, rng="philox", seed=1234, ring=not args.no_ring, ring_seed=99, replica_id0=rank * R, lanes=wl["lanes"], prefetch=args.prefetch, pops_per_lane=args.ppl)
     Q = torch.zeros((R, nS, nA), dtype=torch.float32, device=dev) if qlearn else None
     res = None
 

@@ -180,7 +180,7 @@ typedef struct ols_run {
   int32_t ep_cap;             /* row length of Gs / lengths (>= n_episodes + 1)                  */
   int32_t stage_smem;         /* 1: stage the replica's cursor table (and Q) in shared memory
                                  when it fits; 0: operate on global memory                       */
-  int32_t pops_per_lane;      /* records each lane examines per round: 1, 2, or 0 = auto (2 with
+  int32_t pops_per_lane;      /* records each lane examines per round: 1, 2, 4, or 0 = auto (2 with
                                  Philox/fed uniforms, 1 with PCG64 replay)                       */
   int32_t prefetch;           /* rounds ahead whose records are prefetched into L2 (0 = off; useful for
                                  long reject chains, i.e. lanes >= 16)                           */

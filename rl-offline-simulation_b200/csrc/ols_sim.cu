@@ -172,8 +172,9 @@ extern "C" int ols_run(const ols_queues_t* q, const ols_replicas_t* r, const ols
               "ols_run: need n_states >= 1 and ep_cap >= n_episodes + 1");
   OLS_REQUIRE(c->reject_mode == OLS_REJECT_DEFAULT || c->reject_mode == OLS_REJECT_ACCEPT_ALL, OLS_ERR_INVALID, "ols_run: bad reject_mode");
   OLS_REQUIRE(c->compute_mode == OLS_COMPUTE_F64 || c->compute_mode == OLS_COMPUTE_F32, OLS_ERR_INVALID, "ols_run: bad compute_mode");
-  OLS_REQUIRE(c->pops_per_lane >= 0 && c->pops_per_lane <= 2, OLS_ERR_INVALID, "ols_run: pops_per_lane must be 0, 1 or 2");
-  OLS_REQUIRE(!(c->pops_per_lane == 2 && r->rng_mode == OLS_RNG_PCG64), OLS_ERR_UNSUPPORTED,
+  OLS_REQUIRE(c->pops_per_lane == 0 || c->pops_per_lane == 1 || c->pops_per_lane == 2 || c->pops_per_lane == 4, OLS_ERR_INVALID,
+              "ols_run: pops_per_lane must be 0, 1, 2 or 4");
+  OLS_REQUIRE(!(c->pops_per_lane >= 2 && r->rng_mode == OLS_RNG_PCG64), OLS_ERR_UNSUPPORTED,
               "ols_run: PCG64 replay examines one record per lane per round");
   if (r->n_replicas == 0) return OLS_OK;
   OLS_REQUIRE(c->Gs && c->lengths, OLS_ERR_INVALID, "ols_run: null Gs / lengths");

@@ -218,7 +218,7 @@ __device__ __forceinline__ int pop_round(const ols_queues_t& q, const ols_replic
   constexpr int NA = 4 * NV;
   constexpr int kRec = 16 * (NV + 1);  // record bytes
   constexpr bool accept_all = (RNG == RNGT_NONE);
-  constexpr bool paired = (RNG == RNGT_PHILOX && PPL == 2);  // one Philox block serves the lane's two pops
+  constexpr bool paired = (RNG == RNGT_PHILOX && PPL % 2 == 0);  // one Philox block serves two consecutive pops of a lane
   static_assert(RNG != RNGT_PCG64 || PPL == 1, "PCG64 replay is sequential per lane group: one pop per lane");
   static_assert(!accept_all || PPL == 1, "accept-all examines one record per round");
   typedef typename std::conditional<RNG == RNGT_PHILOX, float, double>::type ustore_t;
@@ -283,23 +283,26 @@ __device__ __forceinline__ int pop_round(const ols_queues_t& q, const ols_replic
   }
   ols_u128 stepped = pcg_s;
   if (paired) {
-    if (valid[0] || valid[1]) {
-      const uint64_t blk = ((draws - (uint64_t)align) >> 1) + (uint64_t)sub;
-      ols_u4 c;
-      c.x = (uint32_t)blk;
-      c.y = (uint32_t)(blk >> 32);
-      c.z = (uint32_t)rid;
-      c.w = (uint32_t)(rid >> 32);
-      const ols_u4 o = ols_philox4x32_10_keyed(c, PK);
-      // float image of u from its top 32 bits: |error| <= 2^-32 + 2^-24 u, i.e. < 2^-19 relative once u >= 2^-12;
-      // the rare smaller draws (2.4e-4) are converted from all 53 bits instead
-      float f0 = __uint2float_rn(o.y) * 2.3283064365386963e-10f, f1 = __uint2float_rn(o.w) * 2.3283064365386963e-10f;
-      if (o.y < (1u << 20)) f0 = __ull2float_rn((((uint64_t)o.y << 32) | o.x) >> 11) * 1.1102230246251565e-16f;
-      if (o.w < (1u << 20)) f1 = __ull2float_rn((((uint64_t)o.w << 32) | o.z) >> 11) * 1.1102230246251565e-16f;
-      u[0] = (ustore_t)f0;
-      u[PPL - 1] = (ustore_t)f1;
-      tiny[0] = !(f0 >= 8.6736174e-19f);  // u < 2^-60 (incl. 0): not resolved in float32
-      tiny[PPL - 1] = !(f1 >= 8.6736174e-19f);
+#pragma unroll
+    for (int j = 0; j < PPL / 2; ++j) {
+      if (valid[2 * j] || valid[2 * j + 1]) {
+        const uint64_t blk = ((draws - (uint64_t)align) >> 1) + (uint64_t)(sub * (PPL / 2) + j);
+        ols_u4 c;
+        c.x = (uint32_t)blk;
+        c.y = (uint32_t)(blk >> 32);
+        c.z = (uint32_t)rid;
+        c.w = (uint32_t)(rid >> 32);
+        const ols_u4 o = ols_philox4x32_10_keyed(c, PK);
+        // float image of u from its top 32 bits: |error| <= 2^-32 + 2^-24 u, i.e. < 2^-19 relative once u >= 2^-12;
+        // the rare smaller draws (2.4e-4) are converted from all 53 bits instead
+        float f0 = __uint2float_rn(o.y) * 2.3283064365386963e-10f, f1 = __uint2float_rn(o.w) * 2.3283064365386963e-10f;
+        if (o.y < (1u << 20)) f0 = __ull2float_rn((((uint64_t)o.y << 32) | o.x) >> 11) * 1.1102230246251565e-16f;
+        if (o.w < (1u << 20)) f1 = __ull2float_rn((((uint64_t)o.w << 32) | o.z) >> 11) * 1.1102230246251565e-16f;
+        u[2 * j] = (ustore_t)f0;
+        u[2 * j + 1] = (ustore_t)f1;
+        tiny[2 * j] = !(f0 >= 8.6736174e-19f);  // u < 2^-60 (incl. 0): not resolved in float32
+        tiny[2 * j + 1] = !(f1 >= 8.6736174e-19f);
+      }
     }
   } else if (!accept_all) {
 #pragma unroll
@@ -354,15 +357,6 @@ __device__ __forceinline__ int pop_round(const ols_queues_t& q, const ols_replic
   }
   // ---- first accepting pop of each group, in queue order
   int first_acc = 1 << 20, first_lack = 1 << 20;
-#ifdef OLS_EXP_OLDBALLOT
-  if (PPL == 2) {
-#pragma unroll
-    for (int i = 0; i < PPL; ++i) {
-      const unsigned ba = (__ballot_sync(kFull, acc[i]) >> gbase) & gmask;
-      if (ba) first_acc = min(first_acc, (__ffs(ba) - 1) * PPL + i - align);
-    }
-  } else {
-#else
   if (PPL == 2) {
     const unsigned g_any = (__ballot_sync(kFull, acc[0] || acc[PPL - 1]) >> gbase) & gmask;
     const unsigned g_a0 = (__ballot_sync(kFull, acc[0]) >> gbase) & gmask;
@@ -371,9 +365,14 @@ __device__ __forceinline__ int pop_round(const ols_queues_t& q, const ols_replic
       first_acc = 2 * w + (((g_a0 >> w) & 1u) ? 0 : 1) - align;
     }
   } else {
-#endif
-    const unsigned ba = (__ballot_sync(kFull, acc[0]) >> gbase) & gmask;
-    if (ba) first_acc = __ffs(ba) - 1;
+    // each lane's earliest accepting pop, then the earliest lane of the group
+    int mine = PPL;
+#pragma unroll
+    for (int i = PPL - 1; i >= 0; --i) mine = acc[i] ? i : mine;
+    const unsigned g_any = (__ballot_sync(kFull, mine < PPL) >> gbase) & gmask;
+    const int w = g_any ? __ffs(g_any) - 1 : 0;
+    const int wi = __shfl_sync(kFull, mine, gbase + w);
+    if (g_any) first_acc = w * PPL + wi - align;
   }
   if (RNG == RNGT_FEED) {
 #pragma unroll
@@ -399,7 +398,9 @@ __device__ __forceinline__ int pop_round(const ols_queues_t& q, const ols_replic
   const int wk = (first_acc < (1 << 20)) ? first_acc + align : 0;
   const int src = gbase + wk / PPL;
   float4 sel = tail[0];
-  if (PPL == 2 && (wk & 1)) sel = tail[PPL - 1];
+#pragma unroll
+  for (int i = 1; i < PPL; ++i)
+    if ((wk % PPL) == i) sel = tail[i];
   sel.x = __shfl_sync(kFull, sel.x, src);
   sel.y = __shfl_sync(kFull, sel.y, src);
   sel.z = __shfl_sync(kFull, sel.z, src);
@@ -972,8 +973,8 @@ inline cudaError_t launch_run_rng(const ols_queues_t& q, const ols_replicas_t& r
   } while (0)
   if (c.reject_mode == OLS_REJECT_ACCEPT_ALL) OLS_GO(RNGT_NONE, 1);
   else if (r.rng_mode == OLS_RNG_PCG64) OLS_GO(RNGT_PCG64, 1);
-  else if (r.rng_mode == OLS_RNG_FEED) { if (ppl == 2) OLS_GO(RNGT_FEED, 2); else OLS_GO(RNGT_FEED, 1); }
-  else { if (ppl == 2) OLS_GO(RNGT_PHILOX, 2); else OLS_GO(RNGT_PHILOX, 1); }
+  else if (r.rng_mode == OLS_RNG_FEED) { if (ppl == 4) OLS_GO(RNGT_FEED, 4); else if (ppl == 2) OLS_GO(RNGT_FEED, 2); else OLS_GO(RNGT_FEED, 1); }
+  else { if (ppl == 4) OLS_GO(RNGT_PHILOX, 4); else if (ppl == 2) OLS_GO(RNGT_PHILOX, 2); else OLS_GO(RNGT_PHILOX, 1); }
 #undef OLS_GO
   return cudaGetLastError();
 }

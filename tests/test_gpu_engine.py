@@ -199,7 +199,8 @@ def _golden_log(ob, g):
 
 @pytest.mark.parametrize("case", DRIVER_CASES)
 @pytest.mark.parametrize("tag", ["const", "sched"])
-@pytest.mark.parametrize("lanes,ppl,stage", [(1, 1, False), (4, 2, True), (32, 2, False), (2, 2, True), (8, 1, True)])
+@pytest.mark.parametrize("lanes,ppl,stage", [(1, 1, False), (4, 2, True), (32, 2, False), (2, 2, True), (8, 1, True), (1, 4, True),
+                                             (16, 4, False)])
 def test_fused_qlearn_matches_reference(ob, golden, case, tag, lanes, ppl, stage):
     import torch
     g = golden(case)
@@ -391,7 +392,7 @@ def test_learning_curve_and_totals(ob):
 
 # --------------------------------------------------------------------------------------- production streams vs the C oracle
 @pytest.mark.parametrize("agent", ["qlearn", "evalmc"])
-@pytest.mark.parametrize("lanes,ppl", [(4, 2), (32, 2), (8, 1), (1, 2)])
+@pytest.mark.parametrize("lanes,ppl", [(4, 2), (32, 2), (8, 1), (1, 2), (1, 4), (2, 4)])
 @pytest.mark.parametrize("ring", [False, True])
 def test_philox_replicas_match_c_oracle(ob, agent, lanes, ppl, ring):
     """Counter-based uniforms + ring offsets: thousands of replicas compared with oracle/ols_oracle.c, which
@@ -463,7 +464,7 @@ def test_accept_filter_never_changes_a_decision(ob):
                 z = int(g["z"][env.init[init_i]]); init_i += 1
     U = np.array(U + [0.5] * 64)
     log = device_log(ob, g, n_buckets=nS)
-    for lanes, ppl in [(1, 1), (4, 2), (32, 2)]:
+    for lanes, ppl in [(1, 1), (4, 2), (32, 2), (1, 4), (8, 4)]:
         sim = ob.BatchedPSRS(log, 1, rng="feed", u_feed=U, lanes=lanes, pops_per_lane=ppl)
         res = sim.run_evalmc(nS, 10**6 // 1000, pi=pi, gamma=1.0, trace_cap=N, max_steps=len(trace), ep_cap=2000)
         got = res.trace_row[0, :len(trace)].cpu().numpy()
