@@ -36,13 +36,13 @@ WORKLOADS = {
     "c5": dict(rows=100_000_000, states=1_000, actions=4, replicas=32_000, budget=100, delta=1e-3, lanes=32,
                desc="rejection-heavy: 100M-transition log, 1000 states, p_b=(1-d,d/3,d/3,d/3) d=1e-3, uniform target, 32k replicas/GPU"),
     # configs[1] shape: cartpole-box sized state space, 10k replicas on one GPU
-    "c2": dict(rows=1_000_000, states=162, actions=2, replicas=10_000, budget=2_000, delta=None, lanes=2,
+    "c2": dict(rows=1_000_000, states=162, actions=2, replicas=10_000, budget=2_000, delta=None, lanes=8,
                desc="cartpole-shaped: 1M-transition log, 162 states, 2 actions, eps-greedy Q-learning, 10k replicas"),
 }
 # DRAM bytes (read + write) per accepted transition of the fused run kernel, from the committed `ncu --set full`
-# captures (profiles/r01c_ncu_full_run_kernel_v5_*.txt): dram__bytes_read.sum + dram__bytes_write.sum divided by the
+# captures (profiles/r01f_ncu_full_run_kernel_final_*.txt): dram__bytes_read.sum + dram__bytes_write.sum divided by the
 # accepted transitions of the captured launch.  Used to report `roofline.traffic` per launch.
-NCU_DRAM_BYTES_PER_ACCEPTED = {"c4": (24.510792e9 + 2.574961e9) / 3.75e7, "c5": (78.320005e9 + 1.573043e9) / 3.2e6}
+NCU_DRAM_BYTES_PER_ACCEPTED = {"c4": (24.621403e9 + 2.587398e9) / 3.75e7, "c5": (78.641898e9 + 1.658046e9) / 3.2e6}
 EPS, ALPHA, GAMMA = 0.1, 0.1, 0.99
 EP_CAP = 512
 
@@ -370,7 +370,8 @@ def main():
         out = {
             "metric": "simulated accepted transitions/sec", "value": value, "unit": "transitions/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64 accept rule, f32 Q", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "dtype_note": "accept rule decided exactly as float64 (float32 pre-filter + exact fallback); Q table float32",
+            "data": "synthetic",
             "config": {"workload": args.workload + ": " + wl["desc"], "rows": N, "states": nS, "actions": nA,
                        "replicas_per_gpu": R, "accepted_per_replica_per_step": T, "lanes": wl["lanes"],
                        "queue_order": "log order" + ("" if args.no_ring else " + per-(replica,state) ring offset"),
@@ -381,8 +382,8 @@ def main():
                          "unit": "GB/s", "frac": gather_gbs / hbm_peak,
                          "traffic": (NCU_DRAM_BYTES_PER_ACCEPTED[args.workload] * float(sim.accepted.sum())
                                      if args.workload in NCU_DRAM_BYTES_PER_ACCEPTED else None),
-                         "traffic_note": "DRAM read+write bytes per launch = ncu bytes per accepted transition (profiles/r01c_*) x accepted per launch",
-                         "algorithmic_bytes_per_launch": my_pops / max(1, args.steps) * rec_bytes, "peak_source": peak_src,
+                         "traffic_note": "DRAM read+write bytes per launch = ncu bytes per accepted transition (profiles/r01f_*) x accepted per launch",
+                         "algorithmic_bytes_per_launch": my_pops * rec_bytes, "peak_source": peak_src,
                          "algorithmic_bytes_per_pop": rec_bytes, "agent_state_GBps": agent_gbs, "kernel_ms": float(run_ms)},
             "bucketing": {"rows": N, "ms": bucket_ms, "GBps": bucket_bytes / bucket_ms / 1e6, "frac": bucket_bytes / bucket_ms / 1e6 / hbm_peak,
                           "note": "ols_bucket + ols_init_queue kernels; bytes = z twice + order + log columns + packed record per row"},
