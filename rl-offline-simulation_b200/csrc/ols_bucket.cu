@@ -263,9 +263,11 @@ __global__ void __launch_bounds__(kBucketThreads) scatter_pack_kernel(ols_log_t 
 #pragma unroll
     for (int j = 0; j < U; ++j) peers[j] = __match_any_sync(kFull, key[j]);
     // ---- the turn: batches update the tile's slot counters strictly in log order
+    // acquire: spin on the token, then fence so the counters written by the previous holder are visible
     if (lane == 0)
       while (*turn != jb) {
       }
+    __threadfence_block();
     __syncwarp();
     uint32_t first[U];
 #pragma unroll
@@ -279,7 +281,8 @@ __global__ void __launch_bounds__(kBucketThreads) scatter_pack_kernel(ols_log_t 
       __syncwarp();
       first[j] = __shfl_sync(kFull, f, leader);
     }
-    __threadfence_block();
+    __syncwarp();
+    __threadfence_block();  // release: the leaders' counter updates precede the token hand-over
     if (lane == 0) *turn = jb + 1;
     // ---- scattered stores, overlapping with the other warps' loads and turns
 #pragma unroll
