@@ -155,6 +155,29 @@ def python_port_leg(cols, wl, seconds):
     return dict(value=steps / max(timed, 1e-9), seconds=timed, rows=n, runs=runs)
 
 
+def python_port_multiprocess(cols, wl, seconds, procs, workload):
+    """The reference has no multi-process mode for PSRS (MPI is only used by its PPO agent); the closest equivalent is P
+    independent single-replica runs in P separate processes, rates summed.  Plain subprocesses
+    with a hard timeout: no fork of the CUDA-initialised parent, no pool."""
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "log.npz")
+        np.savez(path, **{k: v[:1_000_000] for k, v in cols.items()})
+        cmd = [sys.executable, os.path.abspath(__file__), "--py-worker", path, "--py-seconds", str(seconds), "--workload", workload]
+        ps = [subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for _ in range(procs)]
+        vals = []
+        deadline = time.time() + seconds * 6 + 90
+        for pr in ps:
+            try:
+                out, _ = pr.communicate(timeout=max(1.0, deadline - time.time()))
+                vals.append(json.loads(out.strip().splitlines()[-1])["value"])
+            except Exception:
+                pr.kill()
+    if len(vals) != procs:
+        return None
+    return dict(value=float(sum(vals)), processes=procs, seconds=seconds)
+
+
 def run_reference(args, wl, rank, world):
     """--impl reference: the CPU implementation of the path on this box's host cores (the oracle's C
     restatement, all threads), same metric/config; rank 0 only."""
@@ -205,7 +228,13 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--py-worker", help=argparse.SUPPRESS)      # internal: one process of the multi-process python baseline
+    ap.add_argument("--py-seconds", type=float, default=4.0, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.py_worker:
+        cols = dict(np.load(args.py_worker))
+        print(json.dumps(python_port_leg(cols, dict(WORKLOADS[args.workload]), args.py_seconds)))
+        return
     wl = dict(WORKLOADS[args.workload])
     for k in ("rows", "states", "replicas", "budget", "lanes"):
         if getattr(args, k) is not None:
@@ -361,12 +390,14 @@ def main():
             threads = os.cpu_count() or 1
             leg = cpu_leg(cpu_cols, wl, args.cpu_seconds, threads)
             py = python_port_leg(cpu_cols, wl, 4.0) if qlearn else None
+            py_mp = python_port_multiprocess(cpu_cols, wl, 4.0, threads, args.workload) if qlearn else None
             cpu = {"value": leg["value"], "unit": "transitions/s", "cores": leg["threads"], "kind": "port",
                    "sample": (f"oracle/ols_oracle.c (C restatement of the reference's PSRS + learner loop), {leg['threads']} threads, same "
                               f"synthetic log truncated to {leg['rows']} rows, {leg['replicas']} replicas x {leg['budget']} accepted steps, "
                               f"{leg['seconds']:.1f} s"),
                    "pops_per_s": leg["pops_per_s"],
-                   "python_port_1core": None if py is None else {"value": py["value"], "rows": py["rows"], "seconds": py["seconds"]}}
+                   "python_port_1core": None if py is None else {"value": py["value"], "rows": py["rows"], "seconds": py["seconds"]},
+                   "python_port_multiprocess": py_mp}
         out = {
             "metric": "simulated accepted transitions/sec", "value": value, "unit": "transitions/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
