@@ -208,6 +208,36 @@ def run_reference(args, wl, rank, world):
     }))
 
 
+def gather_stress_leg(ob, torch, dev, hbm_peak, launches=5, warm=3):
+    """Second half of the BASELINE metric ("PSRS gather HBM GB/s vs peak"): the rejection-heavy configuration
+    (BASELINE.json configs[4], workload c5) is the streaming-gather regime.  Rank 0, one GPU, a few launches."""
+    wl = WORKLOADS["c5"]
+    N, nS, nA, R, T = wl["rows"], wl["states"], wl["actions"], wl["replicas"], wl["budget"]
+    cols = ob.synth_columns(N, nS, behaviour_table(nS, nA, wl["delta"]), seed=0, device=dev)
+    log = ob.BucketedLog(z=cols["z"], z_next=cols["z_next"], action=cols["action"], reward=cols["reward"],
+                         terminal=cols["terminal"], p_log=cols["p_log"], steps=cols["steps"], n_buckets=nS, z_offset=0, device=dev)
+    del cols
+    sim = ob.BatchedPSRS(log, R, rng="philox", seed=4321, ring=True, ring_seed=7, lanes=wl["lanes"])
+    pi = np.full((nS, nA), 1.0 / nA)
+    res, ms, pops = None, [], 0.0
+    for i in range(launches + warm):
+        sim.restart()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = sim.run_evalmc(nS, EP_CAP - 1, pi, GAMMA, max_steps=T, ep_cap=EP_CAP, outputs=res)
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= warm:               # the first launches are warm-up
+            ms.append(e0.elapsed_time(e1))
+            pops = float(sim.pops.sum())
+    t = sum(ms) / len(ms) / 1e3
+    gbs = pops * log.rec_bytes / t / 1e9
+    return {"workload": "c5: " + wl["desc"], "kernel": "run_kernel (fixed-policy evaluation, lanes=32 x 2 records)", "pops_per_s": pops / t,
+            "accepted_per_s": float(sim.accepted.sum()) / t, "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+            "kernel_ms": 1e3 * t, "launches": launches,
+            "traffic": NCU_DRAM_BYTES_PER_ACCEPTED["c5"] * float(sim.accepted.sum()), "algorithmic_bytes_per_launch": pops * log.rec_bytes}
+
+
 # ------------------------------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -227,6 +257,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-stress", action="store_true", help="skip the c5 streaming-gather measurement appended to a c4 run")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--py-worker", help=argparse.SUPPRESS)      # internal: one process of the multi-process python baseline
     ap.add_argument("--py-seconds", type=float, default=4.0, help=argparse.SUPPRESS)
@@ -333,9 +364,10 @@ def main():
     value = accepted / secs
     # roofline of the dominant kernel (fused run kernel) on this rank
     my_pops = float(sim.pops.sum())
+    last_accepted = float(sim.accepted.sum())
     run_s = float(run_ms) / 1e3
     gather_gbs = my_pops * rec_bytes / run_s / 1e9
-    agent_gbs = float(sim.accepted.sum()) * (4 * nA + 4 + 8 if qlearn else 8) / run_s / 1e9
+    agent_gbs = last_accepted * (4 * nA + 4 + 8 if qlearn else 8) / run_s / 1e9
 
     # ---- e2e: host-resident log -> H2D -> bucket -> run -> curve -> D2H, every step
     e2e = None
@@ -384,6 +416,11 @@ def main():
     else:
         cpu_cols = {k: v[:1_000_000].cpu().numpy() for k, v in cols.items()}
 
+    stress = None
+    if rank == 0 and args.workload == "c4" and not args.skip_stress:
+        sim = Q = res = None        # release the c4 state (25 GB) before building the c5 log
+        torch.cuda.empty_cache()
+        stress = gather_stress_leg(ob, torch, dev, hbm_peak)
     if rank == 0:
         cpu = None
         if not args.skip_cpu and world == 1:
@@ -411,13 +448,14 @@ def main():
             "pops_per_s": pops / secs,
             "roofline": {"bound": "hbm", "kernel": "run_kernel (fused PSRS step + agent update)", "achieved": gather_gbs, "peak": hbm_peak,
                          "unit": "GB/s", "frac": gather_gbs / hbm_peak,
-                         "traffic": (NCU_DRAM_BYTES_PER_ACCEPTED[args.workload] * float(sim.accepted.sum())
+                         "traffic": (NCU_DRAM_BYTES_PER_ACCEPTED[args.workload] * last_accepted
                                      if args.workload in NCU_DRAM_BYTES_PER_ACCEPTED else None),
                          "traffic_note": "DRAM read+write bytes per launch = ncu bytes per accepted transition (profiles/r01f_*) x accepted per launch",
                          "algorithmic_bytes_per_launch": my_pops * rec_bytes, "peak_source": peak_src,
                          "algorithmic_bytes_per_pop": rec_bytes, "agent_state_GBps": agent_gbs, "kernel_ms": float(run_ms)},
             "bucketing": {"rows": N, "ms": bucket_ms, "GBps": bucket_bytes / bucket_ms / 1e6, "frac": bucket_bytes / bucket_ms / 1e6 / hbm_peak,
                           "note": "ols_bucket + ols_init_queue kernels; bytes = z twice + order + log columns + packed record per row"},
+            "gather_stress": stress,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 4 * args.steps, "clocks": clocks,
         }
         print(json.dumps(out))
