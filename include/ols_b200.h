@@ -191,6 +191,10 @@ typedef struct ols_run {
   const double* epsilon;      /* [n_episodes] exploration per episode (psrs.py:129-132), QLEARN  */
   const void* pi;             /* [n_states][n_actions] fixed policy, FIXED_PI/EXPSARSA           */
   void* Q;                    /* [n_replicas][n_states][n_actions], QLEARN/EXPSARSA              */
+  void* state_aos;            /* optional, instead of r->cursor and Q: [n_replicas][n_states] entries of 32 bytes
+                                 { int32 cursor; int32 pad[3]; float q[4]; } — cursor and Q row of a state in ONE
+                                 DRAM sector.  Requires n_actions <= 4, float32 Q, z_offset == 0, n_states ==
+                                 n_buckets, no distinct s_next, Philox or fed uniforms (2 records per lane).      */
   double* Gs;                 /* [n_replicas][ep_cap] discounted return per episode              */
   int32_t* lengths;           /* [n_replicas][ep_cap] episode lengths                            */
   /* optional parity taps (NULL to disable)                                                    */

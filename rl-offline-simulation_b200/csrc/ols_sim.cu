@@ -59,7 +59,7 @@ int check_sim(const ols_queues_t* q, const ols_replicas_t* r, const char* who) {
   OLS_REQUIRE((uintptr_t)q->records % 32 == 0, OLS_ERR_INVALID, "%s: records must be 32-byte aligned", who);
   OLS_REQUIRE(r->n_replicas >= 0, OLS_ERR_INVALID, "%s: negative n_replicas", who);
   if (r->n_replicas == 0) return OLS_OK;
-  OLS_REQUIRE(r->cursor && r->init_cursor && r->cur_z && r->cur_s && r->status && r->draws && r->ties && r->pops &&
+  OLS_REQUIRE(r->init_cursor && r->cur_z && r->cur_s && r->status && r->draws && r->ties && r->pops &&
                   r->accepted && r->ep_index && r->ep_len_count && r->ep_t && r->ep_open && r->ep_G && r->ep_disc,
               OLS_ERR_INVALID, "%s: null replica buffer", who);
   OLS_REQUIRE(r->rng_mode == OLS_RNG_FEED || r->rng_mode == OLS_RNG_PCG64 || r->rng_mode == OLS_RNG_PHILOX, OLS_ERR_INVALID,
@@ -78,7 +78,7 @@ inline int align16(int64_t x) { return (int)((x + 15) / 16 * 16); }
 // if that still fits, its Q table.  Budget 96 KB per CTA keeps two CTAs resident per SM.
 StagePlan make_stage_plan(const ols_queues_t* q, const ols_run_t* c) {
   StagePlan p = {0, 0, 0};
-  if (!c->stage_smem) return p;
+  if (!c->stage_smem || c->state_aos) return p;  // the AoS entries are read straight from HBM, one sector per state
   const int groups = kThreads / c->lanes;
   const int64_t budget = 96 * 1024 - (int64_t)sizeof(Cold) * groups;
   const int64_t cb = align16((int64_t)q->n_buckets * 4);
@@ -101,7 +101,8 @@ extern "C" int ols_replicas_init(const ols_queues_t* q, const ols_replicas_t* r,
   int rc = check_sim(q, r, "ols_replicas_init");
   if (rc) return rc;
   if (r->n_replicas == 0) return OLS_OK;
-  OLS_CUDA_CHECK(cudaMemsetAsync(r->cursor, 0, sizeof(int32_t) * (size_t)r->n_replicas * q->n_buckets, (cudaStream_t)stream));
+  if (r->cursor)  // NULL when the block only ever runs with ols_run_t.state_aos (the caller zeroes that table)
+    OLS_CUDA_CHECK(cudaMemsetAsync(r->cursor, 0, sizeof(int32_t) * (size_t)r->n_replicas * q->n_buckets, (cudaStream_t)stream));
   int blocks = ols_div_up(r->n_replicas, kThreads);
   if (blocks > OLS_SM_COUNT * 8) blocks = OLS_SM_COUNT * 8;
   replicas_init_kernel<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(*q, *r, seeds);
@@ -130,6 +131,7 @@ static int step_impl(const ols_queues_t* q, const ols_replicas_t* r, const uint8
   OLS_REQUIRE(reject_mode == OLS_REJECT_DEFAULT || reject_mode == OLS_REJECT_ACCEPT_ALL, OLS_ERR_INVALID, "%s: bad reject_mode", who);
   OLS_REQUIRE(compute_mode == OLS_COMPUTE_F64 || compute_mode == OLS_COMPUTE_F32, OLS_ERR_INVALID, "%s: bad compute_mode", who);
   if (r->n_replicas == 0) return OLS_OK;
+  OLS_REQUIRE(r->cursor, OLS_ERR_INVALID, "%s: null cursor table", who);
   OLS_REQUIRE((p_new || act) && out && out->row && out->action && out->reward && out->terminal && out->s_next && out->z_from,
               OLS_ERR_INVALID, "%s: null input / output buffer", who);
   OLS_REQUIRE(p_stride == 0 || p_stride >= q->n_actions, OLS_ERR_INVALID, "%s: p_stride must be 0 or >= n_actions", who);
@@ -180,7 +182,18 @@ extern "C" int ols_run(const ols_queues_t* q, const ols_replicas_t* r, const ols
   OLS_REQUIRE(c->Gs && c->lengths, OLS_ERR_INVALID, "ols_run: null Gs / lengths");
   OLS_REQUIRE(q->records, OLS_ERR_INVALID, "ols_run: queues not bucketed");
   OLS_REQUIRE(q->n_init == 0 || (q->init_z && q->init_s), OLS_ERR_INVALID, "ols_run: null init arrays");
-  if (c->agent != OLS_AGENT_FIXED_PI) OLS_REQUIRE(c->Q && c->alpha, OLS_ERR_INVALID, "ols_run: learner needs Q and alpha");
+  OLS_REQUIRE(r->cursor || c->state_aos, OLS_ERR_INVALID, "ols_run: null cursor table");
+  if (c->state_aos) {
+    OLS_REQUIRE(c->agent != OLS_AGENT_FIXED_PI && !c->q_is_f64 && q->n_actions <= 4 && q->z_offset == 0 &&
+                    c->n_states == q->n_buckets && q->s_next == nullptr && r->rng_mode != OLS_RNG_PCG64 &&
+                    c->reject_mode == OLS_REJECT_DEFAULT && (c->pops_per_lane == 0 || c->pops_per_lane == 2),
+                OLS_ERR_UNSUPPORTED,
+                "ols_run: state_aos needs a float32 learner, <= 4 actions, z_offset 0, n_states == n_buckets, s == z, "
+                "Philox/fed uniforms, default reject rule, 2 records per lane");
+    OLS_REQUIRE((uintptr_t)c->state_aos % 32 == 0 && c->alpha, OLS_ERR_INVALID, "ols_run: state_aos must be 32-byte aligned");
+  } else if (c->agent != OLS_AGENT_FIXED_PI) {
+    OLS_REQUIRE(c->Q && c->alpha, OLS_ERR_INVALID, "ols_run: learner needs Q and alpha");
+  }
   if (c->agent == OLS_AGENT_QLEARN) OLS_REQUIRE(c->epsilon, OLS_ERR_INVALID, "ols_run: qlearn needs epsilon");
   if (c->agent != OLS_AGENT_QLEARN) OLS_REQUIRE(c->pi, OLS_ERR_INVALID, "ols_run: fixed-policy agents need pi");
   OLS_REQUIRE((!c->trace_row && !c->td_error) || c->trace_cap > 0, OLS_ERR_INVALID, "ols_run: trace taps need trace_cap > 0");

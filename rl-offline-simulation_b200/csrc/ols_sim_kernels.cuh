@@ -169,8 +169,29 @@ struct Bucket {
 };
 
 // psrs.py:44 — `self.queues[z]`: a z that was never logged as a from-state has no queue (KeyError).
+// A replica's learner state in array-of-structures form: one 32-byte entry per state,
+//     { int32 cursor; int32 pad[3]; float q[4]; }
+// so that the queue cursor and the Q row of a state share ONE DRAM sector.  A step reads the next state's entry with a
+// single 256-bit load (cursor for the pops + Q row for the bootstrap and the next policy) and dirties only the current
+// state's entry (cursor and Q[S, A]): two random sector accesses per transition instead of four.  Used by the fused
+// float32 learners when the agent's observation id is the state id (the reference's shipped configs).
+struct AosEntry {
+  int cursor;
+  float q[4];
+};
+__device__ __forceinline__ AosEntry load_aos(const unsigned char* aos, int state) {
+  float4 a, b;
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(aos + (size_t)state * 32));
+  AosEntry e;
+  e.cursor = __float_as_int(a.x);
+  e.q[0] = b.x; e.q[1] = b.y; e.q[2] = b.z; e.q[3] = b.w;
+  return e;
+}
+
 __device__ __forceinline__ bool load_bucket(const ols_queues_t& q, const ols_replicas_t& R, uint32_t h_rep, const int32_t* cur_tab,
-                                            int z, Bucket& B) {
+                                            int z, Bucket& B, bool have_cursor = false, int cursor_value = 0) {
   B.b = z + q.z_offset;
   B.lo = B.len = B.cur = 0;
   B.start = 0;
@@ -184,7 +205,7 @@ __device__ __forceinline__ bool load_bucket(const ols_queues_t& q, const ols_rep
     B.b = -1;
     return false;
   }
-  B.cur = cur_tab[B.b];
+  B.cur = have_cursor ? cursor_value : cur_tab[B.b];
   if (R.ring_mode) B.start = ols_ring_start(h_rep, (uint32_t)B.b, (uint32_t)B.len);
   return true;
 }
@@ -563,10 +584,11 @@ struct __align__(16) Cold {
 // The run loop.  Lane groups of a warp are DECOUPLED: every iteration each live group executes one pop round
 // against its own queue; a group whose round accepted a record runs the learner update and prepares its next
 // step in the same iteration (predicated), so no group waits for the longest reject chain in its warp.
-template <int NV, int AGENT, typename QT, int RNG, int PPL>
+template <int NV, int AGENT, typename QT, int RNG, int PPL, bool AOS = false>
 __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel(ols_queues_t q, ols_replicas_t R, ols_run_t cfg,
                                                                                   StagePlan plan, ols_philox_keys PK) {
   constexpr int NA = 4 * NV;
+  static_assert(!AOS || (NV == 1 && sizeof(QT) == 4 && AGENT != OLS_AGENT_FIXED_PI), "AoS state: float32 learners, <= 4 actions");
   extern __shared__ __align__(16) unsigned char s_mem[];
   const int nA = q.n_actions;
   const int nS = cfg.n_states;
@@ -619,16 +641,17 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
     C->ep_disc = R.ep_disc[r];
     live = (status == OLS_IDLE || status == OLS_RUNNING);  // terminated replicas stay terminated
   }
-  int32_t* cur_tab = R.cursor + rr * (int64_t)q.n_buckets;
-  QT* Qr = (AGENT == OLS_AGENT_FIXED_PI) ? nullptr : ((QT*)cfg.Q + rr * (int64_t)nS * nA);
+  int32_t* cur_tab = AOS ? nullptr : R.cursor + rr * (int64_t)q.n_buckets;
+  QT* Qr = (AGENT == OLS_AGENT_FIXED_PI || AOS) ? nullptr : ((QT*)cfg.Q + rr * (int64_t)nS * nA);
+  unsigned char* aos = AOS ? (unsigned char*)cfg.state_aos + (size_t)rr * (size_t)nS * 32 : nullptr;
   // ---- stage the replica's tables in shared memory (the group's lanes copy cooperatively)
-  if (plan.cursor_bytes) {
+  if (!AOS && plan.cursor_bytes) {
     int32_t* sc = (int32_t*)my_slot;
     if (exists)
       for (int i = sub; i < q.n_buckets; i += G) sc[i] = cur_tab[i];
     cur_tab = sc;
   }
-  if (AGENT != OLS_AGENT_FIXED_PI && plan.q_bytes) {
+  if (!AOS && AGENT != OLS_AGENT_FIXED_PI && plan.q_bytes) {
     QT* sq = (QT*)(my_slot + plan.cursor_bytes);
     if (exists)
       for (int i = sub; i < nS * nA; i += G) sq[i] = Qr[i];
@@ -681,7 +704,16 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
         }
       }
       if (new_status < 0 && (cur_s < 0 || cur_s >= nS)) new_status = OLS_NO_QUEUE;  // IndexError on Q[S] / pi[S]
-      if (new_status < 0 && !bucket_valid && !load_bucket(q, R, h_rep, cur_tab, cur_z, B))
+      if (AOS) {
+        if (new_status < 0 && !bucket_valid) {
+          // episode start: one 256-bit load brings the state's cursor and Q row
+          const AosEntry e = load_aos(aos, cur_s);
+          if (!load_bucket(q, R, h_rep, nullptr, cur_z, B, true, e.cursor)) new_status = OLS_NO_QUEUE;
+#pragma unroll
+          for (int j = 0; j < NA; ++j) row[j] = (j < nA) ? (QT)e.q[j & 3] : (QT)-INFINITY;
+          row_valid = true;
+        }
+      } else if (new_status < 0 && !bucket_valid && !load_bucket(q, R, h_rep, cur_tab, cur_z, B))
         new_status = OLS_NO_QUEUE;  // KeyError in the reference (psrs.py:44); no partial episode is appended
       // ---- the agent's action distribution for the current state
       bool used_tie = false;
@@ -691,8 +723,14 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
       if (AGENT == OLS_AGENT_QLEARN && new_status < 0) {
         // tabular.py:24-32 epsilon_greedy_policy on the single row Q[[S], :] (psrs.py:158)
         if (!row_valid) {
+          if (AOS) {
+            const AosEntry e = load_aos(aos, cur_s);
 #pragma unroll
-          for (int j = 0; j < NA; ++j) row[j] = (j < nA) ? Qr[(int64_t)cur_s * nA + j] : -INFINITY;  // padding never wins
+            for (int j = 0; j < NA; ++j) row[j] = (j < nA) ? (QT)e.q[j & 3] : (QT)-INFINITY;
+          } else {
+#pragma unroll
+            for (int j = 0; j < NA; ++j) row[j] = (j < nA) ? Qr[(int64_t)cur_s * nA + j] : -INFINITY;  // padding never wins
+          }
         }
         QT mx = row[0];
 #pragma unroll
@@ -814,7 +852,10 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
         S2 = q.s_next ? __ldg(q.s_next + row_idx) : Z2;
         // the next state is known: fetch its queue head now, ahead of the learner's own memory traffic.  (The cursor
         // of the queue just popped is still the old one in memory; a self-loop patches it from the register.)
-        const bool next_ok = done ? false : load_bucket(q, R, h_rep, cur_tab, Z2, B);
+        AosEntry e2;
+        e2.cursor = 0;
+        if (AOS && S2 >= 0 && S2 < nS) e2 = load_aos(aos, S2);  // the next state's cursor AND Q row: one sector
+        const bool next_ok = done ? false : load_bucket(q, R, h_rep, cur_tab, Z2, B, AOS, e2.cursor);
         if (next_ok && B.b == b_done) B.cur = cur_done;
         bucket_valid = next_ok;
         need_step = true;
@@ -825,7 +866,7 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
             const double alpha = __ldg(cfg.alpha + ep_index);
             QT nrow[NA];
 #pragma unroll
-            for (int j = 0; j < NA; ++j) nrow[j] = (j < nA) ? Qr[(int64_t)S2 * nA + j] : -INFINITY;
+            for (int j = 0; j < NA; ++j) nrow[j] = (j < nA) ? (AOS ? (QT)e2.q[j & 3] : Qr[(int64_t)S2 * nA + j]) : (QT)-INFINITY;
             QT boot;
             if (AGENT == OLS_AGENT_QLEARN) {
               boot = nrow[0];  // Q[S_].max()
@@ -849,7 +890,7 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
               for (int j = 1; j < NA; ++j)
                 if (j == A) qsa = row[j];
             } else {
-              qsa = Qr[(int64_t)S * nA + A];
+              qsa = AOS ? (QT)((const float*)(aos + (size_t)S * 32 + 16))[A] : Qr[(int64_t)S * nA + A];
             }
             td = QMath<QT>::td((QT)Rw, (QT)cfg.gamma, boot, qsa);
             qn = QMath<QT>::upd(qsa, (QT)alpha, td);
@@ -883,12 +924,16 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
       }
       __syncwarp(gm);
       // ---------------- phase 2: writes (every lane of the group writes the same values)
-      if (b_done >= 0) cur_tab[b_done] = cur_done;
+      if (b_done >= 0) {
+        if (AOS) *(int*)(aos + (size_t)b_done * 32) = cur_done;
+        else cur_tab[b_done] = cur_done;
+      }
       // an accepted transition is committed unless the learner found its next observation out of range
       const bool commit = accepted && !(AGENT != OLS_AGENT_FIXED_PI && !q_write);
       if (commit) {
         if (q_write) {
-          Qr[(int64_t)S * nA + A] = qn;
+          if (AOS) ((float*)(aos + (size_t)S * 32 + 16))[A] = (float)qn;
+          else Qr[(int64_t)S * nA + A] = qn;
           if (sub == 0 && cfg.td_error && acc_idx < cfg.trace_cap) cfg.td_error[rr * cfg.trace_cap + acc_idx] = (double)td;
         }
         if (cfg.trace_row && sub == 0 && acc_idx < cfg.trace_cap) cfg.trace_row[rr * cfg.trace_cap + acc_idx] = row_idx;
@@ -918,12 +963,12 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
   }
   // ---- write the staged tables back
   __syncwarp();
-  if (plan.cursor_bytes && exists) {
+  if (!AOS && plan.cursor_bytes && exists) {
     const int32_t* sc = (const int32_t*)my_slot;
     int32_t* g_cur = R.cursor + rr * (int64_t)q.n_buckets;
     for (int i = sub; i < q.n_buckets; i += G) g_cur[i] = sc[i];
   }
-  if (AGENT != OLS_AGENT_FIXED_PI && plan.q_bytes && exists) {
+  if (!AOS && AGENT != OLS_AGENT_FIXED_PI && plan.q_bytes && exists) {
     const QT* sq = (const QT*)(my_slot + plan.cursor_bytes);
     QT* g_Q = (QT*)cfg.Q + rr * (int64_t)nS * nA;
     for (int i = sub; i < nS * nA; i += G) g_Q[i] = sq[i];
@@ -959,9 +1004,28 @@ struct RunLaunch {
   cudaStream_t stream;
 };
 
+// the AoS-state variant exists for the production shape only: <= 4 actions, float32 Q, Philox or fed uniforms, 2 records/lane
+template <int NV, int AGENT, typename QT>
+inline cudaError_t launch_run_aos(const ols_queues_t& q, const ols_replicas_t& r, const ols_run_t& c, const RunLaunch& L) {
+  if constexpr (NV == 1 && sizeof(QT) == 4 && AGENT != OLS_AGENT_FIXED_PI) {
+    auto kf = run_kernel<NV, AGENT, QT, RNGT_FEED, 2, true>;
+    auto kp = run_kernel<NV, AGENT, QT, RNGT_PHILOX, 2, true>;
+    auto k = (r.rng_mode == OLS_RNG_FEED) ? kf : kp;
+    if (L.smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+      if (e != cudaSuccess) return e;
+    }
+    k<<<L.grid, kThreads, L.smem, L.stream>>>(q, r, c, L.plan, L.keys);
+    return cudaGetLastError();
+  } else {
+    return cudaErrorInvalidValue;
+  }
+}
+
 template <int NV, int AGENT, typename QT>
 inline cudaError_t launch_run_rng(const ols_queues_t& q, const ols_replicas_t& r, const ols_run_t& c, const RunLaunch& L,
                                   int ppl) {
+  if (c.state_aos != nullptr) return launch_run_aos<NV, AGENT, QT>(q, r, c, L);
 #define OLS_GO(RNG, PPL)                                                                                               \
   do {                                                                                                                 \
     auto k = run_kernel<NV, AGENT, QT, RNG, PPL>;                                                                      \

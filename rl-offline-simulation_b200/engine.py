@@ -254,7 +254,7 @@ class BatchedPSRS:
     def __init__(self, log: BucketedLog, n_replicas: int, rng: str = "philox", seed: Optional[int] = 0,
                  seeds=None, u_feed=None, tie_feed=None, reject: str = "default", ring: bool = False,
                  ring_seed: int = 0, replica_id0: int = 0, lanes: int = 4, pops_per_lane: int = 0,
-                 stage_smem: bool = True, prefetch: int = -1):
+                 stage_smem: bool = True, prefetch: int = -1, aos_state: bool = False):
         self.lib = abi.load()
         self.log = log
         dev = log.device
@@ -265,6 +265,8 @@ class BatchedPSRS:
         self.lanes = 1 if self.reject_mode == abi.REJECT_ACCEPT_ALL else int(lanes)
         self.pops_per_lane = int(pops_per_lane)     # 0 = auto (2 with Philox / fed uniforms)
         self.stage_smem = bool(stage_smem)          # stage cursor table (+Q) in shared memory when it fits
+        self.aos_state = bool(aos_state)            # cursor + Q row of a state in one 32-byte entry (fused float32 learners)
+        self.aos = None
         self.prefetch = int(prefetch)               # rounds ahead prefetched into L2 (<= 0: off; measured neutral on B200)
         self.rng_mode = {"feed": abi.RNG_FEED, "pcg64": abi.RNG_PCG64, "philox": abi.RNG_PHILOX}[rng]
         if seed is None:
@@ -273,7 +275,7 @@ class BatchedPSRS:
         with torch.cuda.device(dev):
             z32 = lambda: torch.zeros(max(R, 1), dtype=torch.int32, device=dev)
             z64 = lambda: torch.zeros(max(R, 1), dtype=torch.int64, device=dev)
-            self.cursor = torch.empty((max(R, 1), log.n_buckets), dtype=torch.int32, device=dev)
+            self.cursor = None if aos_state else torch.empty((max(R, 1), log.n_buckets), dtype=torch.int32, device=dev)
             self.init_cursor, self.cur_z, self.cur_s, self.status = z32(), z32(), z32(), z32()
             self.draws, self.ties, self.pops, self.accepted = z64(), z64(), z64(), z64()
             self.ep_index, self.ep_len_count, self.ep_t, self.ep_open = z32(), z32(), z32(), z32()
@@ -326,6 +328,8 @@ class BatchedPSRS:
         with torch.cuda.device(self.device):
             q, r = self.log.queues_struct(), self.replicas_struct()
             abi.check(self.lib.ols_replicas_init(C.byref(q), C.byref(r), _ptr(self._seeds), _stream_ptr()))
+            if self.aos is not None:
+                self.aos.zero_()            # cursors 0, Q 0
 
     def reset(self, mask=None):
         """psrs.py:32-37 for every replica (or those with ``mask``): returns ``(s, status)`` tensors."""
@@ -335,12 +339,17 @@ class BatchedPSRS:
             abi.check(self.lib.ols_reset(C.byref(q), C.byref(r), _ptr(m), _stream_ptr()))
         return self.cur_s, self.status
 
+    def _need_cursor_table(self, what):
+        if self.cursor is None:
+            raise RuntimeError(f"{what} needs the separate cursor table: build the block with aos_state=False")
+
     def step(self, p_new, mask=None, compute: Optional[str] = None):
         """psrs.py:39-57 for every RUNNING replica.  ``p_new``: [nA] shared or [R, nA] per replica.
 
         Returns a dict of device tensors: ``row`` (accepted log row, -1 if none), ``action``, ``reward``,
         ``terminal``, ``s_next``, ``z_from``, ``status``.
         """
+        self._need_cursor_table("step()")
         with torch.cuda.device(self.device):
             p = _as_tensor(p_new, self.device)
             if p.dtype not in (torch.float32, torch.float64):
@@ -368,6 +377,7 @@ class BatchedPSRS:
         rejection.  Needs a log bucketed with ``key_by_action=True``.  Returns the same dict as :meth:`step`."""
         if not self.log.key_by_action:
             raise ValueError("step_action needs BucketedLog(..., key_by_action=True)")
+        self._need_cursor_table("step_action()")
         with torch.cuda.device(self.device):
             a = _as_tensor(actions, self.device, torch.int32)
             if a.dim() == 0:
@@ -401,6 +411,19 @@ class BatchedPSRS:
         R, nA = self.R, self.log.n_actions
         with torch.cuda.device(dev):
             ep_cap = int(ep_cap or (n_episodes + 1))
+            use_aos = self.aos_state and agent != abi.AGENT_FIXED_PI
+            if self.aos_state and not use_aos:
+                self._need_cursor_table("a fixed-policy evaluation")
+            if use_aos:
+                if q_dtype != torch.float32 or nA > 4 or n_states != self.log.n_buckets or self.log.z_offset != 0 \
+                        or self.log.s_next is not None or self.rng_mode == abi.RNG_PCG64 or self.reject_mode != abi.REJECT_DEFAULT:
+                    raise ValueError("aos_state needs a float32 learner, <= 4 actions, n_states == n_buckets, z_offset 0, "
+                                     "s == z, Philox/fed uniforms and the default reject rule")
+                if self.aos is None:
+                    self.aos = torch.zeros((max(R, 1), n_states, 8), dtype=torch.float32, device=dev)
+                if Q is not None and Q.data_ptr() != self.aos.data_ptr() + 16:
+                    self.aos[:, :, 4:4 + nA] = Q.to(torch.float32)      # caller-supplied initial Q
+                Q = self.aos[:, :, 4:4 + nA]                            # strided view of the Q rows inside the entries
             if outputs is None:
                 Gs = torch.zeros((max(R, 1), ep_cap), dtype=torch.float64, device=dev)
                 lengths = torch.zeros((max(R, 1), ep_cap), dtype=torch.int32, device=dev)
@@ -409,7 +432,8 @@ class BatchedPSRS:
                 if agent != abi.AGENT_FIXED_PI and Q is None:
                     Q = torch.zeros((max(R, 1), n_states, nA), dtype=q_dtype, device=dev)
             else:
-                Gs, lengths, trace_row, td, Q = outputs.Gs, outputs.lengths, outputs.trace_row, outputs.td_error, outputs.Q
+                Gs, lengths, trace_row, td = outputs.Gs, outputs.lengths, outputs.trace_row, outputs.td_error
+                Q = Q if use_aos else outputs.Q
             pi_t = None
             pi_is_f64 = 0
             if pi is not None:
@@ -424,13 +448,14 @@ class BatchedPSRS:
             a_t = None if alpha is None else self._schedule(alpha, n_episodes)
             e_t = None if epsilon is None else self._schedule(epsilon, n_episodes)
             cfg = abi.Run(agent=agent, n_states=n_states, q_is_f64=int(Q is not None and Q.dtype == torch.float64),
+                          state_aos=_ptr(self.aos if use_aos else None),
                           pi_is_f64=pi_is_f64, reject_mode=self.reject_mode,
                           compute_mode=abi.COMPUTE_F32 if compute == "f32" else abi.COMPUTE_F64, lanes=self.lanes,
                           n_episodes=int(n_episodes), ep_cap=ep_cap, stage_smem=int(self.stage_smem),
                           pops_per_lane=0 if self.rng_mode == abi.RNG_PCG64 else self.pops_per_lane,
                           prefetch=max(self.prefetch, 0),
                           max_steps=int(max_steps),
-                          gamma=float(gamma), alpha=_ptr(a_t), epsilon=_ptr(e_t), pi=_ptr(pi_t), Q=_ptr(Q), Gs=_ptr(Gs),
+                          gamma=float(gamma), alpha=_ptr(a_t), epsilon=_ptr(e_t), pi=_ptr(pi_t), Q=_ptr(None if use_aos else Q), Gs=_ptr(Gs),
                           lengths=_ptr(lengths), trace_row=_ptr(trace_row), td_error=_ptr(td), trace_cap=int(trace_cap))
             q, r = self.log.queues_struct(), self.replicas_struct()
             abi.check(self.lib.ols_run(C.byref(q), C.byref(r), C.byref(cfg), _stream_ptr()))

@@ -528,3 +528,43 @@ def test_learning_curves_agree_with_oracle_under_independent_rngs_ks(ob):
     # and the reduced learning curve is the mean of those per-replica returns
     s, s2, c = sim.learning_curve(res, 6, all_reduce=False)
     np.testing.assert_allclose((s / c).cpu().numpy(), [Gs[ne > e, e].mean() for e in range(6)], rtol=1e-10)
+
+
+@pytest.mark.parametrize("agent", ["qlearn", "expsarsa"])
+@pytest.mark.parametrize("lanes,ring", [(2, True), (4, False), (32, True), (1, False)])
+def test_aos_state_layout_is_bitwise_equivalent(ob, agent, lanes, ring):
+    """Cursor + Q row in one 32-byte entry per (replica, state) is only a layout: accepted rows, Q tables, returns and
+    counters must be identical to the run with the separate cursor / Q arrays, also across resumed (budgeted) launches."""
+    import torch
+    g = make_log(61, 120000, 200, 4, ep_len=20)
+    nS, R = 200, 2500
+    log = device_log(ob, g, n_buckets=nS)
+    pi = np.random.default_rng(9).dirichlet(np.ones(4), size=nS)
+    outs = []
+    for aos in (False, True):
+        sim = ob.BatchedPSRS(log, R, rng="philox", seed=77, ring=ring, ring_seed=3, lanes=lanes, aos_state=aos)
+        res = None
+        for _ in range(3):          # three budgeted launches: the state must carry over in either layout
+            if agent == "qlearn":
+                res = sim.run_qlearn(nS, 40, gamma=0.9, alpha=0.1, epsilon=0.1, max_steps=150, trace_cap=500, outputs=res)
+            else:
+                res = sim.run_expsarsa(nS, 40, pi=pi, gamma=0.9, alpha=0.1, max_steps=150, trace_cap=500, outputs=res)
+        outs.append((res, sim.draws.clone(), sim.ties.clone()))
+    (a, da, ta), (b, db, tb) = outs
+    assert torch.equal(a.trace_row, b.trace_row) and torch.equal(a.accepted, b.accepted) and torch.equal(a.pops, b.pops)
+    assert torch.equal(da, db) and torch.equal(ta, tb) and torch.equal(a.status, b.status)
+    assert torch.equal(a.Q, b.Q.contiguous()) and torch.equal(a.Gs, b.Gs) and torch.equal(a.lengths, b.lengths)
+    assert int(a.accepted.sum()) > 0.9 * R * 450
+
+
+def test_aos_state_rejects_unsupported_shapes(ob):
+    import torch
+    g = make_log(62, 5000, 10, 4)
+    log = device_log(ob, g, n_buckets=10)
+    sim = ob.BatchedPSRS(log, 4, aos_state=True)
+    with pytest.raises(ValueError):
+        sim.run_qlearn(10, 5, gamma=0.9, q_dtype=torch.float64)
+    with pytest.raises(RuntimeError):
+        sim.step(np.full(4, 0.25))
+    with pytest.raises(RuntimeError):
+        sim.run_evalmc(10, 5, pi=np.full((10, 4), 0.25), gamma=0.9)
