@@ -253,6 +253,7 @@ def main():
     ap.add_argument("--lanes", type=int)
     ap.add_argument("--prefetch", type=int, default=-1)
     ap.add_argument("--ppl", type=int, default=0, help="records per lane per round (0 = auto)")
+    ap.add_argument("--slices", type=int, default=-1, help="time slices of the fused run: -1 auto, 0 off, k forced")
     ap.add_argument("--no-aos", action="store_true", help="separate cursor / Q arrays instead of one 32-byte entry per (replica, state)")
     ap.add_argument("--no-ring", action="store_true", help="all replicas consume the queues from slot 0 (L2-resident gather)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -312,7 +313,7 @@ def main():
     rec_bytes = log.rec_bytes
     bucket_bytes = N * (12 + 17 + 4 * nA + rec_bytes)   # z twice + order, log columns once, record written once
     sim = ob.BatchedPSRS(log, R, rng="philox", seed=1234, ring=not args.no_ring, ring_seed=99, replica_id0=rank * R, lanes=wl["lanes"], prefetch=args.prefetch, pops_per_lane=args.ppl,
-                         aos_state=(qlearn and nA <= 4 and not args.no_aos))
+                         aos_state=(qlearn and nA <= 4 and not args.no_aos), slices=args.slices)
     use_aos = qlearn and nA <= 4 and not args.no_aos
     Q = torch.zeros((R, nS, nA), dtype=torch.float32, device=dev) if (qlearn and not use_aos) else None
     res = None
@@ -445,6 +446,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": args.workload + ": " + wl["desc"], "rows": N, "states": nS, "actions": nA,
                        "replicas_per_gpu": R, "accepted_per_replica_per_step": T, "lanes": wl["lanes"],
+                       "time_slices": ("auto (16 per replica block when the blocks are not a whole number of waves)" if args.slices == -1 else args.slices),
                        "replica_state": ("one 32-byte entry {cursor, Q row} per (replica, state)" if use_aos else "separate cursor and Q arrays"),
                        "queue_order": "log order" + ("" if args.no_ring else " + per-(replica,state) ring offset"),
                        "l2": "working set (records %.1f GB + replica state %.1f GB) >> 126 MB L2; no flush" % (

@@ -184,6 +184,11 @@ typedef struct ols_run {
                                  Philox/fed uniforms, 1 with PCG64 replay)                       */
   int32_t prefetch;           /* rounds ahead whose records are prefetched into L2 (0 = off; useful for
                                  long reject chains, i.e. lanes >= 16)                           */
+  int32_t slices;             /* time slicing of a budgeted run (max_steps > 0): 0/1 off; k > 1 = the budget is
+                                 served in k slices per 256-thread replica block, handed to the SMs through a
+                                 ticket counter, so a replica count that is not a whole number of waves keeps
+                                 every SM busy; -1 = let the library decide.  Results do not depend on it.     */
+  int32_t _pad;
   int64_t max_steps;          /* > 0: every replica stops after this many accepted transitions in
                                  THIS call and stays resumable (not in the reference)            */
   double gamma;
@@ -195,6 +200,8 @@ typedef struct ols_run {
                                  { int32 cursor; int32 pad[3]; float q[4]; } — cursor and Q row of a state in ONE
                                  DRAM sector.  Requires n_actions <= 4, float32 Q, z_offset == 0, n_states ==
                                  n_buckets, no distinct s_next, Philox or fed uniforms (2 records per lane).      */
+  int32_t* sched;             /* device scratch of ols_run_sched_bytes() for slices != 0/1 (zeroed by ols_run);
+                                 NULL = never slice                                              */
   double* Gs;                 /* [n_replicas][ep_cap] discounted return per episode              */
   int32_t* lengths;           /* [n_replicas][ep_cap] episode lengths                            */
   /* optional parity taps (NULL to disable)                                                    */
@@ -274,6 +281,8 @@ int ols_reseed(const ols_replicas_t* r, const uint64_t* seeds, const uint8_t* ma
 /* psrs.py:119-271 `qlearn_psrs` / `expSARSA_psrs` / `evalMC_psrs`, one independent run per replica,
  * fused with the agent update and the per-episode return evaluator.                            */
 int ols_run(const ols_queues_t* q, const ols_replicas_t* r, const ols_run_t* run, void* stream);
+/* bytes of ols_run_t.sched for a run over n_replicas replicas with the given lane-group width   */
+size_t ols_run_sched_bytes(int64_t n_replicas, int32_t lanes);
 
 /* ---- evaluators --------------------------------------------------------------------------- */
 size_t ols_curve_scratch_bytes(int64_t n_replicas, int32_t n_episodes);

@@ -9,11 +9,11 @@
 // The sort is a STABLE counting sort in one scatter pass.  The rows are cut into T contiguous
 // tiles, one tile per CTA.  Pass 1 builds the tile's histogram in shared memory (all warps, atomics:
 // order is irrelevant for counting); a column scan over the [tile][bucket] table gives every tile its
-// first slot in every queue; pass 2 re-walks the tile: the CTA's warps take 64-row batches round-robin,
-// load their rows' columns concurrently, and then pass a TURN token in batch order through a short
-// critical section in which equal keys of the batch are ranked with __match_any_sync (lower lane =
-// earlier row) against the tile's running per-queue slot counters in shared memory.  Outside the token
-// the loads and the scattered stores of all warps overlap.  Each row's packed record (which carries the
+// first slot in every queue; pass 2 re-walks the tile in rounds of 8 batches (one per warp, consecutive rows):
+// every warp loads its batch's columns and ranks equal keys with __match_any_sync (lower lane = earlier row), then
+// the warps take their slots from the tile's running per-queue counters in shared memory one after the other, in
+// log order, separated by __syncthreads (8 cheap barriers per 1024 rows - no spinning, no fences), and finally all
+// warps scatter concurrently.  Each row's packed record (which carries the
 // row index, i.e. the queue order) goes straight to its final slot as full 32-byte sectors.  Algorithmic
 // traffic per row: z twice (8 B), the log columns once (~13 + 4*nA B), the record once (rec_bytes).
 #include <limits.h>
@@ -32,7 +32,10 @@ struct BucketPlan {
 };
 
 constexpr int kBucketThreads = 256;  // 8 warps per CTA
-constexpr int kBatchRows = 64;       // rows a warp holds per turn (2 x 32)
+#ifndef OLS_BATCH_ROWS
+#define OLS_BATCH_ROWS 128
+#endif
+constexpr int kBatchRows = OLS_BATCH_ROWS;  // rows a warp holds per round (U x 32)
 
 // One counter array of n_buckets entries per CTA; as many CTAs per SM as shared memory and the thread
 // limit allow, and a grid that is a multiple of the SM count.
@@ -228,22 +231,22 @@ __device__ __forceinline__ void load_row(const ols_log_t& log, int64_t i, RowDat
 template <int NV>
 __global__ void __launch_bounds__(kBucketThreads) scatter_pack_kernel(ols_log_t log, ols_queues_t q, int64_t tile_rows,
                                                                        const uint32_t* __restrict__ tile_hist) {
-  extern __shared__ uint32_t s_next_slot[];   // [n_buckets] next free slot of every queue for this tile, then the turn
+  extern __shared__ uint32_t s_next_slot[];   // [n_buckets] next free slot of every queue for this tile
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_warps = blockDim.x >> 5;
+  constexpr int kWarps = kBucketThreads / 32;
   const int nB = q.n_buckets;
-  volatile int* turn = (volatile int*)(s_next_slot + nB);
   const uint32_t* th = tile_hist + (size_t)blockIdx.x * nB;
   for (int b = threadIdx.x; b < nB; b += blockDim.x) s_next_slot[b] = (uint32_t)__ldg(q.offsets + b) + th[b];
-  if (threadIdx.x == 0) *turn = 0;
   __syncthreads();
   const int64_t lo = (int64_t)blockIdx.x * tile_rows;
   const int64_t hi = min(lo + tile_rows, log.n_rows);
-  const int n_batches = (int)((hi - lo + kBatchRows - 1) / kBatchRows);
   const uint32_t lt_mask = (1u << lane) - 1u;
   constexpr int U = kBatchRows / 32;
-  for (int jb = warp; jb < n_batches; jb += n_warps) {
-    const int64_t base = lo + (int64_t)jb * kBatchRows;
+  // The tile is consumed in rounds of kWarps batches; warp w holds the w-th batch of the round (kBatchRows consecutive
+  // rows), so log order = (round, warp, j, lane).  The loop count is uniform over the CTA: barriers inside.
+  const int n_rounds = (int)((hi - lo + (int64_t)kWarps * kBatchRows - 1) / ((int64_t)kWarps * kBatchRows));
+  for (int rd = 0; rd < n_rounds; ++rd) {
+    const int64_t base = lo + ((int64_t)rd * kWarps + warp) * kBatchRows;
     int key[U];
     RowData<NV> row[U];
 #pragma unroll
@@ -262,29 +265,26 @@ __global__ void __launch_bounds__(kBucketThreads) scatter_pack_kernel(ols_log_t 
     unsigned peers[U];
 #pragma unroll
     for (int j = 0; j < U; ++j) peers[j] = __match_any_sync(kFull, key[j]);
-    // ---- the turn: batches update the tile's slot counters strictly in log order
-    // acquire: spin on the token, then fence so the counters written by the previous holder are visible
-    if (lane == 0)
-      while (*turn != jb) {
-      }
-    __threadfence_block();
-    __syncwarp();
+    // ---- the warps take their slots strictly in log order: one barrier-separated turn per warp
     uint32_t first[U];
+#pragma unroll 1
+    for (int w = 0; w < kWarps; ++w) {
+      if (warp == w) {
 #pragma unroll
-    for (int j = 0; j < U; ++j) {
-      const int leader = __ffs(peers[j]) - 1;
-      uint32_t f = 0;
-      if (key[j] >= 0 && lane == leader) {
-        f = s_next_slot[key[j]];
-        s_next_slot[key[j]] = f + __popc(peers[j]);
+        for (int j = 0; j < U; ++j) {
+          const int leader = __ffs(peers[j]) - 1;
+          uint32_t f = 0;
+          if (key[j] >= 0 && lane == leader) {
+            f = s_next_slot[key[j]];
+            s_next_slot[key[j]] = f + __popc(peers[j]);
+          }
+          __syncwarp();  // the next j may hit the same counter from another lane
+          first[j] = __shfl_sync(kFull, f, leader);
+        }
       }
-      __syncwarp();
-      first[j] = __shfl_sync(kFull, f, leader);
+      __syncthreads();
     }
-    __syncwarp();
-    __threadfence_block();  // release: the leaders' counter updates precede the token hand-over
-    if (lane == 0) *turn = jb + 1;
-    // ---- scattered stores, overlapping with the other warps' loads and turns
+    // ---- scattered stores
 #pragma unroll
     for (int j = 0; j < U; ++j) {
       if (key[j] >= 0) {

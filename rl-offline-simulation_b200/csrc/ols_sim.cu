@@ -163,6 +163,11 @@ extern "C" int ols_step_action(const ols_queues_t* q, const ols_replicas_t* r, c
   return step_impl(q, r, mask, nullptr, 0, 0, OLS_REJECT_ACCEPT_ALL, OLS_COMPUTE_F64, 1, out, action, stream, "ols_step_action");
 }
 
+extern "C" size_t ols_run_sched_bytes(int64_t n_replicas, int32_t lanes) {
+  if (n_replicas < 0 || !valid_lanes(lanes)) return 0;
+  return sizeof(int32_t) * (size_t)((n_replicas * lanes + kThreads - 1) / kThreads + 1);
+}
+
 extern "C" int ols_run(const ols_queues_t* q, const ols_replicas_t* r, const ols_run_t* c, void* stream) {
   int rc = check_sim(q, r, "ols_run");
   if (rc) return rc;
@@ -198,8 +203,27 @@ extern "C" int ols_run(const ols_queues_t* q, const ols_replicas_t* r, const ols
   if (c->agent != OLS_AGENT_QLEARN) OLS_REQUIRE(c->pi, OLS_ERR_INVALID, "ols_run: fixed-policy agents need pi");
   OLS_REQUIRE((!c->trace_row && !c->td_error) || c->trace_cap > 0, OLS_ERR_INVALID, "ols_run: trace taps need trace_cap > 0");
   RunLaunch L;
-  L.grid = (int)((r->n_replicas * c->lanes + kThreads - 1) / kThreads);  // one lane group per replica, no grid-stride loop
+  const int n_blocks = (int)((r->n_replicas * c->lanes + kThreads - 1) / kThreads);  // one lane group per replica
   L.plan = make_stage_plan(q, c);
+  // ---- time slicing (see run_kernel): only a budgeted run has slices to hand out
+  OLS_REQUIRE(c->slices >= -1 && c->slices <= 4096, OLS_ERR_INVALID, "ols_run: slices must be -1 (auto), 0/1 (off) or 2..4096");
+  OLS_REQUIRE(c->slices <= 1 || (c->sched && c->max_steps > 0), OLS_ERR_INVALID,
+              "ols_run: time slicing needs max_steps > 0 and the sched scratch");
+  int slices = c->slices > 1 ? c->slices : 1;
+  if (c->slices == -1 && c->sched && c->max_steps > 0 && L.plan.slot_bytes == 0) {
+    // resident CTAs per wave under the kernels' launch bounds; slice when the last wave would run part-empty
+    const int resident = OLS_SM_COUNT * (q->n_actions <= 4 ? OLS_MINB : 2);
+    const int full = n_blocks / resident, rest = n_blocks % resident;
+    if (full >= 1 && rest != 0 && rest < resident * 9 / 10) {
+      int64_t k = c->max_steps / 512;  // at least 512 accepted transitions per slice
+      slices = (int)(k < 1 ? 1 : k > 16 ? 16 : k);
+    }
+  }
+  ols_run_t cfg = *c;
+  cfg.slices = slices;
+  c = &cfg;
+  if (slices > 1) OLS_CUDA_CHECK(cudaMemsetAsync(cfg.sched, 0, sizeof(int32_t) * (size_t)(n_blocks + 1), (cudaStream_t)stream));
+  L.grid = n_blocks * slices;
   L.smem = (sizeof(Cold) + (size_t)L.plan.slot_bytes) * (kThreads / c->lanes);
   L.keys = ols_philox_make_keys(r->seed);
   L.stream = (cudaStream_t)stream;

@@ -181,7 +181,7 @@ struct AosEntry {
 };
 __device__ __forceinline__ AosEntry load_aos(const unsigned char* aos, int state) {
   float4 a, b;
-  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+  asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
                : "l"(aos + (size_t)state * 32));
   AosEntry e;
@@ -597,8 +597,31 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
   const int sub = lane & (G - 1);
   const int gbase = lane - sub;
   const unsigned gmask = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
-  // one lane group per replica, one launch-time warp per 32/G replicas (the grid covers all of them)
-  const int64_t r = ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5) * (32 / G) + (lane / G);
+  // ---- the CTA's unit of work.  Plain launch: replica block blockIdx.x, budget cfg.max_steps.  Time-sliced launch
+  // (cfg.slices > 1): the grid holds slices x blocks CTAs; a CTA draws a ticket u and serves slice u / blocks of
+  // replica block u % blocks once that block's previous slice has been published.  Tickets rise with start time,
+  // so the awaited slice always belongs to a CTA that is already running: no deadlock, and the SMs stay full when
+  // the blocks do not divide evenly into waves (977 blocks over 592 resident CTAs = 1.65 waves cost 2 unsliced).
+  int blk = blockIdx.x, slice = 0;
+  long long budget = cfg.max_steps;
+  if (cfg.slices > 1) {
+    __shared__ int s_ticket;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(cfg.sched, 1);
+    __syncthreads();
+    const int n_blk = gridDim.x / cfg.slices;
+    blk = s_ticket % n_blk;
+    slice = s_ticket / n_blk;
+    const long long per = (cfg.max_steps + cfg.slices - 1) / cfg.slices;
+    budget = min(per, cfg.max_steps - (long long)slice * per);  // <= 0: nothing left, just pass the token on
+    if (threadIdx.x == 0) {
+      const volatile int* turn = (const volatile int*)cfg.sched + 1 + blk;
+      while (*turn != slice) __nanosleep(256);
+      __threadfence();  // acquire: the previous slice's replica state (written on another SM) is visible below
+    }
+    __syncthreads();
+  }
+  // one lane group per replica, one warp per 32/G replicas (the blocks cover all of them)
+  const int64_t r = ((blk * (int64_t)blockDim.x + threadIdx.x) >> 5) * (32 / G) + (lane / G);
   const bool exists = r < R.n_replicas;
   const int64_t rr = exists ? r : 0;
   const uint64_t rid = (uint64_t)(R.replica_id0 + rr);
@@ -618,28 +641,28 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
   C->n_acc = 0;
   C->eps_episode = -1;
   if (exists) {
-    const int status = R.status[r];
-    cur_z = R.cur_z[r];
-    cur_s = R.cur_s[r];
-    draws = R.draws[r];
+    const int status = __ldcg(R.status + r);
+    cur_z = __ldcg(R.cur_z + r);
+    cur_s = __ldcg(R.cur_s + r);
+    draws = __ldcg(R.draws + r);
     if (RNG == RNGT_PCG64) {
       const uint64_t* p = R.pcg_state + 4 * r;
-      pcg_s.hi = p[0];
-      pcg_s.lo = p[1];
-      pcg_inc.hi = p[2];
-      pcg_inc.lo = p[3];
+      pcg_s.hi = __ldcg(p);
+      pcg_s.lo = __ldcg(p + 1);
+      pcg_inc.hi = __ldcg(p + 2);
+      pcg_inc.lo = __ldcg(p + 3);
     }
     C->status = status;
-    C->init_cursor = R.init_cursor[r];
-    C->ties = R.ties[r];
-    C->accepted0 = R.accepted[r];
-    C->ep_index = R.ep_index[r];
-    C->ep_len_count = R.ep_len_count[r];
-    C->ep_t = R.ep_t[r];
-    C->ep_open = R.ep_open[r];
-    C->ep_G = R.ep_G[r];
-    C->ep_disc = R.ep_disc[r];
-    live = (status == OLS_IDLE || status == OLS_RUNNING);  // terminated replicas stay terminated
+    C->init_cursor = __ldcg(R.init_cursor + r);
+    C->ties = __ldcg(R.ties + r);
+    C->accepted0 = __ldcg(R.accepted + r);
+    C->ep_index = __ldcg(R.ep_index + r);
+    C->ep_len_count = __ldcg(R.ep_len_count + r);
+    C->ep_t = __ldcg(R.ep_t + r);
+    C->ep_open = __ldcg(R.ep_open + r);
+    C->ep_G = __ldcg(R.ep_G + r);
+    C->ep_disc = __ldcg(R.ep_disc + r);
+    live = (status == OLS_IDLE || status == OLS_RUNNING) && (cfg.slices <= 1 || budget > 0);  // terminated replicas stay terminated
   }
   int32_t* cur_tab = AOS ? nullptr : R.cursor + rr * (int64_t)q.n_buckets;
   QT* Qr = (AGENT == OLS_AGENT_FIXED_PI || AOS) ? nullptr : ((QT*)cfg.Q + rr * (int64_t)nS * nA);
@@ -943,7 +966,7 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
         C->ep_G = G_new;
         C->ep_disc = __dmul_rn(disc, cfg.gamma);
         C->ep_t = t_new;
-        if (cfg.max_steps > 0 && (int64_t)(n_acc_old + 1) >= cfg.max_steps) live = false;  // budget: stays resumable
+        if (budget > 0 && (long long)(n_acc_old + 1) >= budget) live = false;  // budget: stays resumable
       }
       if (close_ep) {
         if (sub == 0) {
@@ -980,7 +1003,7 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
     R.init_cursor[r] = C->init_cursor;
     R.draws[r] = draws;
     R.ties[r] = C->ties;
-    R.pops[r] += n_pop;
+    R.pops[r] = __ldcg(R.pops + r) + n_pop;
     R.accepted[r] = C->accepted0 + (unsigned long long)C->n_acc;
     if (RNG == RNGT_PCG64) {
       R.pcg_state[4 * r] = pcg_s.hi;
@@ -992,6 +1015,13 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
     R.ep_open[r] = C->ep_open;
     R.ep_G[r] = C->ep_G;
     R.ep_disc[r] = C->ep_disc;
+  }
+  if (cfg.slices > 1) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();  // release: every thread's state writes precede the token
+      *((volatile int*)cfg.sched + 1 + blk) = slice + 1;
+    }
   }
 }
 
@@ -1011,7 +1041,7 @@ inline cudaError_t launch_run_aos(const ols_queues_t& q, const ols_replicas_t& r
     auto kf = run_kernel<NV, AGENT, QT, RNGT_FEED, 2, true>;
     auto kp = run_kernel<NV, AGENT, QT, RNGT_PHILOX, 2, true>;
     auto k = (r.rng_mode == OLS_RNG_FEED) ? kf : kp;
-    if (L.smem > 48 * 1024) {
+    if (L.smem > 40 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
       if (e != cudaSuccess) return e;
     }
@@ -1029,7 +1059,7 @@ inline cudaError_t launch_run_rng(const ols_queues_t& q, const ols_replicas_t& r
 #define OLS_GO(RNG, PPL)                                                                                               \
   do {                                                                                                                 \
     auto k = run_kernel<NV, AGENT, QT, RNG, PPL>;                                                                      \
-    if (L.smem > 48 * 1024) {                                                                                          \
+    if (L.smem > 40 * 1024) {                                                                                          \
       cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);               \
       if (e != cudaSuccess) return e;                                                                                  \
     }                                                                                                                  \

@@ -254,7 +254,7 @@ class BatchedPSRS:
     def __init__(self, log: BucketedLog, n_replicas: int, rng: str = "philox", seed: Optional[int] = 0,
                  seeds=None, u_feed=None, tie_feed=None, reject: str = "default", ring: bool = False,
                  ring_seed: int = 0, replica_id0: int = 0, lanes: int = 4, pops_per_lane: int = 0,
-                 stage_smem: bool = True, prefetch: int = -1, aos_state: bool = False):
+                 stage_smem: bool = True, prefetch: int = -1, aos_state: bool = False, slices: int = -1):
         self.lib = abi.load()
         self.log = log
         dev = log.device
@@ -267,6 +267,8 @@ class BatchedPSRS:
         self.stage_smem = bool(stage_smem)          # stage cursor table (+Q) in shared memory when it fits
         self.aos_state = bool(aos_state)            # cursor + Q row of a state in one 32-byte entry (fused float32 learners)
         self.aos = None
+        self.slices = int(slices)                   # time slices of a budgeted fused run: -1 auto, 0/1 off, k > 1 forced
+        self._sched = None
         self.prefetch = int(prefetch)               # rounds ahead prefetched into L2 (<= 0: off; measured neutral on B200)
         self.rng_mode = {"feed": abi.RNG_FEED, "pcg64": abi.RNG_PCG64, "philox": abi.RNG_PHILOX}[rng]
         if seed is None:
@@ -447,7 +449,10 @@ class BatchedPSRS:
                 compute = "f32" if (pi_t is not None and not pi_is_f64 and self.log.p_source_f32) else "f64"
             a_t = None if alpha is None else self._schedule(alpha, n_episodes)
             e_t = None if epsilon is None else self._schedule(epsilon, n_episodes)
-            cfg = abi.Run(agent=agent, n_states=n_states, q_is_f64=int(Q is not None and Q.dtype == torch.float64),
+            if self._sched is None and self.slices not in (0, 1):
+                n_sched = int(self.lib.ols_run_sched_bytes(R, self.lanes)) // 4
+                self._sched = torch.zeros(max(n_sched, 1), dtype=torch.int32, device=dev)
+            cfg = abi.Run(agent=agent, n_states=n_states, slices=self.slices if max_steps > 0 else 0, sched=_ptr(self._sched), q_is_f64=int(Q is not None and Q.dtype == torch.float64),
                           state_aos=_ptr(self.aos if use_aos else None),
                           pi_is_f64=pi_is_f64, reject_mode=self.reject_mode,
                           compute_mode=abi.COMPUTE_F32 if compute == "f32" else abi.COMPUTE_F64, lanes=self.lanes,

@@ -568,3 +568,46 @@ def test_aos_state_rejects_unsupported_shapes(ob):
         sim.step(np.full(4, 0.25))
     with pytest.raises(RuntimeError):
         sim.run_evalmc(10, 5, pi=np.full((10, 4), 0.25), gamma=0.9)
+
+
+@pytest.mark.parametrize("agent,aos", [("qlearn", True), ("qlearn", False), ("expsarsa", True), ("evalmc", False)])
+@pytest.mark.parametrize("lanes,slices", [(2, 16), (4, 3), (32, 7)])
+def test_time_slices_are_invisible(ob, agent, aos, lanes, slices):
+    """A budgeted run served in time slices (ticket scheduler inside the kernel, state handed from CTA to CTA through
+    HBM) must produce exactly the run of one launch per replica block: rows, Q, returns, counters."""
+    import torch
+    g = make_log(63, 120000, 200, 4, ep_len=20)
+    nS, R = 200, 3000
+    log = device_log(ob, g, n_buckets=nS)
+    pi = np.random.default_rng(10).dirichlet(np.ones(4), size=nS)
+    outs = []
+    for k in (0, slices):
+        sim = ob.BatchedPSRS(log, R, rng="philox", seed=5, ring=True, ring_seed=1, lanes=lanes, aos_state=aos, slices=k)
+        res = None
+        for budget in (333, 100):      # 333 is not a multiple of the slice count; the second launch resumes
+            if agent == "qlearn":
+                res = sim.run_qlearn(nS, 60, gamma=0.9, alpha=0.1, epsilon=0.1, max_steps=budget, trace_cap=500, outputs=res)
+            elif agent == "expsarsa":
+                res = sim.run_expsarsa(nS, 60, pi=pi, gamma=0.9, alpha=0.1, max_steps=budget, trace_cap=500, outputs=res)
+            else:
+                res = sim.run_evalmc(nS, 60, pi=pi, gamma=0.9, max_steps=budget, trace_cap=500, outputs=res)
+        outs.append((res, sim.draws.clone(), sim.ties.clone(), sim.cur_z.clone(), sim.ep_t.clone()))
+    (a, da, ta, za, ea), (b, db, tb, zb, eb) = outs
+    assert torch.equal(a.trace_row, b.trace_row) and torch.equal(a.accepted, b.accepted) and torch.equal(a.pops, b.pops)
+    assert torch.equal(da, db) and torch.equal(ta, tb) and torch.equal(a.status, b.status) and torch.equal(za, zb)
+    assert torch.equal(ea, eb) and torch.equal(a.Gs, b.Gs) and torch.equal(a.lengths, b.lengths)
+    if agent != "evalmc":
+        assert torch.equal(a.Q.contiguous(), b.Q.contiguous())
+    assert int(a.accepted.sum()) > 0.9 * R * 433
+
+
+def test_time_slices_need_a_budget(ob):
+    g = make_log(64, 5000, 10, 4)
+    log = device_log(ob, g, n_buckets=10)
+    sim = ob.BatchedPSRS(log, 64, slices=4)
+    res = sim.run_qlearn(10, 5, gamma=0.9)            # no max_steps: runs unsliced
+    assert int(res.accepted.sum()) > 0
+    import ctypes as C
+    from offsim4rl_b200 import _abi as abi
+    assert abi.load().ols_run_sched_bytes(1000, 2) == 4 * (8 + 1)
+    assert abi.load().ols_run_sched_bytes(1000, 3) == 0
