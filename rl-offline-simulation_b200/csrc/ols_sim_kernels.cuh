@@ -578,8 +578,27 @@ struct __align__(16) Cold {
   int ep_index, ep_len_count, ep_t, ep_open;
   int init_cursor, status, n_acc, pn_ok;
   float ipn_base, ipn_top;  // 1 / (eps/nA) and 1 / (1 - eps + eps/nA) of the open episode (QLEARN)
-  int eps_episode, pad;     // the episode index these were computed for (-1 = none)
+  int eps_episode;          // the episode index these were computed for (-1 = none)
+  int budget;               // accepted transitions this launch (or time slice) may still add; 0 = unlimited
+  float qrow[4];            // AoS Q-learning: Q[S, :] of the current state (the bootstrap row of the previous step)
+  unsigned h_rep;           // ring hash of the replica
+  int pad[3];
 };
+
+// 128-bit accesses to a group's Cold block (the struct is volatile for the scalar fields)
+__device__ __forceinline__ float4 cold_ld4(const volatile float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"((unsigned)__cvta_generic_to_shared((const void*)p))
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void cold_st4(volatile float* p, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"((unsigned)__cvta_generic_to_shared((const void*)p)), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
 
 // The run loop.  Lane groups of a warp are DECOUPLED: every iteration each live group executes one pop round
 // against its own queue; a group whose round accepted a record runs the learner update and prepares its next
@@ -588,11 +607,19 @@ template <int NV, int AGENT, typename QT, int RNG, int PPL, bool AOS = false>
 __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel(ols_queues_t q, ols_replicas_t R, ols_run_t cfg,
                                                                                   StagePlan plan, ols_philox_keys PK) {
   constexpr int NA = 4 * NV;
+  // AoS Q-learning keeps the policy row Q[S, :] in the group's Cold block (shared memory) between the bootstrap read of
+  // one step and the action choice of the next, and re-forms the float32 policy from the episode's two cached
+  // reciprocals every round: neither is held in registers across the pop rounds (they were spilled to local memory).
+  constexpr bool QCARRY = AOS && AGENT == OLS_AGENT_QLEARN;
   static_assert(!AOS || (NV == 1 && sizeof(QT) == 4 && AGENT != OLS_AGENT_FIXED_PI), "AoS state: float32 learners, <= 4 actions");
   extern __shared__ __align__(16) unsigned char s_mem[];
   const int nA = q.n_actions;
   const int nS = cfg.n_states;
+#ifdef OLS_FIXED_G
+  const int G = AOS ? OLS_FIXED_G : cfg.lanes;
+#else
   const int G = cfg.lanes;
+#endif
   const int lane = threadIdx.x & 31;
   const int sub = lane & (G - 1);
   const int gbase = lane - sub;
@@ -602,17 +629,17 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
   // replica block u % blocks once that block's previous slice has been published.  Tickets rise with start time,
   // so the awaited slice always belongs to a CTA that is already running: no deadlock, and the SMs stay full when
   // the blocks do not divide evenly into waves (977 blocks over 592 resident CTAs = 1.65 waves cost 2 unsliced).
-  int blk = blockIdx.x, slice = 0;
-  long long budget = cfg.max_steps;
+  __shared__ int s_ticket;
+  int blk = blockIdx.x;
+  long long budget64 = cfg.max_steps;
   if (cfg.slices > 1) {
-    __shared__ int s_ticket;
     if (threadIdx.x == 0) s_ticket = atomicAdd(cfg.sched, 1);
     __syncthreads();
     const int n_blk = gridDim.x / cfg.slices;
     blk = s_ticket % n_blk;
-    slice = s_ticket / n_blk;
+    const int slice = s_ticket / n_blk;
     const long long per = (cfg.max_steps + cfg.slices - 1) / cfg.slices;
-    budget = min(per, cfg.max_steps - (long long)slice * per);  // <= 0: nothing left, just pass the token on
+    budget64 = min(per, cfg.max_steps - (long long)slice * per);  // <= 0: nothing left, just pass the token on
     if (threadIdx.x == 0) {
       const volatile int* turn = (const volatile int*)cfg.sched + 1 + blk;
       while (*turn != slice) __nanosleep(256);
@@ -621,6 +648,8 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
     __syncthreads();
   }
   // one lane group per replica, one warp per 32/G replicas (the blocks cover all of them)
+  const bool no_budget = cfg.slices > 1 && budget64 <= 0;
+  const int budget0 = (int)max(0ll, min(budget64, 0x7fffffffll));  // n_acc is an int: a launch adds < 2^31 transitions
   const int64_t r = ((blk * (int64_t)blockDim.x + threadIdx.x) >> 5) * (32 / G) + (lane / G);
   const bool exists = r < R.n_replicas;
   const int64_t rr = exists ? r : 0;
@@ -633,17 +662,19 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
   // hot registers
   int cur_z = 0, cur_s = 0;
   uint64_t draws = 0;
-  uint32_t n_pop = 0;
+  uint32_t n_pop = 0;  // only read back by the accept-all baselines; otherwise pops == uniforms drawn
   ols_u128 pcg_s = {0, 0}, pcg_inc = {0, 0};
   bool live = false;
   // every lane of the group writes the same values into the group's Cold block
   C->status = OLS_IDLE;
   C->n_acc = 0;
   C->eps_episode = -1;
+  C->budget = budget0;
+  C->h_rep = h_rep;
   if (exists) {
     const int status = __ldcg(R.status + r);
     cur_z = __ldcg(R.cur_z + r);
-    cur_s = __ldcg(R.cur_s + r);
+    cur_s = AOS ? cur_z : __ldcg(R.cur_s + r);  // AoS state: the observation id IS the queue key
     draws = __ldcg(R.draws + r);
     if (RNG == RNGT_PCG64) {
       const uint64_t* p = R.pcg_state + 4 * r;
@@ -662,7 +693,7 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
     C->ep_open = __ldcg(R.ep_open + r);
     C->ep_G = __ldcg(R.ep_G + r);
     C->ep_disc = __ldcg(R.ep_disc + r);
-    live = (status == OLS_IDLE || status == OLS_RUNNING) && (cfg.slices <= 1 || budget > 0);  // terminated replicas stay terminated
+    live = (status == OLS_IDLE || status == OLS_RUNNING) && !no_budget;  // terminated replicas stay terminated
   }
   int32_t* cur_tab = AOS ? nullptr : R.cursor + rr * (int64_t)q.n_buckets;
   QT* Qr = (AGENT == OLS_AGENT_FIXED_PI || AOS) ? nullptr : ((QT*)cfg.Q + rr * (int64_t)nS * nA);
@@ -718,7 +749,7 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
       if (!ep_open0) {
         if (ep_index0 >= cfg.n_episodes) {
           new_status = OLS_DONE;
-        } else if (!reset_one(q, R, h_rep, ic, cur_z, cur_s)) {
+        } else if (!reset_one(q, R, C->h_rep, ic, cur_z, cur_s)) {
           new_status = OLS_INIT_EMPTY;  // terminate without appending (psrs.py:153-155)
         } else {
           started = true;
@@ -726,17 +757,22 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
           bucket_valid = false;
         }
       }
+      if (AOS) cur_s = cur_z;
       if (new_status < 0 && (cur_s < 0 || cur_s >= nS)) new_status = OLS_NO_QUEUE;  // IndexError on Q[S] / pi[S]
+      QT prow[NA];         // Q[S, :] for the action choice
+      bool fresh = false;  // prow was read from memory in this block
+#pragma unroll
+      for (int j = 0; j < NA; ++j) prow[j] = QCARRY ? (QT)0 : row[j];
       if (AOS) {
         if (new_status < 0 && !bucket_valid) {
           // episode start: one 256-bit load brings the state's cursor and Q row
           const AosEntry e = load_aos(aos, cur_s);
-          if (!load_bucket(q, R, h_rep, nullptr, cur_z, B, true, e.cursor)) new_status = OLS_NO_QUEUE;
+          if (!load_bucket(q, R, C->h_rep, nullptr, cur_z, B, true, e.cursor)) new_status = OLS_NO_QUEUE;
 #pragma unroll
-          for (int j = 0; j < NA; ++j) row[j] = (j < nA) ? (QT)e.q[j & 3] : (QT)-INFINITY;
-          row_valid = true;
+          for (int j = 0; j < NA; ++j) prow[j] = (j < nA) ? (QT)e.q[j & 3] : (QT)-INFINITY;
+          fresh = true;
         }
-      } else if (new_status < 0 && !bucket_valid && !load_bucket(q, R, h_rep, cur_tab, cur_z, B))
+      } else if (new_status < 0 && !bucket_valid && !load_bucket(q, R, C->h_rep, cur_tab, cur_z, B))
         new_status = OLS_NO_QUEUE;  // KeyError in the reference (psrs.py:44); no partial episode is appended
       // ---- the agent's action distribution for the current state
       bool used_tie = false;
@@ -745,22 +781,29 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
       bool new_eps = false;
       if (AGENT == OLS_AGENT_QLEARN && new_status < 0) {
         // tabular.py:24-32 epsilon_greedy_policy on the single row Q[[S], :] (psrs.py:158)
-        if (!row_valid) {
+        if (!row_valid && !fresh) {
+          fresh = true;
           if (AOS) {
             const AosEntry e = load_aos(aos, cur_s);
 #pragma unroll
-            for (int j = 0; j < NA; ++j) row[j] = (j < nA) ? (QT)e.q[j & 3] : (QT)-INFINITY;
+            for (int j = 0; j < NA; ++j) prow[j] = (j < nA) ? (QT)e.q[j & 3] : (QT)-INFINITY;
           } else {
 #pragma unroll
-            for (int j = 0; j < NA; ++j) row[j] = (j < nA) ? Qr[(int64_t)cur_s * nA + j] : -INFINITY;  // padding never wins
+            for (int j = 0; j < NA; ++j) prow[j] = (j < nA) ? Qr[(int64_t)cur_s * nA + j] : -INFINITY;  // padding never wins
           }
+        } else if (QCARRY && !fresh) {
+          const float4 v = cold_ld4(C->qrow);
+          prow[0] = (QT)v.x;
+          prow[1 % NA] = (QT)v.y;
+          prow[2 % NA] = (QT)v.z;
+          prow[3 % NA] = (QT)v.w;
         }
-        QT mx = row[0];
+        QT mx = prow[0];
 #pragma unroll
-        for (int j = 1; j < NA; ++j) mx = (row[j] > mx) ? row[j] : mx;
+        for (int j = 1; j < NA; ++j) mx = (prow[j] > mx) ? prow[j] : mx;
         unsigned cand = 0;  // bit j set: action j attains the maximum
 #pragma unroll
-        for (int j = 0; j < NA; ++j) cand |= (row[j] == mx) ? (1u << j) : 0u;
+        for (int j = 0; j < NA; ++j) cand |= (prow[j] == mx) ? (1u << j) : 0u;
         const int ncand = __popc(cand);
         if (ncand > 1) {  // tabular.py:4-5 _random_argmax: a draw is consumed only on ties
           double v = 0.0;
@@ -797,9 +840,7 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
           it = C->ipn_top;
           pn_ok = C->pn_ok;
         }
-#pragma unroll
-        for (int j = 0; j < NA; ++j) P.ipn[j] = (j >= nA) ? __int_as_float(0x7f800000) : ((j == a_star) ? it : ib);
-        P.ok = pn_ok != 0;
+        // the float32 policy itself is re-formed from (ib, it, a*) before every pop round, see below
       } else if (new_status < 0) {
         const void* pi_tab = cfg.pi;
         const int is64 = cfg.pi_is_f64;
@@ -810,6 +851,13 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
       }
       __syncwarp(gm);
       // ---------------- phase 2: writes
+      if (QCARRY) {
+        if (fresh) cold_st4(C->qrow, make_float4((float)prow[0], (float)prow[1 % NA], (float)prow[2 % NA], (float)prow[3 % NA]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < NA; ++j) row[j] = prow[j];
+      }
+      if (fresh) row_valid = true;
       if (started) {
         C->init_cursor = ic;
         C->status = OLS_RUNNING;
@@ -832,7 +880,7 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
       __syncwarp(gm);
     }
     // exact float64 pi(.|S) for the cold path: re-derived from (eps, a*) or re-read from the table when needed
-    const int a_now = a_star, S_now = cur_s;
+    const int a_now = a_star, S_now = AOS ? cur_z : cur_s;
     const double* eps_tab = cfg.epsilon;
     const void* pi_tab = cfg.pi;
     const int pi_is_f64 = cfg.pi_is_f64;
@@ -847,6 +895,12 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
       const int64_t off = (int64_t)S_now * nA + j;
       return pi_is_f64 ? __ldg((const double*)pi_tab + off) : (double)__ldg((const float*)pi_tab + off);
     };
+    if (AGENT == OLS_AGENT_QLEARN) {
+      const float ib = C->ipn_base, it = C->ipn_top;
+#pragma unroll
+      for (int j = 0; j < NA; ++j) P.ipn[j] = (j >= nA) ? __int_as_float(0x7f800000) : ((j == a_star) ? it : ib);
+      P.ok = C->pn_ok != 0;
+    }
     // ---- env.step(p), one round of it: psrs.py:39-57
     float4 tail = make_float4(0.f, 0.f, 0.f, 0.f);
     const int res = pop_round<NV, RNG, PPL>(q, R, G, sub, gbase, gmask, live, rr, rid, P, pn_fn, PK, cfg.compute_mode, B, draws,
@@ -860,7 +914,8 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
       const int b_done = B.b, cur_done = B.cur;  // the queue just popped from and its new cursor
       int new_status = -1;
       bool accepted = (res == OLS_RUNNING), q_write = false, close_ep = false, append_G = false;
-      const int S = cur_s;
+      const int S = AOS ? cur_z : cur_s;
+      const int budget = C->budget;
       const uint32_t meta = __float_as_uint(tail.w);
       const int A = ols_meta_action(meta);
       const int Z2 = __float_as_int(tail.y);
@@ -869,16 +924,17 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
       const double Rw = (double)tail.x;
       int S2 = 0;
       QT qn = (QT)0, td = (QT)0;
+      float4 carry = make_float4(0.f, 0.f, 0.f, 0.f);  // QCARRY: the next step's policy row
       double G_new = G_old;
       int t_new = t_old;
       if (accepted) {
-        S2 = q.s_next ? __ldg(q.s_next + row_idx) : Z2;
+        S2 = (!AOS && q.s_next) ? __ldg(q.s_next + row_idx) : Z2;
         // the next state is known: fetch its queue head now, ahead of the learner's own memory traffic.  (The cursor
         // of the queue just popped is still the old one in memory; a self-loop patches it from the register.)
         AosEntry e2;
         e2.cursor = 0;
         if (AOS && S2 >= 0 && S2 < nS) e2 = load_aos(aos, S2);  // the next state's cursor AND Q row: one sector
-        const bool next_ok = done ? false : load_bucket(q, R, h_rep, cur_tab, Z2, B, AOS, e2.cursor);
+        const bool next_ok = done ? false : load_bucket(q, R, C->h_rep, cur_tab, Z2, B, AOS, e2.cursor);
         if (next_ok && B.b == b_done) B.cur = cur_done;
         bucket_valid = next_ok;
         need_step = true;
@@ -907,7 +963,9 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
               boot = (QT)acc;
             }
             QT qsa;
-            if (AGENT == OLS_AGENT_QLEARN) {
+            if (QCARRY) {
+              qsa = (QT)C->qrow[A & 3];
+            } else if (AGENT == OLS_AGENT_QLEARN) {
               qsa = row[0];
 #pragma unroll
               for (int j = 1; j < NA; ++j)
@@ -920,8 +978,14 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
             q_write = true;
             if (AGENT == OLS_AGENT_QLEARN) {
               // the bootstrap row becomes the next step's policy row (patched if S' == S)
+              if (QCARRY) {
+                const bool self = (S2 == S);
+                carry = make_float4((float)((self && A == 0) ? qn : nrow[0]), (float)((self && A == 1) ? qn : nrow[1 % NA]),
+                                    (float)((self && A == 2) ? qn : nrow[2 % NA]), (float)((self && A == 3) ? qn : nrow[3 % NA]));
+              } else {
 #pragma unroll
-              for (int j = 0; j < NA; ++j) row[j] = (S2 == S && j == A) ? qn : nrow[j];
+                for (int j = 0; j < NA; ++j) row[j] = (S2 == S && j == A) ? qn : nrow[j];
+              }
               row_valid = true;
             }
           }
@@ -957,6 +1021,7 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
         if (q_write) {
           if (AOS) ((float*)(aos + (size_t)S * 32 + 16))[A] = (float)qn;
           else Qr[(int64_t)S * nA + A] = qn;
+          if (QCARRY) cold_st4(C->qrow, carry);
           if (sub == 0 && cfg.td_error && acc_idx < cfg.trace_cap) cfg.td_error[rr * cfg.trace_cap + acc_idx] = (double)td;
         }
         if (cfg.trace_row && sub == 0 && acc_idx < cfg.trace_cap) cfg.trace_row[rr * cfg.trace_cap + acc_idx] = row_idx;
@@ -966,7 +1031,7 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
         C->ep_G = G_new;
         C->ep_disc = __dmul_rn(disc, cfg.gamma);
         C->ep_t = t_new;
-        if (budget > 0 && (long long)(n_acc_old + 1) >= budget) live = false;  // budget: stays resumable
+        if (budget > 0 && n_acc_old + 1 >= budget) live = false;  // budget: stays resumable
       }
       if (close_ep) {
         if (sub == 0) {
@@ -999,11 +1064,12 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
   if (exists && sub == 0) {
     R.status[r] = C->status;
     R.cur_z[r] = cur_z;
-    R.cur_s[r] = cur_s;
+    R.cur_s[r] = AOS ? cur_z : cur_s;
     R.init_cursor[r] = C->init_cursor;
+    const uint64_t draws0 = __ldcg(R.draws + r);
     R.draws[r] = draws;
     R.ties[r] = C->ties;
-    R.pops[r] = __ldcg(R.pops + r) + n_pop;
+    R.pops[r] = __ldcg(R.pops + r) + ((RNG == RNGT_NONE) ? (unsigned long long)n_pop : (unsigned long long)(draws - draws0));
     R.accepted[r] = C->accepted0 + (unsigned long long)C->n_acc;
     if (RNG == RNGT_PCG64) {
       R.pcg_state[4 * r] = pcg_s.hi;
@@ -1020,7 +1086,8 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence();  // release: every thread's state writes precede the token
-      *((volatile int*)cfg.sched + 1 + blk) = slice + 1;
+      const int n_blk = gridDim.x / cfg.slices;
+      *((volatile int*)cfg.sched + 1 + s_ticket % n_blk) = s_ticket / n_blk + 1;
     }
   }
 }
