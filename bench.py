@@ -42,7 +42,7 @@ WORKLOADS = {
 # DRAM bytes (read + write) per accepted transition of the fused run kernel, from the committed `ncu --set full`
 # captures (profiles/r01f_ncu_full_run_kernel_final_*.txt): dram__bytes_read.sum + dram__bytes_write.sum divided by the
 # accepted transitions of the captured launch.  Used to report `roofline.traffic` per launch.
-NCU_DRAM_BYTES_PER_ACCEPTED = {"c4": (24.621403e9 + 2.587398e9) / 3.75e7, "c5": (78.641898e9 + 1.658046e9) / 3.2e6}
+NCU_DRAM_BYTES_PER_ACCEPTED = {"c4": (19.097991e9 + 1.288564e9) / 3.75e7, "c5": (78.641898e9 + 1.658046e9) / 3.2e6}
 EPS, ALPHA, GAMMA = 0.1, 0.1, 0.99
 EP_CAP = 512
 
@@ -64,8 +64,14 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
+    """One `nvidia-smi -lms` process for the whole run.  It is started BEFORE the warm-up (its start-up attaches to the
+    driver and can stall launches for tens of ms) and only the samples that arrive between begin() and stop() count."""
+
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+        self.rows, self.proc, self.idx, self.t_begin = [], None, gpu_index, 0.0
+
+    def begin(self):
+        self.t_begin = time.monotonic()
 
     def start(self):
         try:
@@ -77,13 +83,15 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
         self.proc.terminate()
+        rows = [r for t, r in self.rows if t >= self.t_begin]
+        self.rows = rows if rows else [r for t, r in self.rows[-2:]]
         sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -322,6 +330,8 @@ def main():
 
     def one_step(timed):
         nonlocal res
+        ea = torch.cuda.Event(enable_timing=True); ez = torch.cuda.Event(enable_timing=True)
+        ea.record()
         sim.restart()
         if Q is not None:
             Q.zero_()
@@ -333,8 +343,11 @@ def main():
             res = sim.run_evalmc(nS, EP_CAP - 1, uniform_pi, GAMMA, max_steps=T, ep_cap=EP_CAP, outputs=res)
         e1.record()
         curve = sim.learning_curve(res, EP_CAP - 1)
+        ez.record()
         if timed:
             k_ev["run"].append((e0, e1))
+            k_ev.setdefault("restart", []).append((ea, e0))
+            k_ev.setdefault("reduce", []).append((e1, ez))
         return curve
 
     def barrier():
@@ -342,12 +355,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        one_step(False)
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        one_step(False)
+    barrier()
+    sampler.begin()
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     acc_total = torch.zeros(2, dtype=torch.float64, device=dev)
     t0.record()
@@ -456,11 +470,12 @@ def main():
                          "unit": "GB/s", "frac": gather_gbs / hbm_peak,
                          "traffic": (NCU_DRAM_BYTES_PER_ACCEPTED[args.workload] * last_accepted
                                      if args.workload in NCU_DRAM_BYTES_PER_ACCEPTED else None),
-                         "traffic_note": "DRAM read+write bytes per launch = ncu bytes per accepted transition (profiles/r01f_*) x accepted per launch",
+                         "traffic_note": "DRAM read+write bytes per launch = ncu bytes per accepted transition (profiles/r01i_* for c4, r01f_* for c5) x accepted per launch",
                          "algorithmic_bytes_per_launch": my_pops * rec_bytes, "peak_source": peak_src,
                          "algorithmic_bytes_per_pop": rec_bytes, "agent_state_GBps": agent_gbs, "kernel_ms": float(run_ms)},
             "bucketing": {"rows": N, "ms": bucket_ms, "GBps": bucket_bytes / bucket_ms / 1e6, "frac": bucket_bytes / bucket_ms / 1e6 / hbm_peak,
                           "note": "ols_bucket + ols_init_queue kernels; bytes = z twice + order + log columns + packed record per row"},
+            "step_breakdown_ms": {k: sum(a.elapsed_time(b) for a, b in v) / max(1, len(v)) for k, v in k_ev.items()},
             "gather_stress": stress,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 4 * args.steps, "clocks": clocks,
         }

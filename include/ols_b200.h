@@ -188,7 +188,8 @@ typedef struct ols_run {
                                  served in k slices per 256-thread replica block, handed to the SMs through a
                                  ticket counter, so a replica count that is not a whole number of waves keeps
                                  every SM busy; -1 = let the library decide.  Results do not depend on it.     */
-  int32_t _pad;
+  int32_t state_epoch;        /* state_aos: only entries whose epoch word equals this value are live, all others
+                                 read as cursor 0 / Q 0 — a restart bumps the epoch instead of clearing the table */
   int64_t max_steps;          /* > 0: every replica stops after this many accepted transitions in
                                  THIS call and stays resumable (not in the reference)            */
   double gamma;
@@ -197,7 +198,7 @@ typedef struct ols_run {
   const void* pi;             /* [n_states][n_actions] fixed policy, FIXED_PI/EXPSARSA           */
   void* Q;                    /* [n_replicas][n_states][n_actions], QLEARN/EXPSARSA              */
   void* state_aos;            /* optional, instead of r->cursor and Q: [n_replicas][n_states] entries of 32 bytes
-                                 { int32 cursor; int32 pad[3]; float q[4]; } — cursor and Q row of a state in ONE
+                                 { int32 cursor; int32 epoch; int32 pad[2]; float q[4]; } — cursor and Q row of a state in ONE
                                  DRAM sector.  Requires n_actions <= 4, float32 Q, z_offset == 0, n_states ==
                                  n_buckets, no distinct s_next, Philox or fed uniforms (2 records per lane).      */
   int32_t* sched;             /* device scratch of ols_run_sched_bytes() for slices != 0/1 (zeroed by ols_run);

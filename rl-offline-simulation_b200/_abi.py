@@ -57,7 +57,7 @@ class StepOut(C.Structure):
 class Run(C.Structure):
     _fields_ = [("agent", i32), ("n_states", i32), ("q_is_f64", i32), ("pi_is_f64", i32), ("reject_mode", i32),
                 ("compute_mode", i32), ("lanes", i32), ("n_episodes", i32), ("ep_cap", i32), ("stage_smem", i32),
-                ("pops_per_lane", i32), ("prefetch", i32), ("slices", i32), ("_pad", i32), ("max_steps", i64), ("gamma", f64), ("alpha", p), ("epsilon", p), ("pi", p), ("Q", p), ("state_aos", p), ("sched", p), ("Gs", p),
+                ("pops_per_lane", i32), ("prefetch", i32), ("slices", i32), ("state_epoch", i32), ("max_steps", i64), ("gamma", f64), ("alpha", p), ("epsilon", p), ("pi", p), ("Q", p), ("state_aos", p), ("sched", p), ("Gs", p),
                 ("lengths", p), ("trace_row", p), ("td_error", p), ("trace_cap", i64)]
 
 

@@ -101,6 +101,9 @@ template <int NA>
 struct Policy {
   float ipn[NA];
   bool ok;
+  // pop_round takes a policy SOURCE and materialises the reciprocals right before the accept rule, after the round's
+  // loads and uniforms have been issued; a plain Policy is its own source
+  __device__ __forceinline__ const Policy& get() const { return *this; }
 };
 
 __device__ __forceinline__ float rcp_approx(float x) {
@@ -179,15 +182,24 @@ struct AosEntry {
   int cursor;
   float q[4];
 };
-__device__ __forceinline__ AosEntry load_aos(const unsigned char* aos, int state) {
+// An entry is live only if its epoch word equals the run's epoch: a restart bumps the epoch instead of clearing the
+// table (40 GB per GPU at the production shape), stale entries read as cursor 0 / Q 0, and every write stores the
+// whole entry (one fully covered sector).
+__device__ __forceinline__ AosEntry load_aos(const unsigned char* aos, int state, int epoch) {
   float4 a, b;
   asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
                : "l"(aos + (size_t)state * 32));
   AosEntry e;
-  e.cursor = __float_as_int(a.x);
-  e.q[0] = b.x; e.q[1] = b.y; e.q[2] = b.z; e.q[3] = b.w;
+  const bool fresh = (__float_as_int(a.y) == epoch);
+  e.cursor = fresh ? __float_as_int(a.x) : 0;
+  e.q[0] = fresh ? b.x : 0.f; e.q[1] = fresh ? b.y : 0.f; e.q[2] = fresh ? b.z : 0.f; e.q[3] = fresh ? b.w : 0.f;
   return e;
+}
+__device__ __forceinline__ void store_aos(unsigned char* aos, int state, int cursor, int epoch, float4 qrow) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(aos + (size_t)state * 32), "f"(__int_as_float(cursor)),
+               "f"(__int_as_float(epoch)), "f"(0.f), "f"(0.f), "f"(qrow.x), "f"(qrow.y), "f"(qrow.z), "f"(qrow.w)
+               : "memory");
 }
 
 __device__ __forceinline__ bool load_bucket(const ols_queues_t& q, const ols_replicas_t& R, uint32_t h_rep, const int32_t* cur_tab,
@@ -230,9 +242,9 @@ constexpr int kPopContinue = -2;  // every record examined was rejected; the que
 // group: OLS_RUNNING = a record was accepted (its tail is returned; tail.z is the log row), kPopContinue,
 // OLS_QUEUE_EMPTY (psrs.py:44-45, detected when a round starts on a drained queue), OLS_FEED_EMPTY.
 // B.cur, draws, n_pop (and the PCG64 state) advance by the records consumed.
-template <int NV, int RNG, int PPL, typename PnFn>
+template <int NV, int RNG, int PPL, typename PolT, typename PnFn>
 __device__ __forceinline__ int pop_round(const ols_queues_t& q, const ols_replicas_t& R, int G, int sub, int gbase,
-                                         unsigned gmask, bool active, int64_t r, uint64_t rid, const Policy<4 * NV>& P,
+                                         unsigned gmask, bool active, int64_t r, uint64_t rid, const PolT& pol,
                                          PnFn pn_fn, const ols_philox_keys& PK, int compute_mode, Bucket& B, uint64_t& draws,
                                          uint32_t& n_pop, ols_u128& pcg_s, const ols_u128& pcg_inc, float4& win_tail,
                                          int prefetch = 0) {
@@ -346,6 +358,7 @@ __device__ __forceinline__ int pop_round(const ols_queues_t& q, const ols_replic
     }
   }
   // ---- accept rule per pop
+  const Policy<NA> P = pol.get();
   bool acc[PPL];
 #pragma unroll
   for (int i = 0; i < PPL; ++i) {
@@ -600,10 +613,26 @@ __device__ __forceinline__ void cold_st4(volatile float* p, float4 v) {
                : "memory");
 }
 
+// epsilon-greedy policy source (tabular.py:24-32): two distinct probabilities per episode, their float reciprocals
+// cached in the group's Cold block; which action gets the larger one is the only per-step state.
+template <int NA>
+struct EpsGreedySource {
+  const volatile Cold* C;
+  int a_star, nA;
+  __device__ __forceinline__ Policy<NA> get() const {
+    Policy<NA> P;
+    const float ib = C->ipn_base, it = C->ipn_top;
+#pragma unroll
+    for (int j = 0; j < NA; ++j) P.ipn[j] = (j >= nA) ? __int_as_float(0x7f800000) : ((j == a_star) ? it : ib);
+    P.ok = C->pn_ok != 0;
+    return P;
+  }
+};
+
 // The run loop.  Lane groups of a warp are DECOUPLED: every iteration each live group executes one pop round
 // against its own queue; a group whose round accepted a record runs the learner update and prepares its next
 // step in the same iteration (predicated), so no group waits for the longest reject chain in its warp.
-template <int NV, int AGENT, typename QT, int RNG, int PPL, bool AOS = false>
+template <int NV, int AGENT, typename QT, int RNG, int PPL, bool AOS = false, int GT = 0>
 __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel(ols_queues_t q, ols_replicas_t R, ols_run_t cfg,
                                                                                   StagePlan plan, ols_philox_keys PK) {
   constexpr int NA = 4 * NV;
@@ -615,11 +644,7 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
   extern __shared__ __align__(16) unsigned char s_mem[];
   const int nA = q.n_actions;
   const int nS = cfg.n_states;
-#ifdef OLS_FIXED_G
-  const int G = AOS ? OLS_FIXED_G : cfg.lanes;
-#else
-  const int G = cfg.lanes;
-#endif
+  const int G = GT ? GT : cfg.lanes;  // GT: lane-group width known at compile time (the production widths 2 and 4)
   const int lane = threadIdx.x & 31;
   const int sub = lane & (G - 1);
   const int gbase = lane - sub;
@@ -766,7 +791,7 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
       if (AOS) {
         if (new_status < 0 && !bucket_valid) {
           // episode start: one 256-bit load brings the state's cursor and Q row
-          const AosEntry e = load_aos(aos, cur_s);
+          const AosEntry e = load_aos(aos, cur_s, cfg.state_epoch);
           if (!load_bucket(q, R, C->h_rep, nullptr, cur_z, B, true, e.cursor)) new_status = OLS_NO_QUEUE;
 #pragma unroll
           for (int j = 0; j < NA; ++j) prow[j] = (j < nA) ? (QT)e.q[j & 3] : (QT)-INFINITY;
@@ -784,7 +809,7 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
         if (!row_valid && !fresh) {
           fresh = true;
           if (AOS) {
-            const AosEntry e = load_aos(aos, cur_s);
+            const AosEntry e = load_aos(aos, cur_s, cfg.state_epoch);
 #pragma unroll
             for (int j = 0; j < NA; ++j) prow[j] = (j < nA) ? (QT)e.q[j & 3] : (QT)-INFINITY;
           } else {
@@ -895,16 +920,20 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
       const int64_t off = (int64_t)S_now * nA + j;
       return pi_is_f64 ? __ldg((const double*)pi_tab + off) : (double)__ldg((const float*)pi_tab + off);
     };
-    if (AGENT == OLS_AGENT_QLEARN) {
-      const float ib = C->ipn_base, it = C->ipn_top;
-#pragma unroll
-      for (int j = 0; j < NA; ++j) P.ipn[j] = (j >= nA) ? __int_as_float(0x7f800000) : ((j == a_star) ? it : ib);
-      P.ok = C->pn_ok != 0;
-    }
     // ---- env.step(p), one round of it: psrs.py:39-57
     float4 tail = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int res = pop_round<NV, RNG, PPL>(q, R, G, sub, gbase, gmask, live, rr, rid, P, pn_fn, PK, cfg.compute_mode, B, draws,
-                                            n_pop, pcg_s, pcg_inc, tail, cfg.prefetch);
+    int res;
+    if (AGENT == OLS_AGENT_QLEARN) {
+      EpsGreedySource<NA> src;
+      src.C = C;
+      src.a_star = a_star;
+      src.nA = nA;
+      res = pop_round<NV, RNG, PPL>(q, R, G, sub, gbase, gmask, live, rr, rid, src, pn_fn, PK, cfg.compute_mode, B, draws, n_pop,
+                                    pcg_s, pcg_inc, tail, cfg.prefetch);
+    } else {
+      res = pop_round<NV, RNG, PPL>(q, R, G, sub, gbase, gmask, live, rr, rid, P, pn_fn, PK, cfg.compute_mode, B, draws, n_pop,
+                                    pcg_s, pcg_inc, tail, cfg.prefetch);
+    }
     // ---- learner update and episode bookkeeping for the groups whose round ended the step
     if (live && res != kPopContinue) {
       // ---------------- phase 1: reads of shared state, loads, arithmetic
@@ -925,6 +954,16 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
       int S2 = 0;
       QT qn = (QT)0, td = (QT)0;
       float4 carry = make_float4(0.f, 0.f, 0.f, 0.f);  // QCARRY: the next step's policy row
+      // AoS: Q[S, :] as it stands before this step's update; the entry of S is rewritten whole in phase 2
+      float4 srow = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (QCARRY) {
+        srow = cold_ld4(C->qrow);
+      } else if (AOS) {
+        if (S >= 0 && S < nS) {
+          const AosEntry eS = load_aos(aos, S, cfg.state_epoch);
+          srow = make_float4(eS.q[0], eS.q[1], eS.q[2], eS.q[3]);
+        }
+      }
       double G_new = G_old;
       int t_new = t_old;
       if (accepted) {
@@ -933,7 +972,7 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
         // of the queue just popped is still the old one in memory; a self-loop patches it from the register.)
         AosEntry e2;
         e2.cursor = 0;
-        if (AOS && S2 >= 0 && S2 < nS) e2 = load_aos(aos, S2);  // the next state's cursor AND Q row: one sector
+        if (AOS && S2 >= 0 && S2 < nS) e2 = load_aos(aos, S2, cfg.state_epoch);  // the next state's cursor AND Q row: one sector
         const bool next_ok = done ? false : load_bucket(q, R, C->h_rep, cur_tab, Z2, B, AOS, e2.cursor);
         if (next_ok && B.b == b_done) B.cur = cur_done;
         bucket_valid = next_ok;
@@ -963,15 +1002,15 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
               boot = (QT)acc;
             }
             QT qsa;
-            if (QCARRY) {
-              qsa = (QT)C->qrow[A & 3];
+            if (AOS) {
+              qsa = (QT)((A == 0) ? srow.x : (A == 1) ? srow.y : (A == 2) ? srow.z : srow.w);
             } else if (AGENT == OLS_AGENT_QLEARN) {
               qsa = row[0];
 #pragma unroll
               for (int j = 1; j < NA; ++j)
                 if (j == A) qsa = row[j];
             } else {
-              qsa = AOS ? (QT)((const float*)(aos + (size_t)S * 32 + 16))[A] : Qr[(int64_t)S * nA + A];
+              qsa = Qr[(int64_t)S * nA + A];
             }
             td = QMath<QT>::td((QT)Rw, (QT)cfg.gamma, boot, qsa);
             qn = QMath<QT>::upd(qsa, (QT)alpha, td);
@@ -1011,16 +1050,25 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
       }
       __syncwarp(gm);
       // ---------------- phase 2: writes (every lane of the group writes the same values)
-      if (b_done >= 0) {
-        if (AOS) *(int*)(aos + (size_t)b_done * 32) = cur_done;
-        else cur_tab[b_done] = cur_done;
-      }
       // an accepted transition is committed unless the learner found its next observation out of range
       const bool commit = accepted && !(AGENT != OLS_AGENT_FIXED_PI && !q_write);
+      if (b_done >= 0) {
+        if (AOS) {
+          // b_done == S (the observation id is the queue key): cursor and Q[S, A] go out as one 32-byte store
+          if (commit && q_write) {
+            srow.x = (A == 0) ? (float)qn : srow.x;
+            srow.y = (A == 1) ? (float)qn : srow.y;
+            srow.z = (A == 2) ? (float)qn : srow.z;
+            srow.w = (A == 3) ? (float)qn : srow.w;
+          }
+          store_aos(aos, b_done, cur_done, cfg.state_epoch, srow);
+        } else {
+          cur_tab[b_done] = cur_done;
+        }
+      }
       if (commit) {
         if (q_write) {
-          if (AOS) ((float*)(aos + (size_t)S * 32 + 16))[A] = (float)qn;
-          else Qr[(int64_t)S * nA + A] = qn;
+          if (!AOS) Qr[(int64_t)S * nA + A] = qn;
           if (QCARRY) cold_st4(C->qrow, carry);
           if (sub == 0 && cfg.td_error && acc_idx < cfg.trace_cap) cfg.td_error[rr * cfg.trace_cap + acc_idx] = (double)td;
         }
@@ -1107,7 +1155,9 @@ inline cudaError_t launch_run_aos(const ols_queues_t& q, const ols_replicas_t& r
   if constexpr (NV == 1 && sizeof(QT) == 4 && AGENT != OLS_AGENT_FIXED_PI) {
     auto kf = run_kernel<NV, AGENT, QT, RNGT_FEED, 2, true>;
     auto kp = run_kernel<NV, AGENT, QT, RNGT_PHILOX, 2, true>;
-    auto k = (r.rng_mode == OLS_RNG_FEED) ? kf : kp;
+    auto kp2 = run_kernel<NV, AGENT, QT, RNGT_PHILOX, 2, true, 2>;
+    auto kp4 = run_kernel<NV, AGENT, QT, RNGT_PHILOX, 2, true, 4>;
+    auto k = (r.rng_mode == OLS_RNG_FEED) ? kf : (c.lanes == 2 ? kp2 : c.lanes == 4 ? kp4 : kp);
     if (L.smem > 40 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
       if (e != cudaSuccess) return e;

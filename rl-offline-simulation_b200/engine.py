@@ -231,8 +231,9 @@ class BucketedLog:
 # ----------------------------------------------------------------------------------------------- replicas
 @dataclass
 class RunResult:
-    """Outputs of a fused learner run, as device tensors (reference: psrs.py:180-185, 235-239, 271)."""
-    Q: Optional[torch.Tensor]            # [R, nS, nA]
+    """Outputs of a fused learner run, as device tensors (reference: psrs.py:180-185, 235-239, 271).
+
+    ``Q`` is [R, nS, nA]; with the AoS replica state it is gathered from the live entries on first access."""
     Gs: torch.Tensor                     # [R, ep_cap] discounted returns; row r valid up to n_returns[r]
     lengths: torch.Tensor                # [R, ep_cap] episode lengths; row r valid up to n_lengths[r]
     n_returns: torch.Tensor              # [R]
@@ -242,6 +243,14 @@ class RunResult:
     pops: torch.Tensor                   # [R] lifetime popped records
     trace_row: Optional[torch.Tensor]    # [R, trace_cap] accepted log rows (parity tap)
     td_error: Optional[torch.Tensor]     # [R, trace_cap]
+    _Q: Optional[torch.Tensor] = None
+    _q_fn: Optional[object] = None
+
+    @property
+    def Q(self) -> Optional[torch.Tensor]:
+        if self._Q is None and self._q_fn is not None:
+            self._Q = self._q_fn()
+        return self._Q
 
 
 class BatchedPSRS:
@@ -267,6 +276,7 @@ class BatchedPSRS:
         self.stage_smem = bool(stage_smem)          # stage cursor table (+Q) in shared memory when it fits
         self.aos_state = bool(aos_state)            # cursor + Q row of a state in one 32-byte entry (fused float32 learners)
         self.aos = None
+        self._epoch = 1                             # live epoch of the AoS entries (a zeroed table holds epoch 0: all stale)
         self.slices = int(slices)                   # time slices of a budgeted fused run: -1 auto, 0/1 off, k > 1 forced
         self._sched = None
         self.prefetch = int(prefetch)               # rounds ahead prefetched into L2 (<= 0: off; measured neutral on B200)
@@ -331,7 +341,10 @@ class BatchedPSRS:
             q, r = self.log.queues_struct(), self.replicas_struct()
             abi.check(self.lib.ols_replicas_init(C.byref(q), C.byref(r), _ptr(self._seeds), _stream_ptr()))
             if self.aos is not None:
-                self.aos.zero_()            # cursors 0, Q 0
+                self._epoch += 1            # every entry of the previous run is stale now: cursors 0, Q 0
+                if self._epoch >= 2 ** 31 - 1:
+                    self.aos.zero_()
+                    self._epoch = 1
 
     def reset(self, mask=None):
         """psrs.py:32-37 for every replica (or those with ``mask``): returns ``(s, status)`` tensors."""
@@ -423,19 +436,22 @@ class BatchedPSRS:
                                      "s == z, Philox/fed uniforms and the default reject rule")
                 if self.aos is None:
                     self.aos = torch.zeros((max(R, 1), n_states, 8), dtype=torch.float32, device=dev)
-                if Q is not None and Q.data_ptr() != self.aos.data_ptr() + 16:
-                    self.aos[:, :, 4:4 + nA] = Q.to(torch.float32)      # caller-supplied initial Q
-                Q = self.aos[:, :, 4:4 + nA]                            # strided view of the Q rows inside the entries
+                if Q is not None:                                       # caller-supplied initial Q: make every entry live
+                    words = self.aos.view(torch.int32)
+                    words[:, :, 0] = torch.where(words[:, :, 1] == self._epoch, words[:, :, 0], torch.zeros_like(words[:, :, 0]))
+                    words[:, :, 1] = self._epoch
+                    self.aos[:, :, 4:4 + nA] = Q.to(torch.float32)
+                Q = None
             if outputs is None:
                 Gs = torch.zeros((max(R, 1), ep_cap), dtype=torch.float64, device=dev)
                 lengths = torch.zeros((max(R, 1), ep_cap), dtype=torch.int32, device=dev)
                 trace_row = torch.full((max(R, 1), trace_cap), -1, dtype=torch.int32, device=dev) if trace_cap else None
                 td = torch.zeros((max(R, 1), trace_cap), dtype=torch.float64, device=dev) if (trace_cap and agent == abi.AGENT_QLEARN) else None
-                if agent != abi.AGENT_FIXED_PI and Q is None:
+                if agent != abi.AGENT_FIXED_PI and Q is None and not use_aos:
                     Q = torch.zeros((max(R, 1), n_states, nA), dtype=q_dtype, device=dev)
             else:
                 Gs, lengths, trace_row, td = outputs.Gs, outputs.lengths, outputs.trace_row, outputs.td_error
-                Q = Q if use_aos else outputs.Q
+                Q = None if use_aos else outputs.Q
             pi_t = None
             pi_is_f64 = 0
             if pi is not None:
@@ -452,7 +468,7 @@ class BatchedPSRS:
             if self._sched is None and self.slices not in (0, 1):
                 n_sched = int(self.lib.ols_run_sched_bytes(R, self.lanes)) // 4
                 self._sched = torch.zeros(max(n_sched, 1), dtype=torch.int32, device=dev)
-            cfg = abi.Run(agent=agent, n_states=n_states, slices=self.slices if max_steps > 0 else 0, sched=_ptr(self._sched), q_is_f64=int(Q is not None and Q.dtype == torch.float64),
+            cfg = abi.Run(agent=agent, n_states=n_states, state_epoch=self._epoch, slices=self.slices if max_steps > 0 else 0, sched=_ptr(self._sched), q_is_f64=int(Q is not None and Q.dtype == torch.float64),
                           state_aos=_ptr(self.aos if use_aos else None),
                           pi_is_f64=pi_is_f64, reject_mode=self.reject_mode,
                           compute_mode=abi.COMPUTE_F32 if compute == "f32" else abi.COMPUTE_F64, lanes=self.lanes,
@@ -464,7 +480,14 @@ class BatchedPSRS:
                           lengths=_ptr(lengths), trace_row=_ptr(trace_row), td_error=_ptr(td), trace_cap=int(trace_cap))
             q, r = self.log.queues_struct(), self.replicas_struct()
             abi.check(self.lib.ols_run(C.byref(q), C.byref(r), C.byref(cfg), _stream_ptr()))
-        return RunResult(Q=Q, Gs=Gs, lengths=lengths, n_returns=self.ep_index, n_lengths=self.ep_len_count,
+        q_fn = None
+        if use_aos:
+            aos, epoch = self.aos, self._epoch
+
+            def q_fn():
+                live = (aos.view(torch.int32)[:, :, 1] == epoch).unsqueeze(-1)
+                return torch.where(live, aos[:, :, 4:4 + nA], torch.zeros((), dtype=torch.float32, device=aos.device))
+        return RunResult(_Q=Q, _q_fn=q_fn, Gs=Gs, lengths=lengths, n_returns=self.ep_index, n_lengths=self.ep_len_count,
                          status=self.status, accepted=self.accepted, pops=self.pops, trace_row=trace_row, td_error=td)
 
     def run_qlearn(self, n_states, n_episodes, gamma, alpha=0.1, epsilon=1.0, Q=None, q_dtype=torch.float32,

@@ -611,3 +611,26 @@ def test_time_slices_need_a_budget(ob):
     from offsim4rl_b200 import _abi as abi
     assert abi.load().ols_run_sched_bytes(1000, 2) == 4 * (8 + 1)
     assert abi.load().ols_run_sched_bytes(1000, 3) == 0
+
+
+def test_aos_restart_and_initial_q(ob):
+    """The AoS table is never cleared: a restart makes its entries stale by bumping the epoch.  A restarted block must
+    behave like a new one, and a caller-supplied initial Q like the separate-array layout with the same Q."""
+    import torch
+    g = make_log(65, 60000, 100, 4, ep_len=15)
+    nS, R = 100, 700
+    log = device_log(ob, g, n_buckets=nS)
+    Q0 = torch.from_numpy(np.random.default_rng(3).normal(size=(R, nS, 4)).astype(np.float32)).cuda()
+
+    def run(sim, Q=None):
+        return sim.run_qlearn(nS, 30, gamma=0.9, alpha=0.2, epsilon=0.1, max_steps=200, trace_cap=200, Q=Q)
+
+    used = ob.BatchedPSRS(log, R, rng="philox", seed=9, ring=True, lanes=2, aos_state=True)
+    run(used, Q0.clone())                  # dirty the table, different epoch and different Q
+    for Qinit in (None, Q0):
+        used.restart()
+        a = run(used, None if Qinit is None else Qinit.clone())
+        ref = ob.BatchedPSRS(log, R, rng="philox", seed=9, ring=True, lanes=2, aos_state=False)
+        b = run(ref, None if Qinit is None else Qinit.clone())
+        assert torch.equal(a.trace_row, b.trace_row) and torch.equal(a.Q, b.Q) and torch.equal(a.Gs, b.Gs)
+        assert torch.equal(used.draws, ref.draws) and torch.equal(a.pops, b.pops)
