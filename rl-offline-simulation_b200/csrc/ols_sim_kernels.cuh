@@ -691,7 +691,7 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
   ols_u128 pcg_s = {0, 0}, pcg_inc = {0, 0};
   bool live = false;
   // every lane of the group writes the same values into the group's Cold block
-  C->status = OLS_IDLE;
+  if (!exists) C->status = OLS_IDLE;  // (one write per field and lane: the lanes of a group are not in lockstep)
   C->n_acc = 0;
   C->eps_episode = -1;
   C->budget = budget0;
