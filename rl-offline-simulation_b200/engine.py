@@ -59,6 +59,19 @@ class BucketedLog:
     would produce without re-bucketing.
     """
 
+    @classmethod
+    def from_dataset(cls, dataset, n_buckets=None, z=None, z_next=None, device=None, **kw):
+        """Ingest an ``OfflineDataset`` (in memory, ``load_npz`` or ``load_hdf5``): state ids from ``z``/``z_next`` (an
+        encoder's output, host or device), else the recorded ``infos/z`` columns, else discrete observations
+        (``OfflineDataset.device_columns``); the columns are uploaded once and bucketed on the GPU."""
+        if z is not None and not isinstance(z, np.ndarray):        # ids already on the device stay there
+            cols = dataset.device_columns(z=np.zeros(len(dataset), np.int32), z_next=np.zeros(len(dataset), np.int32))
+            cols["z"], cols["z_next"] = z, z_next
+        else:
+            cols = dataset.device_columns(z=z, z_next=z_next)
+        return cls(z=cols["z"], z_next=cols["z_next"], action=cols["action"], reward=cols["reward"], terminal=cols["terminal"],
+                   p_log=cols["p_log"], steps=cols["steps"], n_buckets=n_buckets, device=device, **kw)
+
     def __init__(self, z, z_next, action, reward, terminal, p_log, s=None, s_next=None, steps=None,
                  n_buckets=None, z_offset=None, device=None, keep_columns=False, key_by_action=False):
         dev = _require_cuda(device)

@@ -569,7 +569,26 @@ def case_psrs_exo():
     save("psrs_exo", **out)
 
 
+def case_recorder():
+    """utils/dataset_utils.py:34-136 `record_dataset_in_memory` on the toy environment of tests/helpers.py: the column
+    layout (`infos/<key>` flattening, first-step key rule, episode ids with several workers) that the ingest consumes."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from tests.helpers import ToyChainEnv, ToyAgent
+    from offsim4rl.utils.dataset_utils import record_dataset_in_memory
+    out = {}
+    for tag, kw in {"w0": dict(seed=5, worker_id=0, workers_num=1), "w2of3": dict(seed=8, worker_id=2, workers_num=3)}.items():
+        np.random.seed(123)
+        agent = ToyAgent(ProbDistribution.Discrete)
+        ds = record_dataset_in_memory(ToyChainEnv(), agent, 300, new_step_api=True, include_infos=True, **kw)
+        for k, v in ds.experience.items():
+            out[f"{tag}/{k}".replace("/", "__")] = np.asarray(v)
+        out[f"{tag}__committed"] = np.array(agent.committed)
+        out[f"{tag}__ended"] = np.array(agent.ended, dtype=np.float64)
+    save("recorder", **out)
+
+
 if __name__ == "__main__":
+    case_recorder()
     case_seeded_walk()
     case_drivers()
     case_accept_rule()

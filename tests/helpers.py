@@ -5,6 +5,9 @@ M32 = 0xFFFFFFFF
 M64 = 0xFFFFFFFFFFFFFFFF
 
 
+import numpy as np
+
+
 def philox4x32_10(ctr, k0, k1):
     c = list(ctr)
     for _ in range(10):
@@ -47,3 +50,66 @@ def ring_start(ring_seed, replica, bucket, length):
 
 def init_ring_start(ring_seed, replica, n_init):
     return (fmix32(ring_replica_hash(ring_seed, replica) ^ 0x85EBCA6B) * n_init) >> 32
+
+
+# --------------------------------------------------------------------------- toy environment / agent for the recorder
+class _Space:
+    def __init__(self, n=None, shape=None):
+        self.n, self.shape = n, shape
+
+
+class ToyChainEnv:
+    """Deterministic (given its seed) new-API gym-style environment: a ring of `n` cells, observation = 2 floats,
+    info reveals the cell id `z`, a float, an array, a string (unsupported type) and a key that is absent at first."""
+
+    def __init__(self, n=7, horizon=9):
+        self.n, self.horizon = n, horizon
+        self.observation_space, self.action_space = _Space(shape=(2,)), _Space(n=3)
+        self.rng = np.random.default_rng(0)
+        self.cell = self.t = 0
+        self.calls = 0
+
+    def _obs(self):
+        return np.array([self.cell / self.n, self.t / self.horizon], dtype=np.float32)
+
+    def reset(self, seed=None):
+        if seed is not None:
+            self.rng = np.random.default_rng(seed)
+        self.cell, self.t = int(self.rng.integers(self.n)), 0
+        return self._obs()
+
+    def step(self, action):
+        self.calls += 1
+        z = self.cell
+        self.cell = (self.cell + int(action) - 1 + (1 if self.rng.random() < 0.2 else 0)) % self.n
+        self.t += 1
+        terminated = self.cell == 0
+        truncated = self.t >= self.horizon
+        info = {"z": z, "z_next": self.cell, "noise": float(self.rng.normal()), "vec": np.array([z, self.cell]), "label": "x"}
+        if self.calls > 1:
+            info["late"] = 1.0
+        return self._obs(), float(self.cell == 0) - 0.1, terminated, truncated, info
+
+
+class ToyAgent:
+    """Observation-dependent fixed distributions; remembers what the recorder told it."""
+
+    def __init__(self, dist_type):
+        self.action_dist_type = dist_type
+        self.committed, self.ended = [], []
+
+    def _dist(self, obs):
+        w = np.array([1.0 + obs[0], 1.0, 2.0 - obs[1]])
+        return w / w.sum()
+
+    def begin_episode(self, observation):
+        return self._dist(observation)
+
+    def step(self, prev_reward, observation):
+        return self._dist(observation)
+
+    def commit_action(self, action):
+        self.committed.append(int(action))
+
+    def end_episode(self, reward, truncated=False):
+        self.ended.append((float(reward), bool(truncated)))

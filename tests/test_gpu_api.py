@@ -411,3 +411,38 @@ def test_psrs_exo_matches_reference(ob, golden, seed):
             ob_ = env.reset(seed=episode)
             obs.append(-1 if ob_ is None else ob_)
     assert n == expect.size and np.array_equal(np.array(obs, dtype=np.int64), g[f"obs_{seed}"])
+
+
+# --------------------------------------------------------------------------- ingest
+@pytest.mark.gpu
+def test_recorded_dataset_flows_into_the_simulator(ob, tmp_path):
+    """record -> save -> load -> device columns -> bucketing -> fused run, against the python oracle on the same
+    columns (fed uniforms and tie draws: bit-exact rows, float64 Q)."""
+    import torch
+    from tests.helpers import ToyChainEnv, ToyAgent
+    from offsim4rl_b200.utils import record_dataset_in_memory
+    from offsim4rl_b200.data import OfflineDataset, ProbDistribution
+    from oracle import psrs_oracle as O
+    np.random.seed(11)
+    ds = record_dataset_in_memory(ToyChainEnv(n=7), ToyAgent(ProbDistribution.Discrete), 4000, seed=2)
+    ds.save_npz(tmp_path / "toy.npz")
+    ds = OfflineDataset.load_npz(tmp_path / "toy.npz")
+    nS, nA = 7, 3
+    log = ob.BucketedLog.from_dataset(ds, n_buckets=nS)
+    cols = ds.device_columns()
+    rng = np.random.default_rng(4)
+    U, T = rng.random(20000), rng.random(5000)
+    sim = ob.BatchedPSRS(log, 3, rng="feed", u_feed=U, tie_feed=T, lanes=4)
+    res = sim.run_qlearn(nS, 30, gamma=0.9, alpha=0.1, epsilon=0.2, q_dtype=torch.float64, trace_cap=4000)
+    env = O.OraclePSRS(z=cols["z"], z_next=cols["z_next"], s=cols["z"], s_next=cols["z_next"], action=cols["action"],
+                       reward=cols["reward"], terminal=cols["terminal"], p_log=cols["p_log"], steps=cols["steps"],
+                       n_buckets=nS, uniforms=O.FeedUniforms(U))
+    Q, info = O.qlearn(env, 30, gamma=0.9, alpha=0.1, epsilon=0.2, ties=O.FeedTies(T), nS=nS, nA=nA)
+    n = len(info["trace"])
+    assert n > 100
+    for r in range(3):
+        assert int(res.accepted[r]) == n and np.array_equal(res.trace_row[r, :n].cpu().numpy(), info["trace"])
+        assert np.array_equal(res.Q[r].cpu().numpy(), Q)
+    # ids handed over as device tensors (an encoder's output) give the same queues
+    log2 = ob.BucketedLog.from_dataset(ds, n_buckets=nS, z=torch.as_tensor(cols["z"]).cuda(), z_next=torch.as_tensor(cols["z_next"]).cuda())
+    assert torch.equal(log2.offsets, log.offsets) and torch.equal(log2.order, log.order)
