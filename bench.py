@@ -246,6 +246,40 @@ def gather_stress_leg(ob, torch, dev, hbm_peak, launches=5, warm=3):
             "traffic": NCU_DRAM_BYTES_PER_ACCEPTED["c5"] * float(sim.accepted.sum()), "algorithmic_bytes_per_launch": pops * log.rec_bytes}
 
 
+def queue_evaluator_leg(ob, torch, dev, hbm_peak, steps=40, warm=5):
+    """the batched QueueEvaluator step (queues keyed by (z, a), the agent's own action picks the queue,
+    no rejection; queue_evaluator.py:121-131) — one `ols_step_action` launch per simulated step over 1M replicas, with the
+    replicas whose transition was terminal re-started by `ols_reset` in between.  Rank 0, one GPU, a second or two."""
+    N, nS, nA, R = 20_000_000, 1000, 4, 1_000_000
+    cols = ob.synth_columns(N, nS, behaviour_table(nS, nA, None), seed=3, device=dev)
+    log = ob.BucketedLog(z=cols["z"], z_next=cols["z_next"], action=cols["action"], reward=cols["reward"], terminal=cols["terminal"],
+                         p_log=cols["p_log"], steps=cols["steps"], n_buckets=nS, z_offset=0, device=dev, key_by_action=True)
+    del cols
+    sim = ob.BatchedPSRS(log, R, rng="philox", seed=5, ring=True, ring_seed=11, lanes=1)
+    acts = torch.randint(0, nA, (steps + warm, R), dtype=torch.int32, device=dev)
+    sim.reset()
+    done = 0
+    for i in range(steps + warm):
+        if i == warm:
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            done = torch.zeros((), dtype=torch.int64, device=dev)
+            e0.record()
+        out = sim.step_action(acts[i])
+        if i >= warm:
+            done += (out["row"] >= 0).sum()
+        sim.reset(mask=out["terminal"])
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) / 1e3
+    n = float(done)
+    per = log.rec_bytes + 8 + 8 + 4 + 21        # record, cursor r/w, current state r/w, action in, step outputs
+    return {"row": "QueueEvaluator.step over (z, a)-keyed queues (queue_evaluator.py:121-131), batched", "rows": N, "states": nS,
+            "actions": nA, "replicas": R, "steps": steps, "value": n / t, "unit": "transitions/s", "launches": 2 * steps,
+            "achieved": n * per / t / 1e9, "peak": hbm_peak, "roofline_unit": "GB/s", "frac": n * per / t / 1e9 / hbm_peak,
+            "algorithmic_bytes_per_transition": per, "note": "one launch per simulated step; random 32-byte record reads"}
+
+
 # ------------------------------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -434,11 +468,13 @@ def main():
     else:
         cpu_cols = {k: v[:1_000_000].cpu().numpy() for k, v in cols.items()}
 
-    stress = None
+    stress = next_rows = None
     if rank == 0 and args.workload == "c4" and not args.skip_stress:
         sim = Q = res = None        # release the c4 state (25 GB) before building the c5 log
         torch.cuda.empty_cache()
         stress = gather_stress_leg(ob, torch, dev, hbm_peak)
+        torch.cuda.empty_cache()
+        next_rows = {"queue_evaluator": queue_evaluator_leg(ob, torch, dev, hbm_peak)}
     if rank == 0:
         cpu = None
         if not args.skip_cpu and world == 1:
@@ -476,7 +512,7 @@ def main():
             "bucketing": {"rows": N, "ms": bucket_ms, "GBps": bucket_bytes / bucket_ms / 1e6, "frac": bucket_bytes / bucket_ms / 1e6 / hbm_peak,
                           "note": "ols_bucket + ols_init_queue kernels; bytes = z twice + order + log columns + packed record per row"},
             "step_breakdown_ms": {k: sum(a.elapsed_time(b) for a, b in v) / max(1, len(v)) for k, v in k_ev.items()},
-            "gather_stress": stress,
+            "gather_stress": stress, "next_rows": next_rows,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 4 * args.steps, "clocks": clocks,
         }
         print(json.dumps(out))
