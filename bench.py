@@ -296,6 +296,7 @@ def main():
     ap.add_argument("--prefetch", type=int, default=-1)
     ap.add_argument("--ppl", type=int, default=0, help="records per lane per round (0 = auto)")
     ap.add_argument("--slices", type=int, default=-1, help="time slices of the fused run: -1 auto, 0 off, k forced")
+    ap.add_argument("--no-hot", action="store_true", help="pop from the 32-byte records only (no 8-byte hot records)")
     ap.add_argument("--no-aos", action="store_true", help="separate cursor / Q arrays instead of one 32-byte entry per (replica, state)")
     ap.add_argument("--no-ring", action="store_true", help="all replicas consume the queues from slot 0 (L2-resident gather)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -347,9 +348,10 @@ def main():
     # ---- setup (untimed): synthetic log generated on the device, bucketed once
     cols = ob.synth_columns(N, nS, pb, seed=0, device=dev)
     torch.cuda.synchronize()
+    use_hot = qlearn and nA <= 4 and not args.no_aos and not args.no_hot and args.workload == "c4"   # no gain when the state fits L2 (c2)
     log = ob.BucketedLog(z=cols["z"], z_next=cols["z_next"], action=cols["action"], reward=cols["reward"],
                          terminal=cols["terminal"], p_log=cols["p_log"], steps=cols["steps"], n_buckets=nS, z_offset=0, device=dev,
-                         keep_columns=True)
+                         keep_columns=True, hot_records=use_hot)
     bucket_ms = log.time_bucketing(3)       # ols_bucket + ols_init_queue, CUDA events on the launching stream
     log.drop_columns()
     rec_bytes = log.rec_bytes
@@ -437,7 +439,7 @@ def main():
             nonlocal res, d2h
             c = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
             lg = ob.BucketedLog(z=c["z"], z_next=c["z_next"], action=c["action"], reward=c["reward"], terminal=c["terminal"],
-                                p_log=c["p_log"], steps=c["steps"], n_buckets=nS, z_offset=0, device=dev)
+                                p_log=c["p_log"], steps=c["steps"], n_buckets=nS, z_offset=0, device=dev, hot_records=use_hot)
             del c
             sim.restart(lg)
             if Q is not None:
@@ -497,6 +499,8 @@ def main():
             "config": {"workload": args.workload + ": " + wl["desc"], "rows": N, "states": nS, "actions": nA,
                        "replicas_per_gpu": R, "accepted_per_replica_per_step": T, "lanes": wl["lanes"],
                        "time_slices": ("auto (16 per replica block when the blocks are not a whole number of waves)" if args.slices == -1 else args.slices),
+                       "hot_records": ("8-byte half-precision images of the records decide all but ~5e-4 of the pops; the 32-byte record is "
+                                       "read for the accepted pop and for the undecided ones" if use_hot else "off"),
                        "replica_state": ("one 32-byte entry {cursor, Q row} per (replica, state)" if use_aos else "separate cursor and Q arrays"),
                        "queue_order": "log order" + ("" if args.no_ring else " + per-(replica,state) ring offset"),
                        "l2": "working set (records %.1f GB + replica state %.1f GB) >> 126 MB L2; no flush" % (

@@ -113,6 +113,10 @@ typedef struct ols_queues {
                                  when it differs from the state id (psrs.py:36,49-50)            */
   const double* p_log64;      /* NULL, or the float64 log distribution [n_rows][n_actions] in ROW
                                  order when it is not exactly float32-representable              */
+  void* hot;                  /* NULL, or [n_rows] 8-byte HOT records in queue order (n_actions <= 4): half-precision
+                                 images of the record's probabilities plus its action — all the accept rule needs for
+                                 all but ~5e-4 of the pops, so the fused run reads 8 instead of 32 bytes per rejected
+                                 record.  Filled by ols_bucket / ols_shuffle_queues when non-NULL.               */
 } ols_queues_t;
 
 /* ---- a block of independent simulation replicas ------------------------------------------ *

@@ -38,7 +38,7 @@ class Log(C.Structure):
 class Queues(C.Structure):
     _fields_ = [("n_rows", i64), ("n_init", i64), ("n_actions", i32), ("n_buckets", i32), ("z_offset", i32),
                 ("rec_bytes", i32), ("offsets", p), ("records", p), ("init_row", p), ("init_z", p),
-                ("init_s", p), ("s_next", p), ("p_log64", p)]
+                ("init_s", p), ("s_next", p), ("p_log64", p), ("hot", p)]
 
 
 class Replicas(C.Structure):

@@ -304,6 +304,29 @@ __global__ void __launch_bounds__(kBucketThreads) scatter_pack_kernel(ols_log_t 
   }
 }
 
+// ---------------------------------------------------------------------------------------- hot records
+// One streaming pass over the packed queues: 32 bytes in, 8 bytes out per record (n_actions <= 4).
+__global__ void __launch_bounds__(256) hot_pack_kernel(ols_queues_t q) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < q.n_rows; i += stride) {
+    const float4* rp = (const float4*)((const char*)q.records + (size_t)i * 32);
+    const float4 p = __ldg(rp);
+    const uint32_t meta = __float_as_uint(__ldg(rp + 1).w);
+    ((uint2*)q.hot)[i] = ols_hot_pack(p, ols_meta_action(meta), q.n_actions);
+  }
+}
+
+inline int pack_hot(const ols_queues_t* q, cudaStream_t stream) {
+  if (q->hot == nullptr || q->n_rows == 0) return OLS_OK;
+  OLS_REQUIRE(q->n_actions <= 4 && q->rec_bytes == 32, OLS_ERR_UNSUPPORTED, "hot records need n_actions <= 4");
+  OLS_REQUIRE((uintptr_t)q->hot % 8 == 0, OLS_ERR_INVALID, "hot records must be 8-byte aligned");
+  int blocks = ols_div_up(q->n_rows, 256);
+  if (blocks > OLS_SM_COUNT * 16) blocks = OLS_SM_COUNT * 16;
+  hot_pack_kernel<<<blocks, 256, 0, stream>>>(*q);
+  OLS_LAUNCH_CHECK();
+  return OLS_OK;
+}
+
 // ---------------------------------------------------------------------------------------- initial rows
 // Stable compaction of the rows with step == 0: per-CTA counts -> scan -> ordered write.
 constexpr int kInitThreads = 256;
@@ -556,7 +579,7 @@ extern "C" int ols_bucket(const ols_log_t* log, const ols_queues_t* q, void* scr
   }
 #undef OLS_SCATTER
   OLS_LAUNCH_CHECK();
-  return OLS_OK;
+  return pack_hot(q, stream);
 }
 
 extern "C" int ols_init_queue(const ols_log_t* log, const ols_queues_t* q, int64_t* n_init_dev, void* scratch,
@@ -619,5 +642,5 @@ extern "C" int ols_shuffle_queues(const ols_queues_t* src, const ols_queues_t* d
   OLS_LAUNCH_CHECK();
   gather_queues_kernel<<<blocks, 256, 0, stream>>>(*src, *dst, perm_scratch);
   OLS_LAUNCH_CHECK();
-  return OLS_OK;
+  return pack_hot(dst, stream);
 }

@@ -1,6 +1,7 @@
 // Shared device/host helpers for the PSRS engine (sm_100a only).
 #pragma once
 
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -54,6 +55,37 @@ __host__ __device__ inline uint32_t ols_pack_meta(int action, int terminal, int 
 __host__ __device__ inline int ols_meta_tame(uint32_t m) { return (int)((m >> 9) & 1); }
 __host__ __device__ inline int ols_meta_action(uint32_t m) { return (int)(m & 0xff); }
 __host__ __device__ inline int ols_meta_terminal(uint32_t m) { return (int)((m >> 8) & 1); }
+
+// ---- hot records (ols_queues_t.hot): what the accept rule needs of a <= 4-action record, in 8 bytes.
+// Four IEEE half images of the logged probabilities (all >= 0, so the sign bits are free): bit 15 of halves 0 and 1
+// carries the action, bit 15 of half 2 the "hot-tame" flag (every probability in [2^-13, 1]: a normal half, relative
+// rounding error <= 2^-11).  The pop loop decides from these with a 2^-9 band (threshold estimate within 1 + 2^-10 + 2^-19
+// of the exact one) and falls back to the full 32-byte record inside the band or when the flag is clear.
+#ifdef __CUDACC__
+__device__ __forceinline__ uint2 ols_hot_pack(float4 p, int action, int n_actions) {
+  const float v[4] = {p.x, p.y, p.z, p.w};
+  unsigned c[4];
+  bool tame = ((unsigned)action < 4u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const bool in_range = (v[j] >= 1.220703125e-4f) && (v[j] <= 1.0f);  // false for NaN
+    tame = tame && (j >= n_actions || in_range);
+    c[j] = (unsigned)__half_as_ushort(__float2half_rn(in_range ? v[j] : 1.0f)) & 0x7fffu;
+  }
+  uint2 h;
+  h.x = c[0] | (c[1] << 16) | (((unsigned)action & 1u) << 15) | ((((unsigned)action >> 1) & 1u) << 31);
+  h.y = c[2] | (c[3] << 16) | ((tame ? 1u : 0u) << 15);
+  return h;
+}
+__device__ __forceinline__ void ols_hot_unpack(uint2 h, float (&p)[4], int& action, bool& tame) {
+  action = (int)(((h.x >> 15) & 1u) | ((h.x >> 31) << 1));
+  tame = ((h.y >> 15) & 1u) != 0u;
+  const unsigned lo = h.x & 0x7fff7fffu, hi = h.y & 0x7fff7fffu;
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&lo));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  p[0] = a.x; p[1] = a.y; p[2] = b.x; p[3] = b.y;
+}
+#endif
 
 // ------------------------------------------------------------------------------------------ Philox4x32-10
 // Salmon et al., "Parallel random numbers: as easy as 1, 2, 3" (SC'11).  Counter-based: the value

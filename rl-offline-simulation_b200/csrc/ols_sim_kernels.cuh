@@ -113,7 +113,8 @@ __device__ __forceinline__ float rcp_approx(float x) {
 }
 
 template <int NA>
-__device__ __forceinline__ int accept_filter(const Policy<NA>& P, const float (&plf)[NA], int a, float uf, bool guards) {
+__device__ __forceinline__ int accept_filter(const Policy<NA>& P, const float (&plf)[NA], int a, float uf, bool guards,
+                                             float band = 1.52587890625e-5f /* 2^-16 */) {
   // padding entries (j >= n_actions) hold p = 1 in the record and ipn = +inf in the policy: t_j = +inf never wins the min
   float t = plf[0] * P.ipn[0];
   float inv_m = t, ta = t;
@@ -125,8 +126,8 @@ __device__ __forceinline__ int accept_filter(const Policy<NA>& P, const float (&
   }
   const float thr = inv_m * rcp_approx(ta);
   int dec = 2;
-  if (uf > thr * (1.0f + 1.52587890625e-5f)) dec = 0;  // 2^-16 band
-  if (uf < thr * (1.0f - 1.52587890625e-5f)) dec = 1;
+  if (uf > thr * (1.0f + band)) dec = 0;
+  if (uf < thr * (1.0f - band)) dec = 1;
   return guards ? dec : 2;
 }
 
@@ -460,6 +461,127 @@ __device__ __forceinline__ int pop_round(const ols_queues_t& q, const ols_replic
   return result;
 }
 
+// ONE pop round over HOT records (ols_queues_t.hot: 8 bytes per record, see ols_common.cuh): every lane examines four
+// consecutive records = 32 bytes, a lane pair one 64-byte DRAM atom, where the full records cost 128 bytes for half as
+// many pops.  Same contract as pop_round<1, RNGT_PHILOX, 4>.  Decision ladder per pop: half-precision estimate with a
+// 2^-9 band -> float32 estimate from the full record with the 2^-16 band -> exact rule; the full record of the ACCEPTED
+// pop (reward, next state, row, terminal) is fetched once the winner is known, by every lane of the group (one sector).
+template <typename PolT, typename PnFn>
+__device__ __forceinline__ int pop_round_hot(const ols_queues_t& q, int G, int sub, int gbase, unsigned gmask, bool active,
+                                             uint64_t rid, const PolT& pol, PnFn pn_fn, const ols_philox_keys& PK,
+                                             int compute_mode, Bucket& B, uint64_t& draws, float4& win_tail) {
+  constexpr int PPL = 4, NA = 4, kRec = 32;
+  const int nA = q.n_actions;
+  int result = active ? kPopContinue : kPopIdle;
+  const int remaining = B.len - B.cur;
+  if (active && remaining <= 0) {
+    result = OLS_QUEUE_EMPTY;
+    active = false;
+  }
+  const int align = (int)(draws & 1);  // rounds are aligned to an even draw index: each lane needs exactly two Philox blocks
+  const int n_eval = active ? min(G * PPL - align, remaining) : 0;
+  const int k0 = sub * PPL - align;
+  uint2 h[PPL];
+  bool valid[PPL];
+#pragma unroll
+  for (int i = 0; i < PPL; ++i) {
+    valid[i] = (unsigned)(k0 + i) < (unsigned)n_eval;
+    h[i] = make_uint2(0u, 0u);
+    if (valid[i]) {
+      uint32_t pos = B.start + (uint32_t)(B.cur + k0 + i);
+      if (pos >= (uint32_t)B.len) pos -= (uint32_t)B.len;
+      h[i] = __ldg((const uint2*)q.hot + (size_t)(uint32_t)(B.lo + (int32_t)pos));
+    }
+  }
+  float u[PPL];
+  bool tiny[PPL];
+#pragma unroll
+  for (int i = 0; i < PPL; ++i) {
+    u[i] = 0.f;
+    tiny[i] = false;
+  }
+#pragma unroll
+  for (int j = 0; j < PPL / 2; ++j) {
+    if (valid[2 * j] || valid[2 * j + 1]) {
+      const uint64_t blk = ((draws - (uint64_t)align) >> 1) + (uint64_t)(sub * (PPL / 2) + j);
+      ols_u4 c;
+      c.x = (uint32_t)blk;
+      c.y = (uint32_t)(blk >> 32);
+      c.z = (uint32_t)rid;
+      c.w = (uint32_t)(rid >> 32);
+      const ols_u4 o = ols_philox4x32_10_keyed(c, PK);
+      float f0 = __uint2float_rn(o.y) * 2.3283064365386963e-10f, f1 = __uint2float_rn(o.w) * 2.3283064365386963e-10f;
+      if (o.y < (1u << 20)) f0 = __ull2float_rn((((uint64_t)o.y << 32) | o.x) >> 11) * 1.1102230246251565e-16f;
+      if (o.w < (1u << 20)) f1 = __ull2float_rn((((uint64_t)o.w << 32) | o.z) >> 11) * 1.1102230246251565e-16f;
+      u[2 * j] = f0;
+      u[2 * j + 1] = f1;
+      tiny[2 * j] = !(f0 >= 8.6736174e-19f);
+      tiny[2 * j + 1] = !(f1 >= 8.6736174e-19f);
+    }
+  }
+  const Policy<NA> P = pol.get();
+  bool acc[PPL];
+#pragma unroll
+  for (int i = 0; i < PPL; ++i) {
+    acc[i] = false;
+    if (valid[i]) {
+      float plf[NA];
+      int a;
+      bool tame;
+      ols_hot_unpack(h[i], plf, a, tame);
+      int dec = accept_filter<NA>(P, plf, a, u[i], P.ok && !tiny[i] && tame, 1.953125e-3f /* 2^-9 */);
+      if (dec == 2) {
+        const int k = k0 + i;
+        uint32_t pos = B.start + (uint32_t)(B.cur + k);
+        if (pos >= (uint32_t)B.len) pos -= (uint32_t)B.len;
+        const float4* rp = (const float4*)((const char*)q.records + (size_t)(uint32_t)(B.lo + (int32_t)pos) * kRec);
+        float4 pf, tl;
+        load_record32(rp, pf, tl);
+        const uint32_t meta = __float_as_uint(tl.w);
+        const float full[NA] = {pf.x, pf.y, pf.z, pf.w};
+        dec = accept_filter<NA>(P, full, ols_meta_action(meta), u[i], P.ok && !tiny[i] && ols_meta_tame(meta) != 0);
+        if (dec == 2) {
+          const double ue = ols_philox_uniform_keyed(PK, rid, 0u, draws + (uint64_t)k);
+          const double* p64 = q.p_log64 ? q.p_log64 + (int64_t)__float_as_int(tl.z) * nA : nullptr;
+          dec = (int)accept_slow(pn_fn, (const float*)rp, p64, nA, ols_meta_action(meta), ue, compute_mode);
+        }
+      }
+      acc[i] = (dec == 1);
+    }
+  }
+  // ---- first accepting pop of the group, in queue order
+  int first_acc = 1 << 20;
+  {
+    int mine = PPL;
+#pragma unroll
+    for (int i = PPL - 1; i >= 0; --i) mine = acc[i] ? i : mine;
+    const unsigned g_any = (__ballot_sync(kFull, mine < PPL) >> gbase) & gmask;
+    const int w = g_any ? __ffs(g_any) - 1 : 0;
+    const int wi = __shfl_sync(kFull, mine, gbase + w);
+    if (g_any) first_acc = w * PPL + wi - align;
+  }
+  int consumed = 0;
+  bool took = false;
+  if (active) {
+    if (first_acc < (1 << 20)) {
+      consumed = first_acc + 1;
+      took = true;
+    } else {
+      consumed = n_eval;
+    }
+  }
+  if (took) {
+    uint32_t pos = B.start + (uint32_t)(B.cur + first_acc);
+    if (pos >= (uint32_t)B.len) pos -= (uint32_t)B.len;
+    float4 pf;
+    load_record32((const float4*)((const char*)q.records + (size_t)(uint32_t)(B.lo + (int32_t)pos) * kRec), pf, win_tail);
+    result = OLS_RUNNING;
+  }
+  B.cur += consumed;
+  draws += (uint64_t)consumed;
+  return result;
+}
+
 // ------------------------------------------------------------------------------------------ kernels: step
 template <int NV, int RNG>
 __global__ void __launch_bounds__(kThreads) step_kernel(ols_queues_t q, ols_replicas_t R, const uint8_t* mask,
@@ -632,7 +754,7 @@ struct EpsGreedySource {
 // The run loop.  Lane groups of a warp are DECOUPLED: every iteration each live group executes one pop round
 // against its own queue; a group whose round accepted a record runs the learner update and prepares its next
 // step in the same iteration (predicated), so no group waits for the longest reject chain in its warp.
-template <int NV, int AGENT, typename QT, int RNG, int PPL, bool AOS = false, int GT = 0>
+template <int NV, int AGENT, typename QT, int RNG, int PPL, bool AOS = false, int GT = 0, bool HOT = false>
 __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel(ols_queues_t q, ols_replicas_t R, ols_run_t cfg,
                                                                                   StagePlan plan, ols_philox_keys PK) {
   constexpr int NA = 4 * NV;
@@ -641,6 +763,7 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
   // reciprocals every round: neither is held in registers across the pop rounds (they were spilled to local memory).
   constexpr bool QCARRY = AOS && AGENT == OLS_AGENT_QLEARN;
   static_assert(!AOS || (NV == 1 && sizeof(QT) == 4 && AGENT != OLS_AGENT_FIXED_PI), "AoS state: float32 learners, <= 4 actions");
+  static_assert(!HOT || (NV == 1 && RNG == RNGT_PHILOX && PPL == 4), "hot records: <= 4 actions, Philox uniforms, 4 per lane");
   extern __shared__ __align__(16) unsigned char s_mem[];
   const int nA = q.n_actions;
   const int nS = cfg.n_states;
@@ -923,7 +1046,17 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
     // ---- env.step(p), one round of it: psrs.py:39-57
     float4 tail = make_float4(0.f, 0.f, 0.f, 0.f);
     int res;
-    if (AGENT == OLS_AGENT_QLEARN) {
+    if constexpr (HOT) {
+      if (AGENT == OLS_AGENT_QLEARN) {
+        EpsGreedySource<NA> src;
+        src.C = C;
+        src.a_star = a_star;
+        src.nA = nA;
+        res = pop_round_hot(q, G, sub, gbase, gmask, live, rid, src, pn_fn, PK, cfg.compute_mode, B, draws, tail);
+      } else {
+        res = pop_round_hot(q, G, sub, gbase, gmask, live, rid, P, pn_fn, PK, cfg.compute_mode, B, draws, tail);
+      }
+    } else if (AGENT == OLS_AGENT_QLEARN) {
       EpsGreedySource<NA> src;
       src.C = C;
       src.a_star = a_star;
@@ -1158,6 +1291,11 @@ inline cudaError_t launch_run_aos(const ols_queues_t& q, const ols_replicas_t& r
     auto kp2 = run_kernel<NV, AGENT, QT, RNGT_PHILOX, 2, true, 2>;
     auto kp4 = run_kernel<NV, AGENT, QT, RNGT_PHILOX, 2, true, 4>;
     auto k = (r.rng_mode == OLS_RNG_FEED) ? kf : (c.lanes == 2 ? kp2 : c.lanes == 4 ? kp4 : kp);
+    if (q.hot != nullptr && r.rng_mode == OLS_RNG_PHILOX) {  // hot records: 4 x 8 bytes per lane and round
+      auto kh = run_kernel<NV, AGENT, QT, RNGT_PHILOX, 4, true, 0, true>;
+      auto kh2 = run_kernel<NV, AGENT, QT, RNGT_PHILOX, 4, true, 2, true>;
+      k = (c.lanes == 2) ? kh2 : kh;
+    }
     if (L.smem > 40 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
       if (e != cudaSuccess) return e;

@@ -73,7 +73,7 @@ class BucketedLog:
                    p_log=cols["p_log"], steps=cols["steps"], n_buckets=n_buckets, device=device, **kw)
 
     def __init__(self, z, z_next, action, reward, terminal, p_log, s=None, s_next=None, steps=None,
-                 n_buckets=None, z_offset=None, device=None, keep_columns=False, key_by_action=False):
+                 n_buckets=None, z_offset=None, device=None, keep_columns=False, key_by_action=False, hot_records=False):
         dev = _require_cuda(device)
         self.device = dev
         lib = abi.load()
@@ -143,6 +143,8 @@ class BucketedLog:
             self.offsets = torch.empty(n_buckets + 1, dtype=torch.int32, device=dev)
             self.s_next = s_next            # kept resident only when the agent's observation id differs from z
             self.records = torch.empty(max(n, 1) * self.rec_bytes // 4, dtype=torch.float32, device=dev)
+            # 8-byte hot records next to the 32-byte ones (n_actions <= 4): what the fused AoS run reads per rejected pop
+            self.hot = torch.empty(max(n, 1), dtype=torch.int64, device=dev) if (hot_records and n_actions <= 4) else None
             init_row = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
             init_z = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
             init_s = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
@@ -157,7 +159,7 @@ class BucketedLog:
             q = abi.Queues(n_rows=n, n_init=0, n_actions=n_actions, n_buckets=n_buckets, z_offset=key_offset,
                            rec_bytes=self.rec_bytes, offsets=_ptr(self.offsets),
                            records=_ptr(self.records), init_row=_ptr(init_row), init_z=_ptr(init_z),
-                           init_s=_ptr(init_s), s_next=_ptr(s_next), p_log64=_ptr(p_log64))
+                           init_s=_ptr(init_s), s_next=_ptr(s_next), p_log64=_ptr(p_log64), hot=_ptr(self.hot))
             abi.check(lib.ols_bucket(C.byref(log_key), C.byref(q), _ptr(scratch), sb, _stream_ptr()))
             abi.check(lib.ols_init_queue(C.byref(log), C.byref(q), _ptr(n_init_dev), _ptr(scratch), sb, _stream_ptr()))
             self.n_init = int(n_init_dev.item())        # one sync: construction is not the step path
@@ -204,7 +206,8 @@ class BucketedLog:
         return abi.Queues(n_rows=self.n_rows, n_init=self.n_init, n_actions=self.n_actions, n_buckets=self.n_buckets,
                           z_offset=self.z_offset, rec_bytes=self.rec_bytes, offsets=_ptr(self.offsets),
                           records=_ptr(self.records), init_row=_ptr(self.init_row), init_z=_ptr(self.init_z),
-                          init_s=_ptr(self.init_s), s_next=_ptr(self.s_next), p_log64=_ptr(self.p_log64))
+                          init_s=_ptr(self.init_s), s_next=_ptr(self.s_next), p_log64=_ptr(self.p_log64),
+                          hot=_ptr(getattr(self, "hot", None)))
 
     @property
     def order(self) -> torch.Tensor:
@@ -224,6 +227,7 @@ class BucketedLog:
         out.__dict__.update(base.__dict__)
         with torch.cuda.device(base.device):
             out.records = torch.empty_like(base.records)
+            out.hot = None if base.hot is None else torch.empty_like(base.hot)
             out.init_row = torch.empty_like(base.init_row)
             out.init_z = torch.empty_like(base.init_z)
             out.init_s = torch.empty_like(base.init_s)

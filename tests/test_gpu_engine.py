@@ -634,3 +634,62 @@ def test_aos_restart_and_initial_q(ob):
         b = run(ref, None if Qinit is None else Qinit.clone())
         assert torch.equal(a.trace_row, b.trace_row) and torch.equal(a.Q, b.Q) and torch.equal(a.Gs, b.Gs)
         assert torch.equal(used.draws, ref.draws) and torch.equal(a.pops, b.pops)
+
+
+# --------------------------------------------------------------------------------------- hot records
+def _expected_hot(p_log, action, nA):
+    """numpy restatement of ols_hot_pack (csrc/ols_common.cuh)."""
+    p = np.ones((p_log.shape[0], 4), dtype=np.float32)
+    p[:, :nA] = p_log
+    in_range = (p >= np.float32(2.0 ** -13)) & (p <= 1.0)
+    tame = in_range[:, :nA].all(1) & (action < 4)
+    codes = np.where(in_range, p, np.float32(1.0)).astype(np.float16).view(np.uint16).astype(np.uint64) & 0x7FFF
+    a = action.astype(np.uint64)
+    lo = codes[:, 0] | (codes[:, 1] << 16) | ((a & 1) << 15) | (((a >> 1) & 1) << 31)
+    hi = codes[:, 2] | (codes[:, 3] << 16) | (tame.astype(np.uint64) << 15)
+    return lo | (hi << 32)
+
+
+@pytest.mark.parametrize("nA,seed", [(4, None), (3, 5), (2, None)])
+def test_hot_records_encode_the_queue_records(ob, nA, seed):
+    g = make_log(70, 30000, 50, nA)
+    g["p_log"][::7, 0] = 1e-5                 # below the half range: not hot-tame
+    g["p_log"][3::11, nA - 1] = 0.0
+    log = device_log(ob, g, n_buckets=50, hot_records=True).seeded(seed)
+    order = log.order.cpu().numpy()
+    want = _expected_hot(g["p_log"][order], g["a"][order], nA)
+    got = log.hot.cpu().numpy().view(np.uint64)[: order.size]
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("agent", ["qlearn", "expsarsa"])
+@pytest.mark.parametrize("lanes,ring,seeded", [(2, True, None), (4, False, 3), (32, True, None), (1, True, 9)])
+def test_hot_records_never_change_a_run(ob, agent, lanes, ring, seeded):
+    """The 8-byte hot records only pre-decide pops whose half-precision threshold estimate is far from the uniform; every
+    other pop goes to the full record.  Rows, Q, returns and all counters must equal the run on the 32-byte records,
+    including logs with probabilities outside the half range, zero probabilities and float64-only values."""
+    import torch
+    g = make_log(71, 150000, 200, 4, ep_len=20, p_dtype=np.float64)
+    g["p_log"][::13, 1] = 3e-6                 # not hot-tame
+    g["p_log"][5::17, 2] = 0.0                  # infinite ratios on the exact path
+    nS, R = 200, 3000
+    pi = np.random.default_rng(12).dirichlet(np.ones(4), size=nS)
+    pi[::9, 0] = 0.0
+    pi /= pi.sum(1, keepdims=True)
+    outs = []
+    for hot in (False, True):
+        log = device_log(ob, g, n_buckets=nS, hot_records=hot).seeded(seeded)
+        assert (log.hot is not None) == hot
+        sim = ob.BatchedPSRS(log, R, rng="philox", seed=21, ring=ring, ring_seed=2, lanes=lanes, aos_state=True)
+        res = None
+        for budget in (260, 140):
+            if agent == "qlearn":
+                res = sim.run_qlearn(nS, 50, gamma=0.9, alpha=0.1, epsilon=0.15, max_steps=budget, trace_cap=400, outputs=res)
+            else:
+                res = sim.run_expsarsa(nS, 50, pi=pi, gamma=0.9, alpha=0.1, max_steps=budget, trace_cap=400, outputs=res)
+        outs.append((res, sim.draws.clone(), sim.ties.clone()))
+    (a, da, ta), (b, db, tb) = outs
+    assert torch.equal(a.trace_row, b.trace_row) and torch.equal(a.accepted, b.accepted) and torch.equal(a.pops, b.pops)
+    assert torch.equal(da, db) and torch.equal(ta, tb) and torch.equal(a.status, b.status)
+    assert torch.equal(a.Q, b.Q) and torch.equal(a.Gs, b.Gs) and torch.equal(a.lengths, b.lengths)
+    assert int(a.accepted.sum()) > 0.5 * R * 400
