@@ -42,7 +42,7 @@ WORKLOADS = {
 # DRAM bytes (read + write) per accepted transition of the fused run kernel, from the committed `ncu --set full`
 # captures (profiles/r01f_ncu_full_run_kernel_final_*.txt): dram__bytes_read.sum + dram__bytes_write.sum divided by the
 # accepted transitions of the captured launch.  Used to report `roofline.traffic` per launch.
-NCU_DRAM_BYTES_PER_ACCEPTED = {"c4": (19.097991e9 + 1.288564e9) / 3.75e7, "c5": (78.641898e9 + 1.658046e9) / 3.2e6}
+NCU_DRAM_BYTES_PER_ACCEPTED = {"c4": (17.565853e9 + 1.293527e9) / 3.75e7, "c5": (78.641898e9 + 1.658046e9) / 3.2e6}
 EPS, ALPHA, GAMMA = 0.1, 0.1, 0.99
 EP_CAP = 512
 
@@ -510,7 +510,7 @@ def main():
                          "unit": "GB/s", "frac": gather_gbs / hbm_peak,
                          "traffic": (NCU_DRAM_BYTES_PER_ACCEPTED[args.workload] * last_accepted
                                      if args.workload in NCU_DRAM_BYTES_PER_ACCEPTED else None),
-                         "traffic_note": "DRAM read+write bytes per launch = ncu bytes per accepted transition (profiles/r01i_* for c4, r01f_* for c5) x accepted per launch",
+                         "traffic_note": "DRAM read+write bytes per launch = ncu bytes per accepted transition (profiles/r01j_* for c4, r01f_* for c5) x accepted per launch",
                          "algorithmic_bytes_per_launch": my_pops * rec_bytes, "peak_source": peak_src,
                          "algorithmic_bytes_per_pop": rec_bytes, "agent_state_GBps": agent_gbs, "kernel_ms": float(run_ms)},
             "bucketing": {"rows": N, "ms": bucket_ms, "GBps": bucket_bytes / bucket_ms / 1e6, "frac": bucket_bytes / bucket_ms / 1e6 / hbm_peak,
