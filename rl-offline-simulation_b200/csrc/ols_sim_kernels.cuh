@@ -967,7 +967,12 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel
           } else {
             used_tie = true;
             const int pick = min(ncand - 1, (int)(v * (double)ncand));
-            for (int t = 0; t < pick; ++t) cand &= cand - 1;  // drop the `pick` lowest candidates
+            if (NA == 4) {  // drop the `pick` lowest candidates, branch-free for the 4-bit mask
+              const unsigned c1 = cand & (cand - 1), c2 = c1 & (c1 - 1), c3 = c2 & (c2 - 1);
+              cand = (pick == 0) ? cand : (pick == 1) ? c1 : (pick == 2) ? c2 : c3;
+            } else {
+              for (int t = 0; t < pick; ++t) cand &= cand - 1;
+            }
           }
         }
         a_star = __ffs(cand) - 1;
