@@ -216,14 +216,15 @@ def run_reference(args, wl, rank, world):
     }))
 
 
-def gather_stress_leg(ob, torch, dev, hbm_peak, launches=5, warm=3):
+def gather_stress_leg(ob, torch, dev, hbm_peak, launches=5, warm=3, hot=True):
     """Second half of the BASELINE metric ("PSRS gather HBM GB/s vs peak"): the rejection-heavy configuration
     (BASELINE.json configs[4], workload c5) is the streaming-gather regime.  Rank 0, one GPU, a few launches."""
     wl = WORKLOADS["c5"]
     N, nS, nA, R, T = wl["rows"], wl["states"], wl["actions"], wl["replicas"], wl["budget"]
     cols = ob.synth_columns(N, nS, behaviour_table(nS, nA, wl["delta"]), seed=0, device=dev)
     log = ob.BucketedLog(z=cols["z"], z_next=cols["z_next"], action=cols["action"], reward=cols["reward"],
-                         terminal=cols["terminal"], p_log=cols["p_log"], steps=cols["steps"], n_buckets=nS, z_offset=0, device=dev)
+                         terminal=cols["terminal"], p_log=cols["p_log"], steps=cols["steps"], n_buckets=nS, z_offset=0, device=dev,
+                         hot_records=hot)
     del cols
     sim = ob.BatchedPSRS(log, R, rng="philox", seed=4321, ring=True, ring_seed=7, lanes=wl["lanes"])
     pi = np.full((nS, nA), 1.0 / nA)
@@ -240,7 +241,9 @@ def gather_stress_leg(ob, torch, dev, hbm_peak, launches=5, warm=3):
             pops = float(sim.pops.sum())
     t = sum(ms) / len(ms) / 1e3
     gbs = pops * log.rec_bytes / t / 1e9
-    return {"workload": "c5: " + wl["desc"], "kernel": "run_kernel (fixed-policy evaluation, lanes=32 x 2 records)", "pops_per_s": pops / t,
+    return {"workload": "c5: " + wl["desc"],
+            "kernel": "run_kernel (fixed-policy evaluation, lanes=32 x %s)" % ("4 hot records of 8 bytes" if hot else "2 records"),
+            "bytes_read_per_rejected_pop": 8 if hot else log.rec_bytes, "pops_per_s": pops / t,
             "accepted_per_s": float(sim.accepted.sum()) / t, "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
             "kernel_ms": 1e3 * t, "launches": launches,
             "traffic": NCU_DRAM_BYTES_PER_ACCEPTED["c5"] * float(sim.accepted.sum()), "algorithmic_bytes_per_launch": pops * log.rec_bytes}
@@ -348,7 +351,8 @@ def main():
     # ---- setup (untimed): synthetic log generated on the device, bucketed once
     cols = ob.synth_columns(N, nS, pb, seed=0, device=dev)
     torch.cuda.synchronize()
-    use_hot = qlearn and nA <= 4 and not args.no_aos and not args.no_hot and args.workload == "c4"   # no gain when the state fits L2 (c2)
+    # learners: hot records need the AoS state and give nothing when the state fits L2 (c2); fixed-policy evaluation (c5): always
+    use_hot = nA <= 4 and not args.no_hot and ((qlearn and not args.no_aos and args.workload == "c4") or not qlearn)
     log = ob.BucketedLog(z=cols["z"], z_next=cols["z_next"], action=cols["action"], reward=cols["reward"],
                          terminal=cols["terminal"], p_log=cols["p_log"], steps=cols["steps"], n_buckets=nS, z_offset=0, device=dev,
                          keep_columns=True, hot_records=use_hot)
@@ -474,7 +478,7 @@ def main():
     if rank == 0 and args.workload == "c4" and not args.skip_stress:
         sim = Q = res = None        # release the c4 state (25 GB) before building the c5 log
         torch.cuda.empty_cache()
-        stress = gather_stress_leg(ob, torch, dev, hbm_peak)
+        stress = gather_stress_leg(ob, torch, dev, hbm_peak, hot=not args.no_hot)
         torch.cuda.empty_cache()
         next_rows = {"queue_evaluator": queue_evaluator_leg(ob, torch, dev, hbm_peak)}
     if rank == 0:

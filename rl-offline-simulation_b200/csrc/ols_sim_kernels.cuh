@@ -1325,6 +1325,18 @@ inline cudaError_t launch_run_rng(const ols_queues_t& q, const ols_replicas_t& r
     }                                                                                                                  \
     k<<<L.grid, kThreads, L.smem, L.stream>>>(q, r, c, L.plan, L.keys);                                                        \
   } while (0)
+  if constexpr (NV == 1 && AGENT == OLS_AGENT_FIXED_PI) {
+    // fixed-policy evaluation over hot records (the streaming-reject regime reads 8 instead of 32 bytes per pop)
+    if (q.hot != nullptr && r.rng_mode == OLS_RNG_PHILOX && c.reject_mode == OLS_REJECT_DEFAULT && (ppl == 2 || ppl == 4)) {
+      auto k = run_kernel<NV, AGENT, QT, RNGT_PHILOX, 4, false, 0, true>;
+      if (L.smem > 40 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
+        if (e != cudaSuccess) return e;
+      }
+      k<<<L.grid, kThreads, L.smem, L.stream>>>(q, r, c, L.plan, L.keys);
+      return cudaGetLastError();
+    }
+  }
   if (c.reject_mode == OLS_REJECT_ACCEPT_ALL) OLS_GO(RNGT_NONE, 1);
   else if (r.rng_mode == OLS_RNG_PCG64) OLS_GO(RNGT_PCG64, 1);
   else if (r.rng_mode == OLS_RNG_FEED) { if (ppl == 4) OLS_GO(RNGT_FEED, 4); else if (ppl == 2) OLS_GO(RNGT_FEED, 2); else OLS_GO(RNGT_FEED, 1); }

@@ -693,3 +693,33 @@ def test_hot_records_never_change_a_run(ob, agent, lanes, ring, seeded):
     assert torch.equal(da, db) and torch.equal(ta, tb) and torch.equal(a.status, b.status)
     assert torch.equal(a.Q, b.Q) and torch.equal(a.Gs, b.Gs) and torch.equal(a.lengths, b.lengths)
     assert int(a.accepted.sum()) > 0.5 * R * 400
+
+
+@pytest.mark.parametrize("lanes,ring,seeded,pi_dtype", [(32, True, None, np.float64), (8, False, 4, np.float32), (2, True, None, np.float64),
+                                                        (16, True, 7, np.float32)])
+def test_hot_records_never_change_an_evaluation(ob, lanes, ring, seeded, pi_dtype):
+    """Fixed-policy evaluation (evalMC_psrs) over hot records, incl. the near-deterministic behaviour policy of the
+    rejection-heavy configuration (long reject chains), float32 and float64 policies: identical rows, returns, lengths."""
+    import torch
+    nS, nA, N, R = 60, 4, 200000, 1500
+    rng = np.random.default_rng(33)
+    g = make_log(72, N, nS, nA, ep_len=12, p_dtype=np.float32)
+    d = 1e-2
+    pb = np.full((nS, nA), d / 3, dtype=np.float32)
+    pb[np.arange(nS), rng.integers(0, nA, nS)] = 1 - d
+    g["p_log"] = pb[g["z"]]
+    g["a"] = (rng.random(N)[:, None] > np.cumsum(pb[g["z"]], 1)).sum(1).clip(0, nA - 1)
+    pi = np.full((nS, nA), 0.25, dtype=pi_dtype)
+    pi[::7] = np.array([0.7, 0.1, 0.1, 0.1], dtype=pi_dtype)
+    outs = []
+    for hot in (False, True):
+        log = device_log(ob, g, n_buckets=nS, hot_records=hot).seeded(seeded)
+        sim = ob.BatchedPSRS(log, R, rng="philox", seed=8, ring=ring, ring_seed=5, lanes=lanes)
+        res = None
+        for budget in (25, 15):
+            res = sim.run_evalmc(nS, 40, pi=pi, gamma=0.95, max_steps=budget, trace_cap=64, outputs=res)
+        outs.append((res, sim.draws.clone()))
+    (a, da), (b, db) = outs
+    assert torch.equal(a.trace_row, b.trace_row) and torch.equal(a.accepted, b.accepted) and torch.equal(a.pops, b.pops)
+    assert torch.equal(da, db) and torch.equal(a.status, b.status) and torch.equal(a.Gs, b.Gs) and torch.equal(a.lengths, b.lengths)
+    assert int(a.accepted.sum()) > 0.5 * R * 40 and int(a.pops.sum()) > 20 * int(a.accepted.sum())
