@@ -260,18 +260,40 @@ def queue_evaluator_leg(ob, torch, dev, hbm_peak, steps=40, warm=5):
     del cols
     sim = ob.BatchedPSRS(log, R, rng="philox", seed=5, ring=True, ring_seed=11, lanes=1)
     acts = torch.randint(0, nA, (steps + warm, R), dtype=torch.int32, device=dev)
+    a_now = torch.empty(R, dtype=torch.int32, device=dev)
+    done = torch.zeros((), dtype=torch.int64, device=dev)
     sim.reset()
-    done = 0
+
+    def one():                     # one simulated step of every replica + restart of the finished episodes
+        out = sim.step_action(a_now)
+        done.add_((out["row"] >= 0).sum())
+        sim.reset(mask=out["terminal"])
+
+    # the loop is launch-bound (two small kernels per step): capture one step in a CUDA graph and replay it
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        a_now.copy_(acts[0])
+        one()                      # warm-up outside capture (lazy module loading)
+    torch.cuda.current_stream().wait_stream(side)
+    try:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            one()
+    except Exception:              # capture not possible here: run the step eagerly
+        graph = None
+        torch.cuda.synchronize()
     for i in range(steps + warm):
         if i == warm:
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            done = torch.zeros((), dtype=torch.int64, device=dev)
+            done.zero_()
             e0.record()
-        out = sim.step_action(acts[i])
-        if i >= warm:
-            done += (out["row"] >= 0).sum()
-        sim.reset(mask=out["terminal"])
+        a_now.copy_(acts[i])
+        if graph is not None:
+            graph.replay()
+        else:
+            one()
     e1.record()
     torch.cuda.synchronize()
     t = e0.elapsed_time(e1) / 1e3
@@ -280,7 +302,8 @@ def queue_evaluator_leg(ob, torch, dev, hbm_peak, steps=40, warm=5):
     return {"row": "QueueEvaluator.step over (z, a)-keyed queues (queue_evaluator.py:121-131), batched", "rows": N, "states": nS,
             "actions": nA, "replicas": R, "steps": steps, "value": n / t, "unit": "transitions/s", "launches": 2 * steps,
             "achieved": n * per / t / 1e9, "peak": hbm_peak, "roofline_unit": "GB/s", "frac": n * per / t / 1e9 / hbm_peak,
-            "algorithmic_bytes_per_transition": per, "note": "one launch per simulated step; random 32-byte record reads"}
+            "algorithmic_bytes_per_transition": per, "note": ("one CUDA-graph replay (step kernel + reset kernel + count) per simulated step" if graph is not None
+                     else "eager: one launch of each kernel per simulated step") + "; random 32-byte record reads"}
 
 
 # ------------------------------------------------------------------------------------------------- GPU arm
@@ -478,9 +501,15 @@ def main():
     if rank == 0 and args.workload == "c4" and not args.skip_stress:
         sim = Q = res = None        # release the c4 state (25 GB) before building the c5 log
         torch.cuda.empty_cache()
-        stress = gather_stress_leg(ob, torch, dev, hbm_peak, hot=not args.no_hot)
+        try:
+            stress = gather_stress_leg(ob, torch, dev, hbm_peak, hot=not args.no_hot)
+        except Exception as exc:   # a side leg must never take the headline line down
+            stress = {"error": repr(exc)}
         torch.cuda.empty_cache()
-        next_rows = {"queue_evaluator": queue_evaluator_leg(ob, torch, dev, hbm_peak)}
+        try:
+            next_rows = {"queue_evaluator": queue_evaluator_leg(ob, torch, dev, hbm_peak)}
+        except Exception as exc:
+            next_rows = {"queue_evaluator": {"error": repr(exc)}}
     if rank == 0:
         cpu = None
         if not args.skip_cpu and world == 1:
