@@ -42,7 +42,8 @@ WORKLOADS = {
 # DRAM bytes (read + write) per accepted transition of the fused run kernel, from the committed `ncu --set full`
 # captures (profiles/r01f_ncu_full_run_kernel_final_*.txt): dram__bytes_read.sum + dram__bytes_write.sum divided by the
 # accepted transitions of the captured launch.  Used to report `roofline.traffic` per launch.
-NCU_DRAM_BYTES_PER_ACCEPTED = {"c4": (17.565853e9 + 1.293527e9) / 3.75e7, "c5": (78.641898e9 + 1.658046e9) / 3.2e6}
+NCU_DRAM_BYTES_PER_ACCEPTED = {"c4": (17.565853e9 + 1.293527e9) / 3.75e7, "c5": (18.883526e9 + 0.301427e9) / 3.2e6,
+                               "c5_full_records": (78.641898e9 + 1.658046e9) / 3.2e6}
 EPS, ALPHA, GAMMA = 0.1, 0.1, 0.99
 EP_CAP = 512
 
@@ -246,7 +247,7 @@ def gather_stress_leg(ob, torch, dev, hbm_peak, launches=5, warm=3, hot=True):
             "bytes_read_per_rejected_pop": 8 if hot else log.rec_bytes, "pops_per_s": pops / t,
             "accepted_per_s": float(sim.accepted.sum()) / t, "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
             "kernel_ms": 1e3 * t, "launches": launches,
-            "traffic": NCU_DRAM_BYTES_PER_ACCEPTED["c5"] * float(sim.accepted.sum()), "algorithmic_bytes_per_launch": pops * log.rec_bytes}
+            "traffic": NCU_DRAM_BYTES_PER_ACCEPTED["c5" if hot else "c5_full_records"] * float(sim.accepted.sum()), "algorithmic_bytes_per_launch": pops * log.rec_bytes}
 
 
 def queue_evaluator_leg(ob, torch, dev, hbm_peak, steps=40, warm=5):
@@ -542,8 +543,9 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "run_kernel (fused PSRS step + agent update)", "achieved": gather_gbs, "peak": hbm_peak,
                          "unit": "GB/s", "frac": gather_gbs / hbm_peak,
                          "traffic": (NCU_DRAM_BYTES_PER_ACCEPTED[args.workload] * last_accepted
-                                     if args.workload in NCU_DRAM_BYTES_PER_ACCEPTED else None),
-                         "traffic_note": "DRAM read+write bytes per launch = ncu bytes per accepted transition (profiles/r01j_* for c4, r01f_* for c5) x accepted per launch",
+                                     if (args.workload in NCU_DRAM_BYTES_PER_ACCEPTED and use_hot and args.ppl == 0 and args.lanes is None)
+                                     else None),   # the captures are of the default configuration
+                         "traffic_note": "DRAM read+write bytes per launch = ncu bytes per accepted transition (profiles/r01j_*) x accepted per launch",
                          "algorithmic_bytes_per_launch": my_pops * rec_bytes, "peak_source": peak_src,
                          "algorithmic_bytes_per_pop": rec_bytes, "agent_state_GBps": agent_gbs, "kernel_ms": float(run_ms)},
             "bucketing": {"rows": N, "ms": bucket_ms, "GBps": bucket_bytes / bucket_ms / 1e6, "frac": bucket_bytes / bucket_ms / 1e6 / hbm_peak,
