@@ -167,7 +167,7 @@ class BucketedLog:
             self.init_z = init_z[: max(self.n_init, 1)]
             self.init_s = init_s[: max(self.n_init, 1)]
             self.seed = None
-            self.base = self
+            self._base = None           # a log-order log is its own base (no self-reference: the buffers must die by refcount)
             self._columns = dict(z=z_key, z_next=z_next, action=action, reward=reward, terminal=terminal, p_log=p,
                                  s=s, s_next=s_next, steps=steps) if keep_columns else None
             self._scratch = scratch if keep_columns else None
@@ -202,6 +202,11 @@ class BucketedLog:
         self._scratch = None
 
     # ------------------------------------------------------------------ views
+    @property
+    def base(self) -> "BucketedLog":
+        """The log-order queues this log was derived from (itself for a freshly bucketed log)."""
+        return self if self._base is None else self._base
+
     def queues_struct(self) -> abi.Queues:
         return abi.Queues(n_rows=self.n_rows, n_init=self.n_init, n_actions=self.n_actions, n_buckets=self.n_buckets,
                           z_offset=self.z_offset, rec_bytes=self.rec_bytes, offsets=_ptr(self.offsets),
@@ -235,7 +240,7 @@ class BucketedLog:
             src, dst = base.queues_struct(), out.queues_struct()
             abi.check(lib.ols_shuffle_queues(C.byref(src), C.byref(dst), C.c_uint64(int(seed)), _ptr(perm), _stream_ptr()))
         out.seed = int(seed)
-        out.base = base
+        out._base = base
         return out
 
     def queue_rows(self, z: int, a: Optional[int] = None) -> torch.Tensor:
