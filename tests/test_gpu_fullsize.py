@@ -1,0 +1,147 @@
+"""BASELINE.json's full sizes (C4: 1e8 transitions, 10k states, 4 actions, 125k replicas per GPU; C5: 1000 states,
+near-deterministic behaviour policy) checked through size-independent properties — the oracle cannot run here:
+the bucketing is a stable sorting permutation that packed every field of every row, hot records decode to the
+records, runs conserve their counters, are idempotent and invariant under replica sharding, and every accelerated
+layout (AoS state, hot records, time slices) reproduces the plain one bit for bit."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+N, NS, NA = 100_000_000, 10_000, 4
+
+
+@pytest.fixture(scope="module")
+def ob():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    if torch.cuda.get_device_properties(0).total_memory < 120 * 2 ** 30:
+        pytest.skip("full-size tests need a 180 GB B200")
+    import offsim4rl_b200 as ob
+    return ob
+
+
+def _behaviour(nS, nA, delta=None, seed=0):
+    rng = np.random.default_rng(seed)
+    if delta is None:
+        pb = np.maximum(rng.dirichlet(np.ones(nA), size=nS), 0.05)
+        return pb / pb.sum(1, keepdims=True)
+    pb = np.full((nS, nA), delta / (nA - 1))
+    pb[np.arange(nS), rng.integers(0, nA, nS)] = 1.0 - delta
+    return pb
+
+
+@pytest.fixture(scope="module")
+def c4(ob):
+    import torch
+    cols = ob.synth_columns(N, NS, _behaviour(NS, NA), seed=0, device=torch.device("cuda:0"))
+    log = ob.BucketedLog(z=cols["z"], z_next=cols["z_next"], action=cols["action"], reward=cols["reward"],
+                         terminal=cols["terminal"], p_log=cols["p_log"], steps=cols["steps"], n_buckets=NS, z_offset=0,
+                         hot_records=True)
+    return cols, log
+
+
+def test_c4_bucketing_is_a_stable_sort_that_packed_every_field(ob, c4):
+    import torch
+    cols, log = c4
+    off, order = log.offsets.long(), log.order.long()
+    assert int(off[0]) == 0 and int(off[-1]) == N and bool((off[1:] >= off[:-1]).all())
+    # a permutation of 0..N-1: exact sum and a multiplicative checksum
+    idx = torch.arange(N, device=order.device)
+    assert int(order.sum()) == N * (N - 1) // 2
+    assert int(((order * 2654435761) & 0xFFFFFFFF).sum()) == int(((idx * 2654435761) & 0xFFFFFFFF).sum())
+    zs = cols["z"].long()[order]
+    assert bool(((zs[1:] > zs[:-1]) | ((zs[1:] == zs[:-1]) & (order[1:] > order[:-1]))).all())      # sorted AND stable
+    assert torch.equal(torch.bincount(cols["z"].long(), minlength=NS), off[1:] - off[:-1])
+    del zs, idx
+    rec = log.records.view(torch.int32).view(-1, 8)[:N]
+    assert torch.equal(rec[:, 5], cols["z_next"][order])                                          # next state
+    assert torch.equal(rec[:, 4].view(torch.float32), cols["reward"][order])
+    assert torch.equal(rec[:, :4].view(torch.float32), cols["p_log"][order])
+    meta = rec[:, 7]
+    assert torch.equal(meta & 0xFF, cols["action"][order]) and torch.equal((meta >> 8) & 1, cols["terminal"][order].int())
+    # initial states: the rows with step 0, in log order
+    first = torch.nonzero(cols["steps"] == 0).flatten().int()
+    assert log.n_init == first.numel() and torch.equal(log.init_row[: log.n_init], first)
+
+
+def test_c4_hot_records_decode_to_the_records(ob, c4):
+    import torch
+    cols, log = c4
+    words = log.hot.view(torch.int32).view(-1, 2)[:N]
+    lo, hi = words[:, 0], words[:, 1]
+    rec = log.records.view(torch.int32).view(-1, 8)[:N]
+    action = ((lo >> 15) & 1) | (((lo >> 31) & 1) << 1)
+    assert torch.equal(action, rec[:, 7] & 0xFF)
+    assert bool((((hi >> 15) & 1) == 1).all())                       # every synthetic probability is in the half range
+    halves = torch.stack([lo & 0x7FFF, (lo >> 16) & 0x7FFF, hi & 0x7FFF, (hi >> 16) & 0x7FFF], 1).to(torch.int16).view(torch.float16)
+    p = rec[:, :4].view(torch.float32)
+    assert torch.equal(halves, p.to(torch.float16))                  # round-to-nearest-even images
+    assert float(((halves.float() - p).abs() / p).max()) <= 2.0 ** -11
+
+
+def _run(ob, log, R, id0, budget, **kw):
+    sim = ob.BatchedPSRS(log, R, rng="philox", seed=1234, ring=True, ring_seed=99, replica_id0=id0, lanes=2, **kw)
+    res = sim.run_qlearn(NS, 511, gamma=0.99, alpha=0.1, epsilon=0.1, max_steps=budget, ep_cap=512)
+    return sim, res
+
+
+def test_c4_run_conserves_is_idempotent_and_shards(ob, c4):
+    import torch
+    cols, log = c4
+    R, T = 125_000, 300
+    sim, res = _run(ob, log, R, 0, T, aos_state=True)
+    acc, pops = res.accepted.clone(), res.pops.clone()
+    from offsim4rl_b200 import _abi as abi
+    assert bool((acc == T).all()) and bool((res.status == abi.RUNNING).all())   # every replica spent its whole budget, still RUNNING
+    assert torch.equal(sim.draws, pops) and bool((pops >= acc).all())
+    # the lengths of the closed episodes plus the open episode's clock account for every accepted transition
+    nl = res.n_lengths.long()
+    closed = (res.lengths.long() * (torch.arange(512, device=nl.device)[None, :] < nl[:, None])).sum(1)
+    assert torch.equal(closed + sim.ep_t.long() * sim.ep_open.long(), acc.long())
+    assert bool(torch.isfinite(res.Gs).all())
+    gs_sum, len_sum = res.Gs.sum(1).clone(), res.lengths.sum(1).clone()
+    q_check = res.Q.sum((1, 2)).clone()
+    del sim, res
+    torch.cuda.empty_cache()
+    # idempotent, and independent of the accelerated layouts: separate cursor/Q arrays, 32-byte records, no time slices
+    plain = ob.BucketedLog.__new__(ob.BucketedLog)
+    plain.__dict__.update(log.__dict__)
+    plain.hot = None
+    sim2, res2 = _run(ob, plain, R, 0, T, aos_state=False, slices=0)
+    assert torch.equal(res2.accepted, acc) and torch.equal(res2.pops, pops)
+    assert torch.equal(res2.Gs.sum(1), gs_sum) and torch.equal(res2.lengths.sum(1), len_sum)
+    assert torch.equal(res2.Q.sum((1, 2)), q_check)
+    del sim2, res2
+    torch.cuda.empty_cache()
+    # sharding: two ranks' worth of replicas, keyed by global replica id
+    half = R // 2
+    parts = []
+    for id0 in (0, half):
+        s, r = _run(ob, log, half, id0, T, aos_state=True)
+        parts.append((r.pops.clone(), r.Gs.sum(1).clone()))
+        del s, r
+        torch.cuda.empty_cache()
+    assert torch.equal(torch.cat([p[0] for p in parts]), pops) and torch.equal(torch.cat([p[1] for p in parts]), gs_sum)
+
+
+def test_c5_evaluation_over_hot_records_at_full_size(ob):
+    import torch
+    nS, R, T = 1000, 32_000, 20
+    cols = ob.synth_columns(N, nS, _behaviour(nS, NA, delta=1e-3), seed=0, device=torch.device("cuda:0"))
+    pi = np.full((nS, NA), 0.25)
+    outs = []
+    for hot in (True, False):
+        log = ob.BucketedLog(z=cols["z"], z_next=cols["z_next"], action=cols["action"], reward=cols["reward"],
+                             terminal=cols["terminal"], p_log=cols["p_log"], steps=cols["steps"], n_buckets=nS, z_offset=0,
+                             hot_records=hot)
+        sim = ob.BatchedPSRS(log, R, rng="philox", seed=4321, ring=True, ring_seed=7, lanes=32)
+        res = sim.run_evalmc(nS, 511, pi, 0.99, max_steps=T, ep_cap=512, trace_cap=T)
+        outs.append((res.pops.clone(), res.accepted.clone(), res.trace_row.clone(), res.Gs.sum(1).clone()))
+        del sim, res, log
+        torch.cuda.empty_cache()
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    pops, acc = outs[0][0].double().sum(), outs[0][1].double().sum()
+    assert bool((outs[0][1] == T).all()) and 500 < float(pops / acc) < 1100          # one accept per ~750 pops (M = 750)
