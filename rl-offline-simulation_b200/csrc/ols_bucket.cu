@@ -228,8 +228,11 @@ __device__ __forceinline__ void load_row(const ols_log_t& log, int64_t i, RowDat
   d.meta = ols_pack_meta(__ldg(log.action + i), __ldg(log.terminal + i), tame);
 }
 
+#ifndef OLS_SCATTER_MINB
+#define OLS_SCATTER_MINB 1
+#endif
 template <int NV>
-__global__ void __launch_bounds__(kBucketThreads) scatter_pack_kernel(ols_log_t log, ols_queues_t q, int64_t tile_rows,
+__global__ void __launch_bounds__(kBucketThreads, OLS_SCATTER_MINB) scatter_pack_kernel(ols_log_t log, ols_queues_t q, int64_t tile_rows,
                                                                        const uint32_t* __restrict__ tile_hist) {
   extern __shared__ uint32_t s_next_slot[];   // [n_buckets] next free slot of every queue for this tile
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -254,11 +257,10 @@ __global__ void __launch_bounds__(kBucketThreads) scatter_pack_kernel(ols_log_t 
       const int64_t i = base + j * 32 + lane;
       key[j] = -1;
       if (i < hi) {
+        // the row's columns are fetched together with its key, not after it: one memory latency per round, not two
         const int b = __ldg(log.z + i) + q.z_offset;
-        if (b >= 0 && b < nB) {
-          key[j] = b;
-          load_row<NV>(log, i, row[j]);
-        }
+        load_row<NV>(log, i, row[j]);
+        key[j] = (b >= 0 && b < nB) ? b : -1;
       }
     }
     // lanes holding the same key, lowest lane = earliest row; invalid lanes form their own group
@@ -291,14 +293,23 @@ __global__ void __launch_bounds__(kBucketThreads) scatter_pack_kernel(ols_log_t 
         const uint32_t pos = first[j] + __popc(peers[j] & lt_mask);
         const int64_t i = base + j * 32 + lane;
         float4* dst = (float4*)((char*)q.records + (size_t)pos * q.rec_bytes);
-#pragma unroll
-        for (int v = 0; v < NV; ++v) dst[v] = row[j].p[v];
         float4 tail;
         tail.x = row[j].r;
         tail.y = __int_as_float(row[j].zn);
         tail.z = __int_as_float((int32_t)i);  // the row index: reading it along a queue gives the queue order
         tail.w = __uint_as_float(row[j].meta);
-        dst[NV] = tail;
+        if (NV == 1) {
+            // a 32-byte record is one sector: ONE 256-bit store, i.e. one full-sector write transaction instead of two
+            // half-sector ones (the scatter is bound by the number of isolated write transactions, not by bytes)
+            const float4 p0 = row[j].p[0];
+            asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "f"(p0.x), "f"(p0.y), "f"(p0.z), "f"(p0.w),
+                         "f"(tail.x), "f"(tail.y), "f"(tail.z), "f"(tail.w)
+                         : "memory");
+        } else {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) dst[v] = row[j].p[v];
+          dst[NV] = tail;
+        }
       }
     }
   }
