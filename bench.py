@@ -572,7 +572,13 @@ def main():
                                      else None),   # the captures are of the default configuration
                          "traffic_note": "DRAM read+write bytes per launch = ncu bytes per accepted transition (profiles/r01j_*) x accepted per launch",
                          "algorithmic_bytes_per_launch": my_pops * rec_bytes, "peak_source": peak_src,
-                         "algorithmic_bytes_per_pop": rec_bytes, "agent_state_GBps": agent_gbs, "kernel_ms": float(run_ms)},
+                         "algorithmic_bytes_per_pop": rec_bytes, "agent_state_GBps": agent_gbs, "kernel_ms": float(run_ms),
+                         "random_access": ({"dram_transactions_per_s": (NCU_DRAM_BYTES_PER_ACCEPTED["c4"] / 128.0) * last_accepted / run_s,
+                                            "ceiling_per_s": 3.6e10,
+                                            "note": "c4 is bound by isolated DRAM transactions (whole 128-byte lines per random sector), "
+                                                    "not by bytes: ncu traffic / 128 B per launch against the 3.6e10/s that "
+                                                    "scratch/randbw.cu sustains on this box (DESIGN.md 4.3)"}
+                                           if (args.workload == "c4" and use_hot and args.ppl == 0 and args.lanes is None) else None)},
             "bucketing": {"rows": N, "ms": bucket_ms, "GBps": bucket_bytes / bucket_ms / 1e6, "frac": bucket_bytes / bucket_ms / 1e6 / hbm_peak,
                           "note": "ols_bucket + ols_init_queue kernels; bytes = z twice + order + log columns + packed record per row"},
             "step_breakdown_ms": {k: sum(a.elapsed_time(b) for a, b in v) / max(1, len(v)) for k, v in k_ev.items()},
