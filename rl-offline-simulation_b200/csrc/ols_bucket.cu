@@ -438,19 +438,25 @@ __global__ void __launch_bounds__(kInitThreads) init_write_kernel(ols_log_t log,
 // ---------------------------------------------------------------------------------------- seeded shuffle
 // np.random.default_rng(seed).shuffle(x) on a length-n list: for i = n-1 .. 1: j = interval(i);
 // swap(x[i], x[j]); interval() is NumPy's masked rejection on buffered 32-bit halves of PCG64 output
-// (64-bit draws when i > 2^32-1, which cannot occur with int32 row indices).  One thread replays one
-// queue: the chain is inherently sequential (every draw count depends on the rejections before it).
+// (64-bit draws when i > 2^32-1, which cannot occur with int32 row indices).  The chain of DRAWS is inherently
+// sequential (every draw count depends on the rejections before it), the SWAPS are not: one warp replays one queue,
+// lane 0 draws the partners of the next 32 steps (registers only), then the 32 swaps run as one parallel round of
+// loads and stores when they touch pairwise distinct slots (the rule for long queues), else lane 0 applies them in order.
 // perm[] holds absolute slot indices, pre-filled with iota; segment `seg` covers [lo, lo+len).
 __global__ void iota_kernel(int32_t* __restrict__ perm, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     perm[i] = (int32_t)i;
 }
 
-__global__ void __launch_bounds__(128) shuffle_perm_kernel(const int32_t* __restrict__ offsets, int n_buckets,
-                                                            int64_t n_rows, int64_t n_init, uint64_t seed,
-                                                            int32_t* __restrict__ perm) {
-  const int seg = blockIdx.x * blockDim.x + threadIdx.x;
-  if (seg > n_buckets) return;
+constexpr int kShuffleWarps = 4;
+
+__global__ void __launch_bounds__(32 * kShuffleWarps) shuffle_perm_kernel(const int32_t* __restrict__ offsets, int n_buckets,
+                                                                          int64_t n_rows, int64_t n_init, uint64_t seed,
+                                                                          int32_t* __restrict__ perm) {
+  __shared__ uint32_t s_j[kShuffleWarps][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int seg = blockIdx.x * kShuffleWarps + warp;
+  if (seg > n_buckets) return;  // warp-uniform
   int64_t lo, len;
   if (seg < n_buckets) {
     lo = offsets[seg];
@@ -461,35 +467,66 @@ __global__ void __launch_bounds__(128) shuffle_perm_kernel(const int32_t* __rest
   }
   if (len < 2) return;
   ols_u128 state, inc;
-  ols_pcg64_seed(seed, &state, &inc);
+  ols_pcg64_seed(seed, &state, &inc);  // every lane seeds; only lane 0 advances
   bool has32 = false;
   uint32_t buffered = 0;
   int32_t* x = perm + lo;
-  for (uint32_t i = (uint32_t)len - 1; i >= 1; --i) {
-    uint32_t mask = i;
-    mask |= mask >> 1;
-    mask |= mask >> 2;
-    mask |= mask >> 4;
-    mask |= mask >> 8;
-    mask |= mask >> 16;
-    uint32_t j;
-    do {
-      uint32_t v;
-      if (has32) {
-        v = buffered;
-        has32 = false;
-      } else {
-        state = ols_pcg_step(state, inc);
-        uint64_t o = ols_pcg_output(state);
-        v = (uint32_t)o;
-        buffered = (uint32_t)(o >> 32);
-        has32 = true;
+  uint32_t* jbuf = s_j[warp];
+  uint32_t i = (uint32_t)len - 1;  // steps i, i-1, ..., 1
+  while (i >= 1) {
+    const uint32_t W = i < 32u ? i : 32u;  // this round: steps i - k, k = 0 .. W-1
+    if (lane == 0) {
+      for (uint32_t k = 0; k < W; ++k) {
+        const uint32_t ii = i - k;
+        uint32_t mask = ii;
+        mask |= mask >> 1;
+        mask |= mask >> 2;
+        mask |= mask >> 4;
+        mask |= mask >> 8;
+        mask |= mask >> 16;
+        uint32_t j;
+        do {
+          uint32_t v;
+          if (has32) {
+            v = buffered;
+            has32 = false;
+          } else {
+            state = ols_pcg_step(state, inc);
+            const uint64_t o = ols_pcg_output(state);
+            v = (uint32_t)o;
+            buffered = (uint32_t)(o >> 32);
+            has32 = true;
+          }
+          j = v & mask;
+        } while (j > ii);
+        jbuf[k] = j;
       }
-      j = v & mask;
-    } while (j > i);
-    int32_t a = x[i], b = x[j];
-    x[i] = b;
-    x[j] = a;
+    }
+    __syncwarp();
+    const bool mine = (uint32_t)lane < W;
+    const uint32_t my_i = i - (uint32_t)lane;
+    const uint32_t my_j = mine ? jbuf[lane] : 0xffffffffu - (uint32_t)lane;  // idle lanes: distinct dummies
+    const bool self = mine && my_j == my_i;  // swap with itself
+    // independent iff every partner lies below the round's own slots (i-W, i] and no two partners coincide
+    const bool below = !mine || self || my_j + W <= i;
+    const unsigned same = __match_any_sync(kFull, self ? 0xffffff00u - (uint32_t)lane : my_j);
+    const bool alone = (same == (1u << lane));
+    if (__all_sync(kFull, below && alone)) {
+      if (mine && !self) {
+        const int32_t a = x[my_i], b = x[my_j];
+        x[my_i] = b;
+        x[my_j] = a;
+      }
+    } else if (lane == 0) {
+      for (uint32_t k = 0; k < W; ++k) {
+        const uint32_t ii = i - k, j = jbuf[k];
+        const int32_t a = x[ii], b = x[j];
+        x[ii] = b;
+        x[j] = a;
+      }
+    }
+    __syncwarp();  // the round's stores precede the next round's loads; jbuf is free again
+    i -= W;
   }
 }
 
@@ -648,7 +685,7 @@ extern "C" int ols_shuffle_queues(const ols_queues_t* src, const ols_queues_t* d
   if (blocks > OLS_SM_COUNT * 8) blocks = OLS_SM_COUNT * 8;
   iota_kernel<<<blocks, 256, 0, stream>>>(perm_scratch, total);
   OLS_LAUNCH_CHECK();
-  shuffle_perm_kernel<<<ols_div_up(src->n_buckets + 1, 128), 128, 0, stream>>>(src->offsets, src->n_buckets, src->n_rows,
+  shuffle_perm_kernel<<<ols_div_up(src->n_buckets + 1, kShuffleWarps), 32 * kShuffleWarps, 0, stream>>>(src->offsets, src->n_buckets, src->n_rows,
                                                                               src->n_init, seed, perm_scratch);
   OLS_LAUNCH_CHECK();
   gather_queues_kernel<<<blocks, 256, 0, stream>>>(*src, *dst, perm_scratch);

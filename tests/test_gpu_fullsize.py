@@ -145,3 +145,40 @@ def test_c5_evaluation_over_hot_records_at_full_size(ob):
         assert torch.equal(a, b)
     pops, acc = outs[0][0].double().sum(), outs[0][1].double().sum()
     assert bool((outs[0][1] == T).all()) and 500 < float(pops / acc) < 1100          # one accept per ~750 pops (M = 750)
+
+
+@pytest.mark.parametrize("seed", [0, 98052])
+def test_c4_seeded_orders_are_numpy_shuffles(ob, c4, seed):
+    """reset_sampler(seed) at full size: the initial-state list (2e6 entries) and the queues are exactly what
+    np.random.default_rng(seed).shuffle makes of the log-order lists (psrs.py:23,29-30)."""
+    cols, log = c4
+    s = log.seeded(seed)
+    init = log.init_row[: log.n_init].cpu().numpy().copy()
+    np.random.default_rng(seed).shuffle(init)
+    assert np.array_equal(s.init_row[: s.n_init].cpu().numpy(), init)
+    off = log.offsets.cpu().numpy()
+    base_order, new_order = log.order, s.order
+    for b in (0, 1, 4999, NS - 1):
+        q = base_order[off[b]:off[b + 1]].cpu().numpy().copy()
+        np.random.default_rng(seed).shuffle(q)
+        assert np.array_equal(new_order[off[b]:off[b + 1]].cpu().numpy(), q)
+    # hot records follow their records
+    rec = s.records.view(s.records.dtype).view(-1, 8)
+    import torch
+    words = s.hot.view(torch.int32).view(-1, 2)[:N]
+    assert torch.equal(((words[:, 0] >> 15) & 1) | (((words[:, 0] >> 31) & 1) << 1), s.records.view(torch.int32).view(-1, 8)[:N, 7] & 0xFF)
+
+
+def test_long_queues_seeded_order_is_numpy_shuffle(ob):
+    """A few very long queues (2.5e6 records each): the regime where the swap rounds of the shuffle run in parallel."""
+    import torch
+    n, nS = 10_000_000, 4
+    cols = ob.synth_columns(n, nS, _behaviour(nS, NA), seed=1, device=torch.device("cuda:0"))
+    log = ob.BucketedLog(z=cols["z"], z_next=cols["z_next"], action=cols["action"], reward=cols["reward"],
+                         terminal=cols["terminal"], p_log=cols["p_log"], steps=cols["steps"], n_buckets=nS, z_offset=0)
+    s = log.seeded(7)
+    off = log.offsets.cpu().numpy()
+    for b in range(nS):
+        q = log.order[off[b]:off[b + 1]].cpu().numpy().copy()
+        np.random.default_rng(7).shuffle(q)
+        assert np.array_equal(s.order[off[b]:off[b + 1]].cpu().numpy(), q)
