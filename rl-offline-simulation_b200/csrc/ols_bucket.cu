@@ -438,10 +438,14 @@ __global__ void __launch_bounds__(kInitThreads) init_write_kernel(ols_log_t log,
 // ---------------------------------------------------------------------------------------- seeded shuffle
 // np.random.default_rng(seed).shuffle(x) on a length-n list: for i = n-1 .. 1: j = interval(i);
 // swap(x[i], x[j]); interval() is NumPy's masked rejection on buffered 32-bit halves of PCG64 output
-// (64-bit draws when i > 2^32-1, which cannot occur with int32 row indices).  The chain of DRAWS is inherently
-// sequential (every draw count depends on the rejections before it), the SWAPS are not: one warp replays one queue,
-// lane 0 draws the partners of the next 32 steps (registers only), then the 32 swaps run as one parallel round of
-// loads and stores when they touch pairwise distinct slots (the rule for long queues), else lane 0 applies them in order.
+// (64-bit draws when i > 2^32-1, which cannot occur with int32 row indices).  One warp replays one queue, 32 steps
+// per round:
+//  * draws: PCG64 is an LCG, so lane l jumps straight to output n0 + l (state = A_l * base + C_l, constants built once):
+//    a round has the next 64 raw 32-bit draws in registers.  Which draw serves which step depends on the rejections
+//    before it; that triangular system (slot t needs the accept count of slots < t) is solved by ballot/popc
+//    fixed-point iteration — exact after at most as many passes as there are slots, two or three in practice;
+//  * swaps: the round's swaps run as one parallel round of loads and stores when they touch pairwise distinct slots
+//    (the rule for long queues), else lane 0 applies them in order.
 // perm[] holds absolute slot indices, pre-filled with iota; segment `seg` covers [lo, lo+len).
 __global__ void iota_kernel(int32_t* __restrict__ perm, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -466,67 +470,98 @@ __global__ void __launch_bounds__(32 * kShuffleWarps) shuffle_perm_kernel(const 
     len = n_init;
   }
   if (len < 2) return;
-  ols_u128 state, inc;
-  ols_pcg64_seed(seed, &state, &inc);  // every lane seeds; only lane 0 advances
-  bool has32 = false;
-  uint32_t buffered = 0;
+  ols_u128 base, inc;  // base = generator state before output n0 (identical in every lane)
+  ols_pcg64_seed(seed, &base, &inc);
+  // lane constants: state before output n0 + lane + 1, i.e. after lane + 1 steps = A * base + C
+  const ols_u128 mult = {OLS_PCG_MULT_HI, OLS_PCG_MULT_LO};
+  ols_u128 A = mult, Cc = inc;
+  for (int k = 0; k < lane; ++k) {
+    Cc = ols_add128(ols_mul128(Cc, mult), inc);
+    A = ols_mul128(A, mult);
+  }
+  const unsigned lt = (1u << lane) - 1u;
+  uint64_t n0 = 0;    // outputs fully consumed so far
+  bool half = false;  // the low half of output n0 is consumed as well
   int32_t* x = perm + lo;
   uint32_t* jbuf = s_j[warp];
   uint32_t i = (uint32_t)len - 1;  // steps i, i-1, ..., 1
   while (i >= 1) {
-    const uint32_t W = i < 32u ? i : 32u;  // this round: steps i - k, k = 0 .. W-1
-    if (lane == 0) {
-      for (uint32_t k = 0; k < W; ++k) {
-        const uint32_t ii = i - k;
-        uint32_t mask = ii;
-        mask |= mask >> 1;
-        mask |= mask >> 2;
-        mask |= mask >> 4;
-        mask |= mask >> 8;
-        mask |= mask >> 16;
-        uint32_t j;
-        do {
-          uint32_t v;
-          if (has32) {
-            v = buffered;
-            has32 = false;
-          } else {
-            state = ols_pcg_step(state, inc);
-            const uint64_t o = ols_pcg_output(state);
-            v = (uint32_t)o;
-            buffered = (uint32_t)(o >> 32);
-            has32 = true;
-          }
-          j = v & mask;
-        } while (j > ii);
-        jbuf[k] = j;
+    const uint32_t W = i < 32u ? i : 32u;  // at most this many steps in the round: i - k, k = 0 .. W-1
+    // ---- the next 64 raw draws: slot 2l = low half, slot 2l+1 = high half of output n0 + l
+    const ols_u128 st = ols_add128(ols_mul128(base, A), Cc);
+    const uint64_t out = ols_pcg_output(st);
+    const uint32_t v_lo = (uint32_t)out, v_hi = (uint32_t)(out >> 32);
+    const bool ok_lo = !(lane == 0 && half);
+    // ---- which draw serves which step: slot t is accepted iff (v & mask(i_t)) <= i_t with i_t = i - #accepted before t
+    unsigned b_lo = 0, b_hi = 0;
+    uint32_t c_lo = 0, c_hi = 0, r_lo = 0, r_hi = 0;
+    for (;;) {
+      c_lo = (uint32_t)(__popc(b_lo & lt) + __popc(b_hi & lt));
+      bool a_lo = false;
+      if (ok_lo && c_lo < W) {
+        const uint32_t it = i - c_lo;
+        r_lo = v_lo & (0xffffffffu >> __clz(it));
+        a_lo = r_lo <= it;
       }
+      c_hi = c_lo + (a_lo ? 1u : 0u);
+      bool a_hi = false;
+      if (c_hi < W) {
+        const uint32_t it = i - c_hi;
+        r_hi = v_hi & (0xffffffffu >> __clz(it));
+        a_hi = r_hi <= it;
+      }
+      const unsigned n_lo = __ballot_sync(kFull, a_lo), n_hi = __ballot_sync(kFull, a_hi);
+      const bool same = (n_lo == b_lo) && (n_hi == b_hi);
+      b_lo = n_lo;
+      b_hi = n_hi;
+      if (same) break;
     }
+    const uint32_t T = (uint32_t)(__popc(b_lo) + __popc(b_hi));  // steps served by this batch of draws (<= W)
+    if ((b_lo >> lane) & 1u) jbuf[c_lo] = r_lo;
+    if ((b_hi >> lane) & 1u) jbuf[c_hi] = r_hi;
+    // raw draws consumed: through the last accepted one when the round is complete, all 64 otherwise
+    uint32_t used = 64;
+    if (T == W) {
+      const unsigned any = b_lo | b_hi;
+      const int last = 31 - __clz(any);
+      used = 2u * (uint32_t)last + (((b_hi >> last) & 1u) ? 2u : 1u);
+    }
+    const uint32_t adv = used >> 1;  // whole outputs consumed; an odd count leaves the low half of the next one used
+    const uint64_t st_hi = __shfl_sync(kFull, st.hi, adv > 0 ? (int)adv - 1 : 0);
+    const uint64_t st_lo = __shfl_sync(kFull, st.lo, adv > 0 ? (int)adv - 1 : 0);
+    if (adv > 0) {
+      base.hi = st_hi;
+      base.lo = st_lo;
+    }
+    n0 += adv;
+    half = (used & 1u) != 0u;
     __syncwarp();
-    const bool mine = (uint32_t)lane < W;
-    const uint32_t my_i = i - (uint32_t)lane;
-    const uint32_t my_j = mine ? jbuf[lane] : 0xffffffffu - (uint32_t)lane;  // idle lanes: distinct dummies
-    const bool self = mine && my_j == my_i;  // swap with itself
-    // independent iff every partner lies below the round's own slots (i-W, i] and no two partners coincide
-    const bool below = !mine || self || my_j + W <= i;
-    const unsigned same = __match_any_sync(kFull, self ? 0xffffff00u - (uint32_t)lane : my_j);
-    const bool alone = (same == (1u << lane));
-    if (__all_sync(kFull, below && alone)) {
-      if (mine && !self) {
-        const int32_t a = x[my_i], b = x[my_j];
-        x[my_i] = b;
-        x[my_j] = a;
+    if (T > 0) {
+      const bool mine = (uint32_t)lane < T;
+      const uint32_t my_i = i - (uint32_t)lane;
+      const uint32_t my_j = mine ? jbuf[lane] : 0xffffffffu - (uint32_t)lane;  // idle lanes: distinct dummies
+      const bool self = mine && my_j == my_i;  // swap with itself
+      // independent iff every partner lies below the round's own slots (i-T, i] and no two partners coincide
+      const bool below = !mine || self || my_j + T <= i;
+      const unsigned peers = __match_any_sync(kFull, self ? 0xffffff00u - (uint32_t)lane : my_j);
+      const bool alone = (peers == (1u << lane));
+      if (__all_sync(kFull, below && alone)) {
+        if (mine && !self) {
+          const int32_t a = x[my_i], b = x[my_j];
+          x[my_i] = b;
+          x[my_j] = a;
+        }
+      } else if (lane == 0) {
+        for (uint32_t k = 0; k < T; ++k) {
+          const uint32_t ii = i - k, j = jbuf[k];
+          const int32_t a = x[ii], b = x[j];
+          x[ii] = b;
+          x[j] = a;
+        }
       }
-    } else if (lane == 0) {
-      for (uint32_t k = 0; k < W; ++k) {
-        const uint32_t ii = i - k, j = jbuf[k];
-        const int32_t a = x[ii], b = x[j];
-        x[ii] = b;
-        x[j] = a;
-      }
+      __syncwarp();  // the round's stores precede the next round's loads; jbuf is free again
+      i -= T;
     }
-    __syncwarp();  // the round's stores precede the next round's loads; jbuf is free again
-    i -= W;
   }
 }
 
