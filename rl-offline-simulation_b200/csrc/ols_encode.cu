@@ -79,28 +79,38 @@ __global__ void __launch_bounds__(kThreads) encode_box_f64_kernel(const double2*
 }
 
 // ---------------------------------------------------------------------------------------- latent-state MLP
-// One row per thread.  W1/b1/W2/b2 are staged once per CTA in shared memory (read as broadcasts);
-// the hidden vector lives in shared memory as h[j][thread] (bank = thread, conflict-free).
-// Arithmetic is a fixed-order float32 FMA chain (bias first, inputs ascending) so the ids are a pure
-// function of the inputs, and argmax keeps the FIRST maximum like torch.max / np.argmax.
+// One row per thread.  The weights are staged once per CTA in shared memory; the hidden vector lives in shared memory
+// as h[j][thread] (bank = thread, conflict-free).  The output layer is evaluated EIGHT latent states at a time: W2 is
+// staged transposed and padded, sW2t[j][k], so the eight weights of one hidden unit arrive as two 128-bit broadcast
+// loads and feed eight independent FMA chains per h[j] load — 3 shared-memory instructions per 8 FMAs where the
+// one-output-at-a-time loop issued 16 (it was shared-memory-bound at 11 % of the FP32 FMA rate).
+// Arithmetic per output is unchanged: a fixed-order float32 FMA chain (bias first, inputs ascending), so the ids are a
+// pure function of the inputs, and argmax keeps the FIRST maximum like torch.max / np.argmax.
 constexpr int kMlpThreads = 128;
+constexpr int kMlpKB = 8;  // latent states per block of the output layer
+
+__host__ __device__ inline int mlp_padded_latent(int n_latent) { return (n_latent + kMlpKB - 1) / kMlpKB * kMlpKB; }
 
 __global__ void __launch_bounds__(kMlpThreads) encode_mlp_kernel(const float* __restrict__ obs, int64_t n, int d_obs,
                                                                   const float* __restrict__ W1, const float* __restrict__ b1,
                                                                   int hidden, const float* __restrict__ W2,
                                                                   const float* __restrict__ b2, int n_latent, float slope,
                                                                   int32_t* __restrict__ ids) {
-  extern __shared__ float smem[];
-  float* sW1 = smem;                       // [hidden][d_obs]
+  extern __shared__ __align__(16) float smem[];
+  const int KP = mlp_padded_latent(n_latent);
+  float* sW2t = smem;                      // [hidden][KP], 16-byte aligned rows
+  float* sb2 = sW2t + hidden * KP;         // [KP]
+  float* sW1 = sb2 + KP;                   // [hidden][d_obs]
   float* sb1 = sW1 + hidden * d_obs;       // [hidden]
-  float* sW2 = sb1 + hidden;               // [n_latent][hidden]
-  float* sb2 = sW2 + n_latent * hidden;    // [n_latent]
-  float* sx = sb2 + n_latent;              // [d_obs][threads]
+  float* sx = sb1 + hidden;                // [d_obs][threads]
   float* sh = sx + d_obs * kMlpThreads;    // [hidden][threads]
   for (int i = threadIdx.x; i < hidden * d_obs; i += blockDim.x) sW1[i] = W1[i];
   for (int i = threadIdx.x; i < hidden; i += blockDim.x) sb1[i] = b1[i];
-  for (int i = threadIdx.x; i < n_latent * hidden; i += blockDim.x) sW2[i] = W2[i];
-  for (int i = threadIdx.x; i < n_latent; i += blockDim.x) sb2[i] = b2[i];
+  for (int i = threadIdx.x; i < hidden * KP; i += blockDim.x) {
+    const int j = i / KP, k = i % KP;
+    sW2t[i] = (k < n_latent) ? W2[k * hidden + j] : 0.0f;
+  }
+  for (int i = threadIdx.x; i < KP; i += blockDim.x) sb2[i] = (i < n_latent) ? b2[i] : 0.0f;
   __syncthreads();
   const int t = threadIdx.x;
   for (int64_t base = blockIdx.x * (int64_t)kMlpThreads; base < n; base += (int64_t)gridDim.x * kMlpThreads) {
@@ -120,13 +130,32 @@ __global__ void __launch_bounds__(kMlpThreads) encode_mlp_kernel(const float* __
       }
       int best = 0;
       float best_v = 0.0f;
-      for (int k = 0; k < n_latent; ++k) {
-        float acc = sb2[k];
-        const float* w = sW2 + k * hidden;
-        for (int j = 0; j < hidden; ++j) acc = __fmaf_rn(sh[j * kMlpThreads + t], w[j], acc);
-        if (k == 0 || acc > best_v) {  // strict >: first maximum wins
-          best_v = acc;
-          best = k;
+      for (int kb = 0; kb < KP; kb += kMlpKB) {
+        float acc[kMlpKB];
+        const float4 ba = *(const float4*)(sb2 + kb), bb = *(const float4*)(sb2 + kb + 4);
+        acc[0] = ba.x; acc[1] = ba.y; acc[2] = ba.z; acc[3] = ba.w;
+        acc[4] = bb.x; acc[5] = bb.y; acc[6] = bb.z; acc[7] = bb.w;
+        const float* w = sW2t + kb;
+#pragma unroll 4
+        for (int j = 0; j < hidden; ++j) {
+          const float h = sh[j * kMlpThreads + t];
+          const float4 wa = *(const float4*)(w + j * KP), wb = *(const float4*)(w + j * KP + 4);
+          acc[0] = __fmaf_rn(h, wa.x, acc[0]);
+          acc[1] = __fmaf_rn(h, wa.y, acc[1]);
+          acc[2] = __fmaf_rn(h, wa.z, acc[2]);
+          acc[3] = __fmaf_rn(h, wa.w, acc[3]);
+          acc[4] = __fmaf_rn(h, wb.x, acc[4]);
+          acc[5] = __fmaf_rn(h, wb.y, acc[5]);
+          acc[6] = __fmaf_rn(h, wb.z, acc[6]);
+          acc[7] = __fmaf_rn(h, wb.w, acc[7]);
+        }
+#pragma unroll
+        for (int u = 0; u < kMlpKB; ++u) {
+          const int k = kb + u;
+          if (k < n_latent && (k == 0 || acc[u] > best_v)) {  // strict >: first maximum wins
+            best_v = acc[u];
+            best = k;
+          }
         }
       }
       ids[i] = best;
@@ -171,7 +200,8 @@ extern "C" int ols_encode_mlp(const float* obs, int64_t n, int32_t d_obs, const 
   OLS_REQUIRE(n >= 0 && d_obs >= 1 && hidden >= 1 && n_latent >= 1, OLS_ERR_INVALID, "ols_encode_mlp: bad sizes");
   if (n == 0) return OLS_OK;
   OLS_REQUIRE(obs && W1 && b1 && W2 && b2 && ids, OLS_ERR_INVALID, "ols_encode_mlp: null pointer");
-  size_t smem = sizeof(float) * ((size_t)hidden * d_obs + hidden + (size_t)n_latent * hidden + n_latent +
+  const int KP = mlp_padded_latent(n_latent);
+  size_t smem = sizeof(float) * ((size_t)hidden * d_obs + hidden + (size_t)KP * hidden + KP +
                                  (size_t)(d_obs + hidden) * kMlpThreads);
   OLS_REQUIRE(smem <= 227 * 1024, OLS_ERR_UNSUPPORTED,
               "ols_encode_mlp: weights + activations need %zu B of shared memory (> 227 KB)", smem);
