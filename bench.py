@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # BASELINE.json configs[3] sharded weak: 100M-transition / 10k-state / 4-action log, 1M replicas over 8 GPUs
-    "c4": dict(rows=100_000_000, states=10_000, actions=4, replicas=125_000, budget=10_000, delta=None, lanes=2,
+    "c4": dict(rows=100_000_000, states=10_000, actions=4, replicas=125_000, budget=10_000, delta=None, lanes=1,
                desc="synthetic 100M-transition log, 10k states, 4 actions, eps-greedy Q-learning, 125k replicas/GPU (1M over 8)"),
     # configs[4]: rejection-heavy stress, near-deterministic behaviour vs uniform target, 256k replicas over 8 GPUs
     "c5": dict(rows=100_000_000, states=1_000, actions=4, replicas=32_000, budget=100, delta=1e-3, lanes=32,

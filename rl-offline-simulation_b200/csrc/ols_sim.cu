@@ -212,7 +212,9 @@ extern "C" int ols_run(const ols_queues_t* q, const ols_replicas_t* r, const ols
   int slices = c->slices > 1 ? c->slices : 1;
   if (c->slices == -1 && c->sched && c->max_steps > 0 && L.plan.slot_bytes == 0) {
     // resident CTAs per wave under the kernels' launch bounds; slice when the last wave would run part-empty
-    const int resident = OLS_SM_COUNT * (q->n_actions <= 4 ? OLS_MINB : 2);
+    // (the one-lane hot-record learner is built for OLS_MINB_G1 CTAs per SM, see run_kernel's launch bounds)
+    const bool g1_hot = c->lanes == 1 && c->state_aos && q->hot && r->rng_mode == OLS_RNG_PHILOX;
+    const int resident = OLS_SM_COUNT * (q->n_actions <= 4 ? (g1_hot ? OLS_MINB_G1 : OLS_MINB) : 2);
     const int full = n_blocks / resident, rest = n_blocks % resident;
     if (full >= 1 && rest != 0 && rest < resident * 9 / 10) {
       int64_t k = c->max_steps / 512;  // at least 512 accepted transitions per slice

@@ -36,6 +36,11 @@ constexpr int kThreads = 256;
 #ifndef OLS_MINB
 #define OLS_MINB 4
 #endif
+// one lane per replica (GT == 1): no register is held redundantly, so three CTAs per SM (85 registers, no spills) still
+// keep 768 replicas per SM in flight
+#ifndef OLS_MINB_G1
+#define OLS_MINB_G1 3
+#endif
 
 // RNGT_NONE: the accept-all baselines (trivial_baselines.py:8-10,22-24) draw no uniform at all
 enum { RNGT_FEED = OLS_RNG_FEED, RNGT_PCG64 = OLS_RNG_PCG64, RNGT_PHILOX = OLS_RNG_PHILOX, RNGT_NONE = 3 };
@@ -555,10 +560,14 @@ __device__ __forceinline__ int pop_round_hot(const ols_queues_t& q, int G, int s
     int mine = PPL;
 #pragma unroll
     for (int i = PPL - 1; i >= 0; --i) mine = acc[i] ? i : mine;
-    const unsigned g_any = (__ballot_sync(kFull, mine < PPL) >> gbase) & gmask;
-    const int w = g_any ? __ffs(g_any) - 1 : 0;
-    const int wi = __shfl_sync(kFull, mine, gbase + w);
-    if (g_any) first_acc = w * PPL + wi - align;
+    if (G == 1) {  // one lane per replica (a compile-time fact in the production kernel): nothing to vote on
+      if (mine < PPL) first_acc = mine - align;
+    } else {
+      const unsigned g_any = (__ballot_sync(kFull, mine < PPL) >> gbase) & gmask;
+      const int w = g_any ? __ffs(g_any) - 1 : 0;
+      const int wi = __shfl_sync(kFull, mine, gbase + w);
+      if (g_any) first_acc = w * PPL + wi - align;
+    }
   }
   int consumed = 0;
   bool took = false;
@@ -755,7 +764,7 @@ struct EpsGreedySource {
 // against its own queue; a group whose round accepted a record runs the learner update and prepares its next
 // step in the same iteration (predicated), so no group waits for the longest reject chain in its warp.
 template <int NV, int AGENT, typename QT, int RNG, int PPL, bool AOS = false, int GT = 0, bool HOT = false>
-__global__ void __launch_bounds__(kThreads, (NV == 1 ? OLS_MINB : 2)) run_kernel(ols_queues_t q, ols_replicas_t R, ols_run_t cfg,
+__global__ void __launch_bounds__(kThreads, (NV == 1 ? (GT == 1 ? OLS_MINB_G1 : OLS_MINB) : 2)) run_kernel(ols_queues_t q, ols_replicas_t R, ols_run_t cfg,
                                                                                   StagePlan plan, ols_philox_keys PK) {
   constexpr int NA = 4 * NV;
   // AoS Q-learning keeps the policy row Q[S, :] in the group's Cold block (shared memory) between the bootstrap read of
@@ -1298,8 +1307,9 @@ inline cudaError_t launch_run_aos(const ols_queues_t& q, const ols_replicas_t& r
     auto k = (r.rng_mode == OLS_RNG_FEED) ? kf : (c.lanes == 2 ? kp2 : c.lanes == 4 ? kp4 : kp);
     if (q.hot != nullptr && r.rng_mode == OLS_RNG_PHILOX) {  // hot records: 4 x 8 bytes per lane and round
       auto kh = run_kernel<NV, AGENT, QT, RNGT_PHILOX, 4, true, 0, true>;
+      auto kh1 = run_kernel<NV, AGENT, QT, RNGT_PHILOX, 4, true, 1, true>;
       auto kh2 = run_kernel<NV, AGENT, QT, RNGT_PHILOX, 4, true, 2, true>;
-      k = (c.lanes == 2) ? kh2 : kh;
+      k = (c.lanes == 2) ? kh2 : (c.lanes == 1) ? kh1 : kh;
     }
     if (L.smem > 40 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
