@@ -40,9 +40,9 @@ WORKLOADS = {
                desc="cartpole-shaped: 1M-transition log, 162 states, 2 actions, eps-greedy Q-learning, 10k replicas"),
 }
 # DRAM bytes (read + write) per accepted transition of the fused run kernel, from the committed `ncu --set full`
-# captures (profiles/r01f_ncu_full_run_kernel_final_*.txt): dram__bytes_read.sum + dram__bytes_write.sum divided by the
+# captures (profiles/r01n_ncu_full_run_kernel_c4.txt, r01j_ncu_full_run_kernel_c5.txt): dram__bytes_read.sum + dram__bytes_write.sum divided by the
 # accepted transitions of the captured launch.  Used to report `roofline.traffic` per launch.
-NCU_DRAM_BYTES_PER_ACCEPTED = {"c4": (17.565853e9 + 1.293527e9) / 3.75e7, "c5": (18.883526e9 + 0.301427e9) / 3.2e6,
+NCU_DRAM_BYTES_PER_ACCEPTED = {"c4": (16.764115e9 + 1.279550e9) / 3.75e7, "c5": (18.883526e9 + 0.301427e9) / 3.2e6,
                                "c5_full_records": (78.641898e9 + 1.658046e9) / 3.2e6}
 EPS, ALPHA, GAMMA = 0.1, 0.1, 0.99
 EP_CAP = 512
@@ -570,7 +570,7 @@ def main():
                          "traffic": (NCU_DRAM_BYTES_PER_ACCEPTED[args.workload] * last_accepted
                                      if (args.workload in NCU_DRAM_BYTES_PER_ACCEPTED and use_hot and args.ppl == 0 and args.lanes is None)
                                      else None),   # the captures are of the default configuration
-                         "traffic_note": "DRAM read+write bytes per launch = ncu bytes per accepted transition (profiles/r01j_*) x accepted per launch",
+                         "traffic_note": "DRAM read+write bytes per launch = ncu bytes per accepted transition (profiles/r01n_ncu_full_run_kernel_c4.txt) x accepted per launch",
                          "algorithmic_bytes_per_launch": my_pops * rec_bytes, "peak_source": peak_src,
                          "algorithmic_bytes_per_pop": rec_bytes, "agent_state_GBps": agent_gbs, "kernel_ms": float(run_ms),
                          "random_access": ({"dram_transactions_per_s": (NCU_DRAM_BYTES_PER_ACCEPTED["c4"] / 128.0) * last_accepted / run_s,
