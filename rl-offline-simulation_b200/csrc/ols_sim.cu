@@ -165,7 +165,8 @@ extern "C" int ols_step_action(const ols_queues_t* q, const ols_replicas_t* r, c
 
 extern "C" size_t ols_run_sched_bytes(int64_t n_replicas, int32_t lanes) {
   if (n_replicas < 0 || !valid_lanes(lanes)) return 0;
-  return sizeof(int32_t) * (size_t)((n_replicas * lanes + kThreads - 1) / kThreads + 1);
+  const int threads = (lanes == 1 && OLS_G1_THREADS < kThreads) ? OLS_G1_THREADS : kThreads;  // the smallest CTA a run may use
+  return sizeof(int32_t) * (size_t)((n_replicas * lanes + threads - 1) / threads + 1);
 }
 
 extern "C" int ols_run(const ols_queues_t* q, const ols_replicas_t* r, const ols_run_t* c, void* stream) {
@@ -203,7 +204,10 @@ extern "C" int ols_run(const ols_queues_t* q, const ols_replicas_t* r, const ols
   if (c->agent != OLS_AGENT_QLEARN) OLS_REQUIRE(c->pi, OLS_ERR_INVALID, "ols_run: fixed-policy agents need pi");
   OLS_REQUIRE((!c->trace_row && !c->td_error) || c->trace_cap > 0, OLS_ERR_INVALID, "ols_run: trace taps need trace_cap > 0");
   RunLaunch L;
-  const int n_blocks = (int)((r->n_replicas * c->lanes + kThreads - 1) / kThreads);  // one lane group per replica
+  // (the one-lane hot-record learner is built for OLS_MINB_G1 CTAs of OLS_G1_THREADS per SM, see run_kernel's launch bounds)
+  const bool g1_hot = c->lanes == 1 && c->state_aos && q->hot && r->rng_mode == OLS_RNG_PHILOX;
+  L.threads = g1_hot ? OLS_G1_THREADS : kThreads;
+  const int n_blocks = (int)((r->n_replicas * c->lanes + L.threads - 1) / L.threads);  // one lane group per replica
   L.plan = make_stage_plan(q, c);
   // ---- time slicing (see run_kernel): only a budgeted run has slices to hand out
   OLS_REQUIRE(c->slices >= -1 && c->slices <= 4096, OLS_ERR_INVALID, "ols_run: slices must be -1 (auto), 0/1 (off) or 2..4096");
@@ -212,8 +216,6 @@ extern "C" int ols_run(const ols_queues_t* q, const ols_replicas_t* r, const ols
   int slices = c->slices > 1 ? c->slices : 1;
   if (c->slices == -1 && c->sched && c->max_steps > 0 && L.plan.slot_bytes == 0) {
     // resident CTAs per wave under the kernels' launch bounds; slice when the last wave would run part-empty
-    // (the one-lane hot-record learner is built for OLS_MINB_G1 CTAs per SM, see run_kernel's launch bounds)
-    const bool g1_hot = c->lanes == 1 && c->state_aos && q->hot && r->rng_mode == OLS_RNG_PHILOX;
     const int resident = OLS_SM_COUNT * (q->n_actions <= 4 ? (g1_hot ? OLS_MINB_G1 : OLS_MINB) : 2);
     const int full = n_blocks / resident, rest = n_blocks % resident;
     if (full >= 1 && rest != 0 && rest < resident * 9 / 10) {
@@ -226,7 +228,7 @@ extern "C" int ols_run(const ols_queues_t* q, const ols_replicas_t* r, const ols
   c = &cfg;
   if (slices > 1) OLS_CUDA_CHECK(cudaMemsetAsync(cfg.sched, 0, sizeof(int32_t) * (size_t)(n_blocks + 1), (cudaStream_t)stream));
   L.grid = n_blocks * slices;
-  L.smem = (sizeof(Cold) + (size_t)L.plan.slot_bytes) * (kThreads / c->lanes);
+  L.smem = (sizeof(Cold) + (size_t)L.plan.slot_bytes) * (L.threads / c->lanes);
   L.keys = ols_philox_make_keys(r->seed);
   L.stream = (cudaStream_t)stream;
   int ppl = c->pops_per_lane;

@@ -41,6 +41,10 @@ constexpr int kThreads = 256;
 #ifndef OLS_MINB_G1
 #define OLS_MINB_G1 3
 #endif
+// CTA size of that one-lane kernel (every other kernel of the simulator runs kThreads per CTA)
+#ifndef OLS_G1_THREADS
+#define OLS_G1_THREADS 256
+#endif
 
 // RNGT_NONE: the accept-all baselines (trivial_baselines.py:8-10,22-24) draw no uniform at all
 enum { RNGT_FEED = OLS_RNG_FEED, RNGT_PCG64 = OLS_RNG_PCG64, RNGT_PHILOX = OLS_RNG_PHILOX, RNGT_NONE = 3 };
@@ -764,7 +768,7 @@ struct EpsGreedySource {
 // against its own queue; a group whose round accepted a record runs the learner update and prepares its next
 // step in the same iteration (predicated), so no group waits for the longest reject chain in its warp.
 template <int NV, int AGENT, typename QT, int RNG, int PPL, bool AOS = false, int GT = 0, bool HOT = false>
-__global__ void __launch_bounds__(kThreads, (NV == 1 ? (GT == 1 ? OLS_MINB_G1 : OLS_MINB) : 2)) run_kernel(ols_queues_t q, ols_replicas_t R, ols_run_t cfg,
+__global__ void __launch_bounds__((GT == 1 ? OLS_G1_THREADS : kThreads), (NV == 1 ? (GT == 1 ? OLS_MINB_G1 : OLS_MINB) : 2)) run_kernel(ols_queues_t q, ols_replicas_t R, ols_run_t cfg,
                                                                                   StagePlan plan, ols_philox_keys PK) {
   constexpr int NA = 4 * NV;
   // AoS Q-learning keeps the policy row Q[S, :] in the group's Cold block (shared memory) between the bootstrap read of
@@ -814,7 +818,7 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? (GT == 1 ? OLS_MINB_G1 : 
   const uint32_t h_rep = R.ring_mode ? ols_ring_replica_hash(R.ring_seed, rid) : 0u;
   const int group = threadIdx.x / G;
   volatile Cold* C = (volatile Cold*)s_mem + group;
-  unsigned char* my_slot = s_mem + sizeof(Cold) * (kThreads / G) + (size_t)group * plan.slot_bytes;
+  unsigned char* my_slot = s_mem + sizeof(Cold) * (blockDim.x / G) + (size_t)group * plan.slot_bytes;
 
   // hot registers
   int cur_z = 0, cur_s = 0;
@@ -1290,6 +1294,7 @@ __global__ void __launch_bounds__(kThreads, (NV == 1 ? (GT == 1 ? OLS_MINB_G1 : 
 // ------------------------------------------------------------------------------------------ per-NV launchers
 struct RunLaunch {
   int grid;
+  int threads;  // CTA size: kThreads, or OLS_G1_THREADS for the one-lane hot-record learner
   size_t smem;
   StagePlan plan;
   ols_philox_keys keys;
@@ -1315,7 +1320,7 @@ inline cudaError_t launch_run_aos(const ols_queues_t& q, const ols_replicas_t& r
       cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
       if (e != cudaSuccess) return e;
     }
-    k<<<L.grid, kThreads, L.smem, L.stream>>>(q, r, c, L.plan, L.keys);
+    k<<<L.grid, L.threads, L.smem, L.stream>>>(q, r, c, L.plan, L.keys);
     return cudaGetLastError();
   } else {
     return cudaErrorInvalidValue;
