@@ -218,7 +218,9 @@ extern "C" int ols_run(const ols_queues_t* q, const ols_replicas_t* r, const ols
     // resident CTAs per wave under the kernels' launch bounds; slice when the last wave would run part-empty
     const int resident = OLS_SM_COUNT * (q->n_actions <= 4 ? (g1_hot ? OLS_MINB_G1 : OLS_MINB) : 2);
     const int full = n_blocks / resident, rest = n_blocks % resident;
-    if (full >= 1 && rest != 0 && rest < resident * 9 / 10) {
+    // the one-lane learner is also sliced when every block is resident at once: its 6.6 CTAs per SM are 6 on some SMs and 7
+    // on others, and slices re-deal the blocks to whichever SM has room (C4: 207.9 ms unsliced, 187.8 ms in 16 slices)
+    if ((full >= 1 && rest != 0 && rest < resident * 9 / 10) || (g1_hot && n_blocks > OLS_SM_COUNT)) {
       int64_t k = c->max_steps / 512;  // at least 512 accepted transitions per slice
       slices = (int)(k < 1 ? 1 : k > 16 ? 16 : k);
     }

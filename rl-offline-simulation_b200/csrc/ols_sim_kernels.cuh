@@ -36,14 +36,14 @@ constexpr int kThreads = 256;
 #ifndef OLS_MINB
 #define OLS_MINB 4
 #endif
-// one lane per replica (GT == 1): no register is held redundantly, so three CTAs per SM (85 registers, no spills) still
-// keep 768 replicas per SM in flight
+// one lane per replica (GT == 1): no register is held redundantly, so the kernel can trade occupancy for registers in finer
+// steps with small CTAs: 7 CTAs of 128 threads per SM = 896 replicas in flight at 72 registers (C4: 187.8 ms; 3 CTAs of 256
+// at 80 registers: 196.9 ms; 4 of 256 at 64: 204-208 ms).  Every other kernel of the simulator runs kThreads per CTA.
 #ifndef OLS_MINB_G1
-#define OLS_MINB_G1 3
+#define OLS_MINB_G1 7
 #endif
-// CTA size of that one-lane kernel (every other kernel of the simulator runs kThreads per CTA)
 #ifndef OLS_G1_THREADS
-#define OLS_G1_THREADS 256
+#define OLS_G1_THREADS 128
 #endif
 
 // RNGT_NONE: the accept-all baselines (trivial_baselines.py:8-10,22-24) draw no uniform at all

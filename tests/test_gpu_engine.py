@@ -601,6 +601,34 @@ def test_time_slices_are_invisible(ob, agent, aos, lanes, slices):
     assert int(a.accepted.sum()) > 0.9 * R * 433
 
 
+@pytest.mark.parametrize("agent", ["qlearn", "expsarsa"])
+def test_one_lane_production_kernel_sliced_equals_two_lane_unsliced(ob, agent):
+    """The C4 production path — one lane per replica over hot records and AoS state, small CTAs, served in automatic time
+    slices because the launch holds more CTAs than SMs — against the two-lane kernel in a single unsliced launch."""
+    import torch
+    g = make_log(91, 600000, 300, 4, ep_len=20)
+    nS, R = 300, 40000                              # 313 CTAs of 128 threads > 148 SMs: the automatic rule slices
+    log = device_log(ob, g, n_buckets=nS, hot_records=True)
+    pi = np.random.default_rng(14).dirichlet(np.ones(4), size=nS)
+    outs = []
+    for lanes, slices in ((1, -1), (2, 0), (1, 5)):
+        sim = ob.BatchedPSRS(log, R, rng="philox", seed=31, ring=True, ring_seed=4, lanes=lanes, aos_state=True, slices=slices)
+        res = None
+        for budget in (1100, 300):                  # 1100 accepted steps -> two automatic slices; the second launch resumes
+            if agent == "qlearn":
+                res = sim.run_qlearn(nS, 200, gamma=0.9, alpha=0.1, epsilon=0.1, max_steps=budget, trace_cap=64, outputs=res)
+            else:
+                res = sim.run_expsarsa(nS, 200, pi=pi, gamma=0.9, alpha=0.1, max_steps=budget, trace_cap=64, outputs=res)
+        outs.append((res, sim.draws.clone(), sim.ties.clone(), sim.cur_z.clone(), sim.ep_t.clone()))
+    a, da, ta, za, ea = outs[1]
+    for b, db, tb, zb, eb in (outs[0], outs[2]):
+        assert torch.equal(a.trace_row, b.trace_row) and torch.equal(a.accepted, b.accepted) and torch.equal(a.pops, b.pops)
+        assert torch.equal(da, db) and torch.equal(ta, tb) and torch.equal(a.status, b.status) and torch.equal(za, zb)
+        assert torch.equal(ea, eb) and torch.equal(a.Gs, b.Gs) and torch.equal(a.lengths, b.lengths)
+        assert torch.equal(a.Q.contiguous(), b.Q.contiguous())
+    assert int(a.accepted.sum()) > 0.9 * R * 1400
+
+
 def test_time_slices_need_a_budget(ob):
     g = make_log(64, 5000, 10, 4)
     log = device_log(ob, g, n_buckets=10)
