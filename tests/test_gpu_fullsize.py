@@ -81,8 +81,9 @@ def test_c4_hot_records_decode_to_the_records(ob, c4):
     assert float(((halves.float() - p).abs() / p).max()) <= 2.0 ** -11
 
 
-def _run(ob, log, R, id0, budget, **kw):
-    sim = ob.BatchedPSRS(log, R, rng="philox", seed=1234, ring=True, ring_seed=99, replica_id0=id0, lanes=2, **kw)
+def _run(ob, log, R, id0, budget, lanes=1, **kw):
+    # lanes = 1 over hot records and AoS state is the production (bench.py) kernel
+    sim = ob.BatchedPSRS(log, R, rng="philox", seed=1234, ring=True, ring_seed=99, replica_id0=id0, lanes=lanes, **kw)
     res = sim.run_qlearn(NS, 511, gamma=0.99, alpha=0.1, epsilon=0.1, max_steps=budget, ep_cap=512)
     return sim, res
 
@@ -105,11 +106,12 @@ def test_c4_run_conserves_is_idempotent_and_shards(ob, c4):
     q_check = res.Q.sum((1, 2)).clone()
     del sim, res
     torch.cuda.empty_cache()
-    # idempotent, and independent of the accelerated layouts: separate cursor/Q arrays, 32-byte records, no time slices
+    # idempotent, and independent of the accelerated layouts: two lanes per replica, separate cursor/Q arrays, 32-byte records,
+    # no time slices
     plain = ob.BucketedLog.__new__(ob.BucketedLog)
     plain.__dict__.update(log.__dict__)
     plain.hot = None
-    sim2, res2 = _run(ob, plain, R, 0, T, aos_state=False, slices=0)
+    sim2, res2 = _run(ob, plain, R, 0, T, lanes=2, aos_state=False, slices=0)
     assert torch.equal(res2.accepted, acc) and torch.equal(res2.pops, pops)
     assert torch.equal(res2.Gs.sum(1), gs_sum) and torch.equal(res2.lengths.sum(1), len_sum)
     assert torch.equal(res2.Q.sum((1, 2)), q_check)
