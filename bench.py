@@ -557,7 +557,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": args.workload + ": " + wl["desc"], "rows": N, "states": nS, "actions": nA,
                        "replicas_per_gpu": R, "accepted_per_replica_per_step": T, "lanes": wl["lanes"],
-                       "time_slices": ("auto (16 per replica block when the blocks are not a whole number of waves)" if args.slices == -1 else args.slices),
+                       "time_slices": ("auto (16 per replica block: the one-lane learner is sliced whenever the launch holds more CTAs than SMs, the others when their blocks are not a whole number of waves)" if args.slices == -1 else args.slices),
                        "hot_records": ("8-byte half-precision images of the records decide all but ~5e-4 of the pops; the 32-byte record is "
                                        "read for the accepted pop and for the undecided ones" if use_hot else "off"),
                        "replica_state": ("one 32-byte entry {cursor, Q row} per (replica, state)" if use_aos else "separate cursor and Q arrays"),
