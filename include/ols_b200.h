@@ -189,9 +189,10 @@ typedef struct ols_run {
   int32_t prefetch;           /* rounds ahead whose records are prefetched into L2 (0 = off; useful for
                                  long reject chains, i.e. lanes >= 16)                           */
   int32_t slices;             /* time slicing of a budgeted run (max_steps > 0): 0/1 off; k > 1 = the budget is
-                                 served in k slices per 256-thread replica block, handed to the SMs through a
-                                 ticket counter, so a replica count that is not a whole number of waves keeps
-                                 every SM busy; -1 = let the library decide.  Results do not depend on it.     */
+                                 served in k slices per replica block (one CTA: 256 threads; 128 for the one-lane
+                                 hot-record learner), handed to the SMs through a ticket counter, so a replica
+                                 count that is not a whole number of waves keeps every SM busy; -1 = let the
+                                 library decide.  Results do not depend on it.                                 */
   int32_t state_epoch;        /* state_aos: only entries whose epoch word equals this value are live, all others
                                  read as cursor 0 / Q 0 — a restart bumps the epoch instead of clearing the table */
   int64_t max_steps;          /* > 0: every replica stops after this many accepted transitions in
