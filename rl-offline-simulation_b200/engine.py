@@ -280,6 +280,11 @@ class BatchedPSRS:
 
     Scalar reference API per replica: ``reset`` = psrs.py:32-37, ``step`` = psrs.py:39-57; fused
     drivers ``run_qlearn`` / ``run_expsarsa`` / ``run_evalmc`` = psrs.py:119-271.
+
+    ``lanes`` = width of the lane group that serves one replica; results never depend on it.  Measured on B200
+    (DESIGN.md 4.3): ``lanes=1`` with ``hot_records=True`` logs and ``aos_state=True`` when there are enough replicas
+    to fill the GPU (>= ~1e5) and reject chains are short (the C4 learner: 188.6 ms per 1.25e9 transitions);
+    ``lanes=32`` for long reject chains (C5: the round streams 128 hot records); 4-8 in between or for few replicas.
     """
 
     def __init__(self, log: BucketedLog, n_replicas: int, rng: str = "philox", seed: Optional[int] = 0,
