@@ -105,6 +105,38 @@ def test_c_philox_ring_replicas_equal_python_oracle_with_same_streams():
         assert np.array_equal(out["Q"][rep], Q)
 
 
+def test_c_agent_ids_sentinel_offset_and_budget_equal_python_oracle():
+    """The checker semantics tests/test_gpu_configs.py leans on: agent ids distinct from the queue keys (s = z + 1), the
+    CartPole sentinel as bucket 0 (z_offset = 1, z' = -1 on terminal rows) and the step budget — C replicas against
+    python-oracle replicas fed the same Philox numbers."""
+    from tests.helpers import philox_uniform
+    rng = np.random.default_rng(8)
+    N, nB, nA, R = 6000, 9, 2, 4
+    z = rng.integers(0, nB - 1, N)
+    zn = rng.integers(-1, nB - 1, N)
+    done = zn < 0
+    pb = rng.dirichlet(np.ones(nA), size=nB).clip(0.1); pb /= pb.sum(1, keepdims=True)
+    p_log = pb[z].astype(np.float32)
+    a = (rng.random(N) > pb[z, 0]).astype(np.int64)
+    r = rng.normal(size=N).astype(np.float32)
+    t = np.where(np.r_[True, done[:-1]], 0, 1)
+    s, sn, nS = z + 1, zn + 1, nB
+    log = CO.Log(z=z, z_next=zn, s=s, s_next=sn, action=a, reward=r, terminal=done, p_log=p_log, steps=t, n_buckets=nB, z_offset=1)
+    out = CO.run(log, R, CO.QLEARN, nS, 50, gamma=0.9, alpha=0.2, epsilon=0.2, seed=5, replica_id0=40, max_steps=120,
+                 trace_cap=200, threads=2)
+    assert (out["accepted"] == 120).all()
+    for rep in range(R):
+        rid = 40 + rep
+        U = [philox_uniform(5, rid, 0, d) for d in range(int(out["draws"][rep]) + 8)]
+        T = [philox_uniform(5, rid, 1, d) for d in range(int(out["ties"][rep]) + 8)]
+        env = O.OraclePSRS(z=z, z_next=zn, s=s, s_next=sn, action=a, reward=r, terminal=done, p_log=p_log, steps=t,
+                           n_buckets=nB, z_offset=1, uniforms=O.FeedUniforms(U))
+        Q, info = O.qlearn(env, 50, gamma=0.9, alpha=0.2, epsilon=0.2, ties=O.FeedTies(T), nS=nS, nA=nA, max_steps=120)
+        n = info["trace"].size
+        assert n == 120 and np.array_equal(out["trace_row"][rep, :n], info["trace"])
+        assert np.array_equal(out["Q"][rep], Q)
+
+
 def test_c_mlp_equals_python_fma_emulation(golden):
     g = golden("encoders")
     for tag in ["mlp_grid", "mlp_cart", "mlp_wide"]:
