@@ -242,7 +242,10 @@ int32_t ols_record_bytes(int32_t n_actions);
 size_t ols_bucket_scratch_bytes(int64_t n_rows, int32_t n_buckets);
 /* Stable counting sort of the rows by z (psrs.py:26: sorted + groupby) fused with record packing.
  * Fills q->offsets and q->records (log order inside every queue).  q's scalar fields and buffer
- * pointers are set by the caller.                                                              */
+ * pointers are set by the caller.  A row whose key z + z_offset falls outside [0, n_buckets) is
+ * DROPPED (the reference would open a new dict entry for it, psrs.py:26): offsets[n_buckets] is the
+ * number of rows actually bucketed, so a caller detects drops by comparing it with n_rows (the
+ * Python host does, and raises).                                                               */
 int ols_bucket(const ols_log_t* log, const ols_queues_t* q, void* scratch, size_t scratch_bytes, void* stream);
 /* psrs.py:22 — initial rows (step == 0) in log order -> q->init_row/init_z/init_s; the count is
  * written to *n_init_dev (device int64).  scratch: ols_bucket_scratch_bytes(n_rows, 1).        */

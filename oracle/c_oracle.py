@@ -32,7 +32,7 @@ class Sim(C.Structure):
         ("n_episodes", i32), ("ep_cap", i32), ("max_steps", i64), ("gamma", f64), ("alpha", p), ("epsilon", p), ("pi", p),
         ("Q", p), ("Gs", p), ("lengths", p), ("n_returns", p), ("n_lengths", p), ("status", p),
         ("accepted", p), ("pops", p), ("draws", p), ("ties", p), ("trace_row", p), ("td_error", p), ("trace_cap", i64),
-        ("trace_hash", p),
+        ("trace_hash", p), ("q_is_f32", i32), ("_pad0", i32), ("replica_ids", p),
     ]
 
 
@@ -97,8 +97,13 @@ class Log:
 
 def run(log: Log, n_replicas, agent, n_states, n_episodes, gamma, alpha=None, epsilon=None, pi=None, seed=0,
         replica_id0=0, u_feed=None, tie_feed=None, ring=False, ring_seed=0, accept_all=False, compute_f32=None,
-        max_steps=0, trace_cap=0, ep_cap=None, threads=1, order=None, init_row=None, want_q=True):
-    """Run ``n_replicas`` fresh replicas; returns a dict of numpy arrays (+ ``threads`` actually used)."""
+        max_steps=0, trace_cap=0, ep_cap=None, threads=1, order=None, init_row=None, want_q=True, q_f32=False,
+        replica_ids=None):
+    """Run ``n_replicas`` fresh replicas; returns a dict of numpy arrays (+ ``threads`` actually used).
+
+    ``q_f32``: the float32 learner of the GPU production path (Q entries are float32 values, the update is four
+    separately rounded float32 operations); ``Q`` is then returned as float32.  ``replica_ids``: global ids of the
+    replicas to run (a sample of a larger fleet), default ``replica_id0 + arange(n_replicas)``."""
     lib = load()
     R, nA = int(n_replicas), log.n_actions
     ep_cap = int(ep_cap or n_episodes + 1)
@@ -130,6 +135,9 @@ def run(log: Log, n_replicas, agent, n_states, n_episodes, gamma, alpha=None, ep
 
     ulen, ustride = feed_shape(u_feed)
     tlen, tstride = feed_shape(tie_feed)
+    rid_a = None if replica_ids is None else _c(replica_ids, np.int64)
+    if rid_a is not None and rid_a.shape[0] != R:
+        raise ValueError("replica_ids must hold n_replicas ids")
     order = log.order if order is None else _c(order, np.int32)
     init_row = log.init_row if init_row is None else _c(init_row, np.int32)
     out = dict(
@@ -155,8 +163,12 @@ def run(log: Log, n_replicas, agent, n_states, n_episodes, gamma, alpha=None, ep
             Q=_p(out["Q"]), Gs=_p(out["Gs"]), lengths=_p(out["lengths"]), n_returns=_p(out["n_returns"]),
             n_lengths=_p(out["n_lengths"]), status=_p(out["status"]), accepted=_p(out["accepted"]), pops=_p(out["pops"]),
             draws=_p(out["draws"]), ties=_p(out["ties"]), trace_row=_p(out["trace_row"]), td_error=_p(out["td_error"]),
-            trace_cap=trace_cap, trace_hash=_p(out["trace_hash"]))
+            trace_cap=trace_cap, trace_hash=_p(out["trace_hash"]), q_is_f32=int(bool(q_f32)), _pad0=0, replica_ids=_p(rid_a))
     out["threads"] = lib.oracle_run(C.byref(S), int(threads))
+    if q_f32 and out["Q"] is not None:
+        q32 = out["Q"].astype(np.float32)
+        assert np.array_equal(q32.astype(np.float64), out["Q"]), "float32 learner left a non-float32 Q entry"
+        out["Q"] = q32
     return out
 
 

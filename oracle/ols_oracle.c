@@ -157,6 +157,14 @@ typedef struct oracle_sim {
   double* td_error;     /* [R][trace_cap] or NULL */
   int64_t trace_cap;
   uint64_t* trace_hash; /* [R] order-sensitive hash of the accepted rows (always written) */
+  /* float32 learner (the GPU production mode): Q entries are float32 values (held in the double array, exactly), and the
+   * update psrs.py:165-168 runs as four separately rounded float32 operations on float32 images of R, gamma, alpha:
+   *     td = ((R + gamma * boot) - Q[S,A]);   Q[S,A] = Q[S,A] + alpha * td
+   * (no contraction: -ffp-contract=off).  The CUDA side states the same order with __fmul_rn/__fadd_rn/__fsub_rn.     */
+  int32_t q_is_f32;
+  int32_t _pad0;
+  const int64_t* replica_ids; /* [R] global replica ids (keys of the Philox streams and ring offsets), or NULL =
+                                 replica_id0 + r: lets a test run a SAMPLE of a large fleet's replicas                */
 } oracle_sim_t;
 
 static double p_at(const oracle_sim_t* S, int64_t row, int j) {
@@ -168,7 +176,7 @@ static double pi_at(const oracle_sim_t* S, int s, int j) {
 
 static void run_replica(const oracle_sim_t* S, int64_t r, int32_t* cursor) {
   const int nA = S->n_actions, nS = S->n_states;
-  const uint64_t rid = (uint64_t)(S->replica_id0 + r);
+  const uint64_t rid = S->replica_ids ? (uint64_t)S->replica_ids[r] : (uint64_t)(S->replica_id0 + r);
   double* Q = S->Q ? S->Q + r * (int64_t)nS * nA : NULL;
   double* Gs = S->Gs + r * (int64_t)S->ep_cap;
   int32_t* lens = S->lengths + r * (int64_t)S->ep_cap;
@@ -257,10 +265,22 @@ static void run_replica(const oracle_sim_t* S, int64_t r, int32_t* cursor) {
         } else {
           boot = 0.0;
           for (int j = 0; j < nA; ++j) boot = fma(nrow[j], pi_at(S, s2, j), boot);
+          if (S->q_is_f32) boot = (double)(float)boot;
         }
         double* q = Q + (int64_t)cs * nA + A;
-        const double td = R + S->gamma * boot - *q;                       /* psrs.py:165 */
-        *q = *q + alpha * td;                                              /* psrs.py:168 */
+        double td;
+        if (S->q_is_f32) {
+          const float Rf = (float)R, gf = (float)S->gamma, af = (float)alpha, bf = (float)boot, qf = (float)*q;
+          const float gb = gf * bf;
+          const float tgt = Rf + gb;
+          const float tdf = tgt - qf;                                      /* psrs.py:165, float32 */
+          const float step = af * tdf;
+          *q = (double)(qf + step);                                        /* psrs.py:168, float32 */
+          td = (double)tdf;
+        } else {
+          td = R + S->gamma * boot - *q;                                   /* psrs.py:165 */
+          *q = *q + alpha * td;                                            /* psrs.py:168 */
+        }
         if (S->td_error && accepted < S->trace_cap) S->td_error[r * S->trace_cap + accepted] = td;
       }
       if (S->trace_row && accepted < S->trace_cap) S->trace_row[r * S->trace_cap + accepted] = row;

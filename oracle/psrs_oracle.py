@@ -329,15 +329,19 @@ def _schedule(x):
 
 
 def qlearn(env: OraclePSRS, n_episodes, gamma, alpha, epsilon, ties, nS, nA, q_init=None,
-           max_steps=None, record=True):
+           max_steps=None, record=True, q_dtype=np.float64):
     """evaluators/psrs.py:119-185 with ``behavior_policy = epsilon_greedy_policy``.
 
     No terminal mask on the bootstrap (psrs.py:165,168); a partial last episode IS appended to Gs
     (psrs.py:160-162,177); ``gamma ** t`` is a fresh power (psrs.py:171).  ``max_steps`` (not in the
     reference) stops after that many accepted transitions, mirroring the product's step budget.
+    ``q_dtype=np.float32``: the float32 learner — the same two update lines on a float32 table; with float32 rewards NumPy
+    >= 2 evaluates them as separately rounded float32 operations with gamma and alpha rounded to float32 (what the
+    reference's own lines do on a float32 table, tests/golden/make_golden.py ``F32Table``); the policy row is still formed
+    from the float64 image of the Q row.
     """
     eps_f, alpha_f = _schedule(epsilon), _schedule(alpha)
-    Q = np.zeros((nS, nA)) if q_init is None else np.array(q_init, dtype=np.float64, copy=True)
+    Q = np.zeros((nS, nA), dtype=q_dtype) if q_init is None else np.array(q_init, dtype=q_dtype, copy=True)
     Gs, lengths, td_errors, trace = [], [], [], []
     episode, terminate, total = 0, False, 0
     while episode < n_episodes and not terminate:
@@ -348,7 +352,7 @@ def qlearn(env: OraclePSRS, n_episodes, gamma, alpha, epsilon, ties, nS, nA, q_i
         S = int(S)
         done = False
         while not done:
-            p = epsilon_greedy_row(Q[S], eps_f(episode), ties)
+            p = epsilon_greedy_row(np.asarray(Q[S], dtype=np.float64), eps_f(episode), ties)
             row = env.step(p)
             if row is None:
                 terminate = True

@@ -705,8 +705,13 @@ struct QMath<double> {
 };
 template <>
 struct QMath<float> {
-  static __device__ __forceinline__ float td(float R, float gamma, float boot, float q) { return R + gamma * boot - q; }
-  static __device__ __forceinline__ float upd(float q, float alpha, float td) { return q + alpha * td; }
+  // float32 production path: the same expressions with every operand rounded to float32 first (gamma, alpha(ep) and the
+  // reward are float32 images) and one IEEE float32 operation at a time — the order is part of the contract
+  // (oracle/ols_oracle.c `q_is_f32`), never left to the compiler's FMA contraction
+  static __device__ __forceinline__ float td(float R, float gamma, float boot, float q) {
+    return __fsub_rn(__fadd_rn(R, __fmul_rn(gamma, boot)), q);
+  }
+  static __device__ __forceinline__ float upd(float q, float alpha, float td) { return __fadd_rn(q, __fmul_rn(alpha, td)); }
 };
 
 // Shared-memory plan of one CTA (host-computed, see ols_sim.cu).  Every lane group owns

@@ -163,6 +163,9 @@ class BucketedLog:
             abi.check(lib.ols_bucket(C.byref(log_key), C.byref(q), _ptr(scratch), sb, _stream_ptr()))
             abi.check(lib.ols_init_queue(C.byref(log), C.byref(q), _ptr(n_init_dev), _ptr(scratch), sb, _stream_ptr()))
             self.n_init = int(n_init_dev.item())        # one sync: construction is not the step path
+            dropped = n - int(self.offsets[-1].item())   # ols_bucket skips rows whose key is outside [0, n_buckets)
+            if dropped:
+                raise ValueError(f"{dropped} rows have a state id outside [-z_offset, n_buckets - z_offset)")
             self.init_row = init_row[: max(self.n_init, 1)]
             self.init_z = init_z[: max(self.n_init, 1)]
             self.init_s = init_s[: max(self.n_init, 1)]
@@ -271,8 +274,16 @@ class RunResult:
     @property
     def Q(self) -> Optional[torch.Tensor]:
         if self._Q is None and self._q_fn is not None:
-            self._Q = self._q_fn()
+            self._Q = self._q_fn(None)
         return self._Q
+
+    def q_rows(self, replicas) -> Optional[torch.Tensor]:
+        """Q tables [k, nS, nA] of the listed replicas only (at the production shape the whole fleet's Q is 20 GB; a
+        parity check of a sample gathers 160 KB per replica)."""
+        idx = torch.as_tensor(replicas, dtype=torch.long, device=self.Gs.device)
+        if self._Q is not None:
+            return self._Q[idx]
+        return None if self._q_fn is None else self._q_fn(idx)
 
 
 class BatchedPSRS:
@@ -435,9 +446,24 @@ class BatchedPSRS:
                     s_next=self.out_s_next, z_from=self.out_z_from, status=self.status)
 
     # ------------------------------------------------------------------ fused drivers
+    def begin_driver_call(self):
+        """A reference driver (psrs.py:119-271) counts its episodes from 0 on EVERY call and keeps consuming the queues
+        where the previous call left them: clear the episode registers and re-arm the replicas a previous fused run left
+        DONE / QUEUE_EMPTY (the run kernel starts every episode with `reset`, which reports INIT_EMPTY by itself).
+        The batched API does not call this: there a second `run_*` RESUMES the first (chunked runs)."""
+        with torch.cuda.device(self.device):
+            for t in (self.ep_index, self.ep_len_count, self.ep_t, self.ep_open):
+                t.zero_()
+            self.ep_G.zero_()
+            self.ep_disc.fill_(1.0)
+            self.status.fill_(abi.RUNNING)
+
     def _schedule(self, x, n_episodes):
         if callable(x):
-            vals = [float(x(e)) for e in range(n_episodes + 1)]
+            # the reference calls a schedule lazily, for episode < n_episodes only (psrs.py:158,168): a schedule defined on
+            # [0, n_episodes) must work; the kernel never reads entry n_episodes before it terminates with DONE
+            vals = [float(x(e)) for e in range(n_episodes)]
+            vals = vals + [vals[-1] if vals else 0.0]
         elif np.ndim(x) == 0:
             vals = [float(x)] * (n_episodes + 1)
         else:
@@ -511,11 +537,15 @@ class BatchedPSRS:
         if use_aos:
             aos, epoch = self.aos, self._epoch
 
-            def q_fn():
-                live = (aos.view(torch.int32)[:, :, 1] == epoch).unsqueeze(-1)
-                return torch.where(live, aos[:, :, 4:4 + nA], torch.zeros((), dtype=torch.float32, device=aos.device))
-        return RunResult(_Q=Q, _q_fn=q_fn, Gs=Gs, lengths=lengths, n_returns=self.ep_index, n_lengths=self.ep_len_count,
-                         status=self.status, accepted=self.accepted, pops=self.pops, trace_row=trace_row, td_error=td)
+            def q_fn(idx):
+                tab = aos if idx is None else aos[idx]
+                live = (tab.view(torch.int32)[:, :, 1] == epoch).unsqueeze(-1)
+                return torch.where(live, tab[:, :, 4:4 + nA], torch.zeros((), dtype=torch.float32, device=aos.device))
+            # the per-replica counters are SNAPSHOTS: a later run / restart on this block does not change a result already
+            # handed out (Gs, lengths and the trace buffers are the result's own unless passed back through `outputs=`)
+            return RunResult(_Q=Q, _q_fn=q_fn, Gs=Gs, lengths=lengths, n_returns=self.ep_index.clone(),
+                             n_lengths=self.ep_len_count.clone(), status=self.status.clone(), accepted=self.accepted.clone(),
+                             pops=self.pops.clone(), trace_row=trace_row, td_error=td)
 
     def run_qlearn(self, n_states, n_episodes, gamma, alpha=0.1, epsilon=1.0, Q=None, q_dtype=torch.float32,
                    max_steps=0, trace_cap=0, ep_cap=None, outputs=None) -> RunResult:

@@ -123,6 +123,13 @@ class PSRS(object):
         self._sim.rng_mode = abi.RNG_FEED
         self._sim.draws.zero_()
 
+    def feed_ties(self, values):
+        """Parity hook for the fused Q-learning driver: tie-break k of ``_random_argmax`` (tabular.py:4-5) picks candidate
+        ``min(n - 1, int(values[k] * n))`` — what a harness does to the reference by patching ``np.random.choice``."""
+        self._sim.tie_feed = torch.as_tensor(np.asarray(values, dtype=np.float64), device=self._sim.device)
+        self._sim.tie_mode = abi.RNG_FEED
+        self._sim.ties.zero_()
+
     # ------------------------------------------------------------------ psrs.py:32-37
     def reset(self, seed=None):
         _, status = self._sim.reset()
@@ -180,6 +187,9 @@ class PSRS(object):
         self.z = int(self._sim.cur_z[0])
         st = int(self._sim.status[0])
         self.s = None if st == abi.INIT_EMPTY else int(self._sim.cur_s[0])
+        if st == abi.DONE:
+            # the reference's env is an ordinary env after a driver returns: a scalar step() continues from the last state
+            self._sim.status.fill_(abi.RUNNING)
 
 
 class PSRS_Exo(object):
@@ -312,12 +322,16 @@ def qlearn_psrs(env, n_episodes, behavior_policy, gamma, alpha=0.1, epsilon=1.0,
 
     With ``behavior_policy = agents.tabular.epsilon_greedy_policy`` and ``save_Q == 0`` the whole run is one
     fused kernel launch (float64 Q, the reference's operation order); any other policy callable falls back to
-    a host-driven loop whose every ``env.step`` is still the CUDA step."""
+    a host-driven loop whose every ``env.step`` is still the CUDA step.  As in the reference, every call counts its
+    episodes from 0 and keeps consuming the queues where the previous call (or scalar stepping) left them.  Rewards
+    travel as float32 inside the packed records: the fused path computes Q / TD / Gs from the float32 image of a
+    float64 reward (~1e-8 relative, inside the 1e-5 contract); ``memory`` tuples carry ``p = None``."""
     if _fusable(env) and behavior_policy is _tabular.epsilon_greedy_policy and not save_Q:
         Q0 = np.zeros((env.nS, env.nA)) if Q_init is None else np.asarray(Q_init, dtype=np.float64)
         Qd = torch.as_tensor(Q0.reshape(1, env.nS, env.nA).copy(), device=env._sim.device)
         cap = max(1, env._log.n_rows)
         first = int(env._sim.accepted[0])
+        env._sim.begin_driver_call()
         res = env._sim.run_qlearn(env.nS, n_episodes, gamma, alpha=alpha, epsilon=epsilon, Q=Qd, trace_cap=cap)
         _raise_on_error(env, res)
         env._sync_from_device()
@@ -365,6 +379,7 @@ def expSARSA_psrs(env, n_episodes, pi, gamma, alpha=0.1, Q_init=None, save_Q=0):
         Q0 = np.zeros((env.nS, env.nA)) if Q_init is None else np.asarray(Q_init, dtype=np.float64)
         Qd = torch.as_tensor(Q0.reshape(1, env.nS, env.nA).copy(), device=env._sim.device)
         first = int(env._sim.accepted[0])
+        env._sim.begin_driver_call()
         res = env._sim.run_expsarsa(env.nS, n_episodes, pi, gamma, alpha=alpha, Q=Qd, trace_cap=max(1, env._log.n_rows))
         _raise_on_error(env, res)
         env._sync_from_device()
@@ -405,6 +420,7 @@ def evalMC_psrs(env, n_episodes, pi, gamma):
     simulated ones (reference: psrs.py:241-271)."""
     pi = np.asarray(pi)
     if _fusable(env):
+        env._sim.begin_driver_call()
         res = env._sim.run_evalmc(env.nS, n_episodes, pi, gamma)
         _raise_on_error(env, res)
         env._sync_from_device()

@@ -90,6 +90,37 @@ from offsim4rl.data import OfflineDataset, ProbDistribution          # noqa: E40
 
 
 # --------------------------------------------------------------------------- harness
+_HELPERS = None
+
+
+def _helpers():
+    """The repo's tests/helpers.py, loaded by FILE PATH: /root/reference is first on sys.path and has its own `tests`
+    package, which would shadow `import tests.helpers`."""
+    global _HELPERS
+    if _HELPERS is None:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_repo_test_helpers", os.path.join(os.path.dirname(OUT), "helpers.py"))
+        _HELPERS = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(_HELPERS)
+    return _HELPERS
+
+
+class F32Table(np.ndarray):
+    """A Q_init whose `.copy().astype(float)` (psrs.py:141) stays float32: the reference's OWN update lines
+    (psrs.py:165-168) then run on a float32 table, i.e. under NumPy >= 2 promotion as separately rounded float32
+    operations `(R + gamma * max) - Q[S,A]`, `Q[S,A] + alpha * td` with gamma and alpha rounded to float32 — the
+    arithmetic of the GPU production learner.  Nothing in the reference is modified."""
+
+    def astype(self, dtype, *a, **k):
+        return np.array(self, dtype=np.float32, copy=True, subok=False)
+
+
+def f64_policy(policy):
+    """The reference's policy evaluated on the float64 image of the (float32) Q row, so that p_new and the accept rule
+    stay float64 as in the float64 runs (the arg-max is unchanged: the values are exact)."""
+    return lambda Q, args: policy(np.asarray(Q, dtype=np.float64), args)
+
+
 class Feed:
     def __init__(self, values):
         self.values = values
@@ -243,6 +274,28 @@ def _drivers_case(name, N, nS, nA, p_dtype, pi_dtype, zero_prob_rows=0, a_dtype=
         out[f"ql_{tag}_trace"] = np.array([id2row[id(m[6]["p"])] for m in info["memory"]], dtype=np.int64)
         out[f"ql_{tag}_draws"] = np.array(feed.k)
         out[f"ql_{tag}_ties"] = np.array(ties.k)
+    # --- the same two runs on a float32 Q table (F32Table): pins the float32 learner's operation order to the reference's code
+    out32 = {}
+    for tag, eps, alpha in [] if (only_mc or log["r"].dtype != np.float32) else [
+            ("const", 0.2, 0.1), ("sched", (lambda e: 1.0 / (1 + e)), (lambda e: 0.5 / (1 + 0.1 * e)))]:
+        env, id2row, feed = fresh()
+        ties = TieFeed(T)
+        saved = np.random.choice
+        np.random.choice = ties
+        try:
+            Q, info = ref_psrs.qlearn_psrs(env, n_episodes=25, behavior_policy=f64_policy(ref_tabular.epsilon_greedy_policy),
+                                           gamma=0.9, alpha=alpha, epsilon=eps, Q_init=np.zeros((nS, nA), np.float32).view(F32Table))
+        finally:
+            np.random.choice = saved
+        assert Q.dtype == np.float32 and info["TD_errors"].dtype == np.float32
+        out32[f"ql_{tag}_Q"] = Q
+        out32[f"ql_{tag}_Gs"] = np.asarray(info["Gs"], dtype=np.float64)
+        out32[f"ql_{tag}_TD"] = info["TD_errors"]
+        out32[f"ql_{tag}_trace"] = np.array([id2row[id(m[6]["p"])] for m in info["memory"]], dtype=np.int64)
+        out32[f"ql_{tag}_draws"] = np.array(feed.k)
+        out32[f"ql_{tag}_ties"] = np.array(ties.k)
+    if out32:
+        save(name + "_f32q", **out32)
     out["ql_sched_eps"] = np.array([1.0 / (1 + e) for e in range(25)])
     out["ql_sched_alpha"] = np.array([0.5 / (1 + 0.1 * e) for e in range(25)])
 
@@ -572,8 +625,7 @@ def case_psrs_exo():
 def case_recorder():
     """utils/dataset_utils.py:34-136 `record_dataset_in_memory` on the toy environment of tests/helpers.py: the column
     layout (`infos/<key>` flattening, first-step key rule, episode ids with several workers) that the ingest consumes."""
-    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
-    from tests.helpers import ToyChainEnv, ToyAgent
+    ToyChainEnv, ToyAgent = _helpers().ToyChainEnv, _helpers().ToyAgent
     from offsim4rl.utils.dataset_utils import record_dataset_in_memory
     out = {}
     for tag, kw in {"w0": dict(seed=5, worker_id=0, workers_num=1), "w2of3": dict(seed=8, worker_id=2, workers_num=3)}.items():
@@ -587,7 +639,112 @@ def case_recorder():
     save("recorder", **out)
 
 
+def case_back_to_back():
+    """Several drivers on ONE env without reset_sampler in between (learn, then evaluate, then learn on): every call counts
+    its episodes from 0 and keeps consuming the queues and the uniform stream where the previous call stopped."""
+    rng = np.random.default_rng(808)
+    N, nS, nA = 6000, 8, 3
+    log = make_log(rng, N, nS, nA, ep_len=6)
+    out = {k: v for k, v in log.items()}
+    U, T = rng.random(2 * N), rng.random(N // 4)
+    pi = rng.dirichlet(np.ones(nA), size=nS)
+    out.update(U=U, T=T, pi=pi, sampler_seed=np.array(7))
+    rows, id2row = legacy_tuples(log)
+    env = ref_psrs.PSRS(rows, nS=nS, nA=nA)
+    env.reset_sampler(seed=7)
+    feed = Feed(U)
+    env.rejection_sampling_rng = feed
+    trace = []
+    orig_step = env.step
+
+    def traced_step(p):
+        res = orig_step(p)
+        if res[0] is not None:
+            trace.append(id2row[id(res[3]["p"])])
+        return res
+    env.step = traced_step
+    ties = TieFeed(T)
+    saved = np.random.choice
+    np.random.choice = ties
+    try:
+        eps_list, alpha_list = [0.5 / (1 + e) for e in range(10)], [0.3] * 10
+        Q1, i1 = ref_psrs.qlearn_psrs(env, n_episodes=10, behavior_policy=ref_tabular.epsilon_greedy_policy, gamma=0.9,
+                                      alpha=lambda e: alpha_list[e], epsilon=lambda e: eps_list[e])   # defined on [0, 10) only
+        k1, d1, t1 = len(trace), feed.k, ties.k
+        Gs2, len2 = ref_psrs.evalMC_psrs(env, n_episodes=12, pi=pi, gamma=0.95)
+        k2, d2 = len(trace), feed.k
+        s_mid = env.s
+        # a scalar step in between, then learning resumes from the learnt table
+        s3, r3, done3, info3 = env.step(pi[env.s])
+        k3, d3 = len(trace), feed.k
+        Q4, i4 = ref_psrs.qlearn_psrs(env, n_episodes=6, behavior_policy=ref_tabular.epsilon_greedy_policy, gamma=0.9,
+                                      alpha=0.2, epsilon=0.1, Q_init=Q1)
+        k4, d4, t4 = len(trace), feed.k, ties.k
+        Q5, i5 = ref_psrs.expSARSA_psrs(env, n_episodes=5, pi=pi, gamma=0.9, alpha=0.2)
+        k5, d5 = len(trace), feed.k
+    finally:
+        np.random.choice = saved
+    out.update(trace=np.array(trace, dtype=np.int64), marks=np.array([k1, k2, k3, k4, k5]), draws=np.array([d1, d2, d3, d4, d5]),
+               ties=np.array([t1, t4]), eps_list=np.array(eps_list), alpha_list=np.array(alpha_list),
+               Q1=Q1, Gs1=i1["Gs"], TD1=i1["TD_errors"], Gs2=Gs2, len2=len2, s_mid=np.array(s_mid), s3=np.array(s3),
+               Q4=Q4, Gs4=i4["Gs"], Q5=Q5, Gs5=i5["Gs"])
+    save("back_to_back", **out)
+
+
+def case_learner_curves():
+    """north_star's third bar: learning curves of the LEARNER under each side's own RNG.  The unmodified `qlearn_psrs`
+    (psrs.py:119-185) with the reference's epsilon-greedy policy runs 320 times; run i re-seeds the reference's own
+    generators (`reset_sampler(seed=5000+i)` -> rejection uniforms from NumPy's PCG64; `np.random.seed(i)` -> MT19937
+    tie-breaks) and follows the data order of GPU replica 10**7 + i: log order in every queue, consumed as a ring from the
+    documented per-(replica, state) offset (`env.queues` / `env.init_queue` are public lists)."""
+    H = _helpers()
+    rng = np.random.default_rng(2024)
+    N, nS, nA, E, RUNS, RING_SEED = 20000, 6, 4, 12, 320, 11
+    log = make_log(rng, N, nS, nA, ep_len=12)
+    # rewards that depend on (state, action), so that what the learner has learnt changes the returns it collects
+    r_table = rng.normal(size=(nS, nA))
+    log["r"] = (r_table[log["z"], log["a"]] + 0.3 * rng.normal(size=N)).astype(np.float32)
+    pb_rows = {int(z): log["p_log"][i] for i, z in enumerate(log["z"])}
+    out = dict(z=log["z"].astype(np.uint8), z_next=log["z_next"].astype(np.uint8), a=log["a"].astype(np.uint8), r=log["r"],
+               done=log["done"], t=log["t"].astype(np.int32), pb_state=np.stack([pb_rows[z] for z in range(nS)]),
+               ring_seed=np.array(RING_SEED), replica_id0=np.array(10**7), n_episodes=np.array(E),
+               gamma=np.array(0.95), alpha=np.array(0.2), epsilon=np.array(0.3))
+    assert np.array_equal(out["pb_state"][log["z"]], log["p_log"])
+    rows, id2row = legacy_tuples(log)
+    lens = np.bincount(log["z"], minlength=nS)
+    n_init = int((log["t"] == 0).sum())
+    Gs = np.full((RUNS, E), np.nan)
+    n_ret = np.zeros(RUNS, dtype=np.int64)
+    acc = np.zeros(RUNS, dtype=np.int64)
+    for i in range(RUNS):
+        rid = 10**7 + i
+        env = ref_psrs.PSRS(rows, nS=nS, nA=nA)
+        env.reset_sampler(seed=5000 + i)
+        for zz, q in env.queues.items():
+            q.sort(key=lambda e: id2row[id(e[7])])                      # back to log order ...
+            o = H.ring_start(RING_SEED, rid, zz, int(lens[zz]))
+            q[:] = q[o:] + q[:o]                                         # ... consumed as a ring from the replica's offset
+        first = [(int(log["z"][j]), int(log["z"][j])) for j in np.nonzero(log["t"] == 0)[0]]
+        o = H.init_ring_start(RING_SEED, rid, n_init)
+        env.init_queue[:] = first[o:] + first[:o]
+        np.random.seed(i)
+        Q, info = ref_psrs.qlearn_psrs(env, n_episodes=E, behavior_policy=ref_tabular.epsilon_greedy_policy, gamma=0.95,
+                                       alpha=0.2, epsilon=0.3)
+        g = np.asarray(info["Gs"], dtype=np.float64)
+        Gs[i, :g.size] = g
+        n_ret[i] = g.size
+        acc[i] = len(info["memory"])
+    out.update(ref_Gs=Gs, ref_n_returns=n_ret, ref_accepted=acc)
+    save("learner_curves", **out)
+
+
 if __name__ == "__main__":
+    only = sys.argv[1:]                   # e.g. `make_golden.py learner_curves` regenerates one fixture
+    if only:
+        for name in only:
+            globals()["case_" + name]()
+        sys.exit(0)
+    case_learner_curves()
     case_recorder()
     case_seeded_walk()
     case_drivers()

@@ -116,6 +116,53 @@ def test_drivers_with_reference_signatures(ob, golden, case):
     assert Q2.shape == (nS, nA) and len(info2["Gs"]) <= 5 and info2["TD_errors"].size == len(info2["memory"])
 
 
+def test_back_to_back_drivers_on_one_env_match_reference(ob, golden):
+    """Learn, evaluate, take a scalar step, learn on from the learnt table, then expected SARSA — all on ONE env without
+    reset_sampler, as the unmodified reference did when tests/golden/back_to_back.npz was recorded: every driver call counts
+    its episodes from 0 and keeps consuming the queues and the uniform stream where the previous call stopped."""
+    from offsim4rl_b200.evaluators.psrs import PSRS, qlearn_psrs, expSARSA_psrs, evalMC_psrs
+    from offsim4rl_b200.agents import tabular
+    g = golden("back_to_back")
+    nS, nA = g["pi"].shape
+    env = PSRS(_legacy(g), nS=nS, nA=nA)
+    env.reset_sampler(seed=int(g["sampler_seed"]))
+    env.feed_uniforms(g["U"])
+    env.feed_ties(g["T"])
+    k1, k2, k3, k4, k5 = (int(v) for v in g["marks"])
+    eps_list, alpha_list = list(g["eps_list"]), list(g["alpha_list"])
+
+    def same_rows(memory, lo, hi):
+        rows = g["trace"][lo:hi]
+        assert len(memory) == hi - lo
+        assert [int(m[1]) for m in memory] == [int(g["a"][r]) for r in rows]
+        assert [float(m[2]) for m in memory] == [float(g["r"][r]) for r in rows]
+
+    # schedules defined on [0, n_episodes) only, like the reference's lazy calls (psrs.py:158,168)
+    Q1, i1 = qlearn_psrs(env, n_episodes=10, behavior_policy=tabular.epsilon_greedy_policy, gamma=0.9,
+                         alpha=lambda e: alpha_list[e], epsilon=lambda e: eps_list[e])
+    same_rows(i1["memory"], 0, k1)
+    assert np.array_equal(Q1, g["Q1"]) and np.array_equal(i1["TD_errors"], g["TD1"])
+    np.testing.assert_allclose(i1["Gs"], g["Gs1"], rtol=1e-5, atol=1e-5)
+    assert int(env._sim.draws[0]) == int(g["draws"][0]) and int(env._sim.ties[0]) == int(g["ties"][0])
+    Gs2, len2 = evalMC_psrs(env, n_episodes=12, pi=g["pi"], gamma=0.95)
+    assert np.array_equal(len2, g["len2"]) and Gs2.size == g["Gs2"].size
+    np.testing.assert_allclose(Gs2, g["Gs2"], rtol=1e-5, atol=1e-5)
+    assert int(env._sim.draws[0]) == int(g["draws"][1]) and int(env.s) == int(g["s_mid"])
+    s3, r3, d3, info3 = env.step(g["pi"][env.s])                              # the env is an ordinary env in between
+    assert int(s3) == int(g["s3"]) and int(env._sim.draws[0]) == int(g["draws"][2])
+    assert float(r3) == float(g["r"][g["trace"][k2]])
+    Q4, i4 = qlearn_psrs(env, n_episodes=6, behavior_policy=tabular.epsilon_greedy_policy, gamma=0.9, alpha=0.2, epsilon=0.1,
+                         Q_init=Q1)
+    same_rows(i4["memory"], k3, k4)
+    assert np.array_equal(Q4, g["Q4"]) and i4["Gs"].size == g["Gs4"].size
+    assert int(env._sim.draws[0]) == int(g["draws"][3]) and int(env._sim.ties[0]) == int(g["ties"][1])
+    Q5, i5 = expSARSA_psrs(env, n_episodes=5, pi=g["pi"], gamma=0.9, alpha=0.2)
+    same_rows(i5["memory"], k4, k5)
+    np.testing.assert_allclose(Q5, g["Q5"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(i5["Gs"], g["Gs5"], rtol=1e-5, atol=1e-5)
+    assert int(env._sim.draws[0]) == int(g["draws"][4])
+
+
 def test_generic_host_loop_equals_fused_kernel(ob, golden):
     """The host-driven loop (arbitrary policy callables) and the fused kernel implement the same algorithm."""
     from offsim4rl_b200.evaluators.psrs import PSRS, expSARSA_psrs, evalMC_psrs

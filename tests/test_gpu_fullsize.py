@@ -1,8 +1,12 @@
 """BASELINE.json's full sizes (C4: 1e8 transitions, 10k states, 4 actions, 125k replicas per GPU; C5: 1000 states,
-near-deterministic behaviour policy) checked through size-independent properties — the oracle cannot run here:
-the bucketing is a stable sorting permutation that packed every field of every row, hot records decode to the
-records, runs conserve their counters, are idempotent and invariant under replica sharding, and every accelerated
-layout (AoS state, hot records, time slices) reproduces the plain one bit for bit."""
+near-deterministic behaviour policy).  Two kinds of checks:
+  * against the ORACLE: oracle/ols_oracle.c (float32-learner mode, pinned to the reference by tests/test_oracle_c.py)
+    buckets the host copy of the same 1e8-row log and runs a few hundred SAMPLED global replica ids; the production
+    kernels (hot records, AoS state, one lane per replica, time slices) must match them draw for draw — accepted rows,
+    pops, ties, returns and the float32 Q tables bit for bit;
+  * size-independent properties over ALL replicas: the bucketing is a stable sorting permutation that packed every
+    field of every row, hot records decode to the records, runs conserve their counters, are idempotent and invariant
+    under replica sharding, and every accelerated layout reproduces the plain one bit for bit."""
 import numpy as np
 import pytest
 
@@ -40,6 +44,45 @@ def c4(ob):
                          terminal=cols["terminal"], p_log=cols["p_log"], steps=cols["steps"], n_buckets=NS, z_offset=0,
                          hot_records=True)
     return cols, log
+
+
+def _host_log(cols, nS):
+    """The same log on the host, bucketed by the C oracle (4.5 GB of host memory at 1e8 rows)."""
+    from oracle import c_oracle as CO
+    h = {k: v.cpu().numpy() for k, v in cols.items()}
+    return CO.Log(z=h["z"], z_next=h["z_next"], action=h["action"], reward=h["reward"], terminal=h["terminal"], p_log=h["p_log"],
+                  steps=h["steps"], n_buckets=nS)
+
+
+@pytest.fixture(scope="module")
+def c4_host(c4):
+    return _host_log(c4[0], NS)
+
+
+def test_c4_production_learner_matches_c_oracle_on_sampled_replicas(ob, c4, c4_host):
+    """The benchmarked C4 configuration at full size (1e8 rows, 10k states, 125k replicas on this GPU, float32 Q, hot
+    records, AoS state, one lane per replica, auto time slices) against the C oracle on 320 sampled global replica ids."""
+    import torch
+    from oracle import c_oracle as CO
+    cols, log = c4
+    clog = c4_host
+    assert np.array_equal(log.offsets.cpu().numpy(), clog.offsets)
+    assert np.array_equal(log.order[:4096].cpu().numpy(), clog.order[:4096]) and np.array_equal(log.order[-4096:].cpu().numpy(), clog.order[N - 4096:N])
+    R, T, id0 = 125_000, 300, 3 * 125_000                      # the shard of rank 3 of 8
+    sim = ob.BatchedPSRS(log, R, rng="philox", seed=1234, ring=True, ring_seed=99, replica_id0=id0, lanes=1, aos_state=True)
+    res = sim.run_qlearn(NS, 511, gamma=0.99, alpha=0.1, epsilon=0.1, max_steps=T, ep_cap=512, trace_cap=T)
+    sample = np.unique(np.r_[0, R - 1, np.random.default_rng(5).integers(0, R, 320)])
+    ref = CO.run(clog, sample.size, CO.QLEARN, NS, 511, gamma=0.99, alpha=0.1, epsilon=0.1, seed=1234, ring=True, ring_seed=99,
+                 max_steps=T, ep_cap=512, trace_cap=T, threads=16, q_f32=True, replica_ids=id0 + sample)
+    idx = torch.as_tensor(sample, device=res.Gs.device)
+    assert np.array_equal(res.trace_row[idx].cpu().numpy(), ref["trace_row"])            # bit-exact accepted rows
+    assert np.array_equal(res.accepted[idx].cpu().numpy(), ref["accepted"]) and bool((ref["accepted"] == T).all())
+    assert np.array_equal(res.pops[idx].cpu().numpy(), ref["pops"]) and np.array_equal(sim.ties[idx].cpu().numpy(), ref["ties"])
+    assert np.array_equal(res.n_returns[idx].cpu().numpy(), ref["n_returns"])
+    mask = np.arange(512)[None, :] < ref["n_returns"][:, None]
+    np.testing.assert_allclose(res.Gs[idx].cpu().numpy()[mask], ref["Gs"][mask], rtol=1e-12, atol=1e-12)
+    assert np.array_equal(res.lengths[idx].cpu().numpy()[mask], ref["lengths"][mask])
+    assert np.array_equal(res.q_rows(sample).cpu().numpy(), ref["Q"])                    # float32 Q tables, bit for bit
 
 
 def test_c4_bucketing_is_a_stable_sort_that_packed_every_field(ob, c4):
@@ -145,6 +188,16 @@ def test_c5_evaluation_over_hot_records_at_full_size(ob):
         torch.cuda.empty_cache()
     for a, b in zip(*outs):
         assert torch.equal(a, b)
+    # against the C oracle on sampled replicas (the streaming reject chains: ~750 pops per accepted transition)
+    from oracle import c_oracle as CO
+    clog = _host_log(cols, nS)
+    sample = np.unique(np.r_[0, R - 1, np.random.default_rng(6).integers(0, R, 256)])
+    ref = CO.run(clog, sample.size, CO.FIXED_PI, nS, 511, gamma=0.99, pi=pi, seed=4321, ring=True, ring_seed=7, max_steps=T,
+                 ep_cap=512, trace_cap=T, threads=16, replica_ids=sample)
+    idx = torch.as_tensor(sample, device=outs[0][0].device)
+    assert np.array_equal(outs[0][2][idx].cpu().numpy(), ref["trace_row"])               # bit-exact accepted rows
+    assert np.array_equal(outs[0][0][idx].cpu().numpy(), ref["pops"]) and np.array_equal(outs[0][1][idx].cpu().numpy(), ref["accepted"])
+    np.testing.assert_allclose(outs[0][3][idx].cpu().numpy(), ref["Gs"].sum(1), rtol=1e-12, atol=1e-12)
     pops, acc = outs[0][0].double().sum(), outs[0][1].double().sum()
     assert bool((outs[0][1] == T).all()) and 500 < float(pops / acc) < 1100          # one accept per ~750 pops (M = 750)
 

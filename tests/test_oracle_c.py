@@ -42,6 +42,33 @@ def test_c_qlearn_matches_reference_golden(golden, case, tag):
         np.testing.assert_allclose(out["Gs"][r, :ne], g[f"ql_{tag}_Gs"], rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("case", DRIVER_CASES)
+@pytest.mark.parametrize("tag", ["const", "sched"])
+def test_c_float32_learner_matches_reference_on_a_float32_table(golden, case, tag):
+    """The float32 learner (the GPU production mode): the reference's own update lines psrs.py:165-168 run on a float32 Q
+    table (tests/golden/make_golden.py `F32Table`) — Q, TD errors, accepted rows, draw and tie counts bit for bit."""
+    g, g32 = golden(case), golden(case + "_f32q")
+    nS, nA = g["pi"].shape
+    log, order, init = _clog(g, int(g["sampler_seed"]))
+    eps, alpha = (0.2, 0.1) if tag == "const" else (g["ql_sched_eps"], g["ql_sched_alpha"])
+    out = CO.run(log, 2, CO.QLEARN, nS, 25, gamma=0.9, alpha=alpha, epsilon=eps, u_feed=g["U"], tie_feed=g["T"],
+                 trace_cap=log.n_rows, order=order, init_row=init, threads=2, q_f32=True)
+    n = g32[f"ql_{tag}_trace"].size
+    assert g32[f"ql_{tag}_Q"].dtype == np.float32 and out["Q"].dtype == np.float32
+    for r in range(2):
+        assert out["accepted"][r] == n
+        assert np.array_equal(out["trace_row"][r, :n], g32[f"ql_{tag}_trace"])
+        assert out["draws"][r] == int(g32[f"ql_{tag}_draws"]) and out["ties"][r] == int(g32[f"ql_{tag}_ties"])
+        assert np.array_equal(out["Q"][r], g32[f"ql_{tag}_Q"])
+        assert np.array_equal(out["td_error"][r, :n].astype(np.float32), g32[f"ql_{tag}_TD"])
+        assert np.array_equal(out["td_error"][r, :n], g32[f"ql_{tag}_TD"].astype(np.float64))
+        ne = out["n_returns"][r]
+        assert ne == g32[f"ql_{tag}_Gs"].size
+        np.testing.assert_allclose(out["Gs"][r, :ne], g32[f"ql_{tag}_Gs"], rtol=1e-5, atol=1e-5)
+    # the float32 and float64 learners really differ on these cases (the fixture is not vacuous)
+    assert not np.array_equal(g32[f"ql_{tag}_Q"].astype(np.float64), g[f"ql_{tag}_Q"])
+
+
 @pytest.mark.parametrize("case", DRIVER_CASES + ["drivers_float_a"])
 def test_c_evalmc_and_expsarsa_match_reference_golden(golden, case):
     g = golden(case)

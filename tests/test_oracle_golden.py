@@ -220,3 +220,46 @@ def test_psrs_exo_oracle_matches_reference(golden, seed):
             row = env.reset(episode)
             obs.append(-1 if row is None else int(g["z"][row]) * nX + int(g["x"][row]))
     assert np.array_equal(trace, g[f"trace_{seed}"]) and np.array_equal(obs, g[f"obs_{seed}"])
+
+
+@pytest.mark.parametrize("case", DRIVER_CASES)
+@pytest.mark.parametrize("tag", ["const", "sched"])
+def test_qlearn_float32_table(golden, case, tag):
+    """The float32 learner: the reference's own update lines on a float32 Q table (make_golden.py `F32Table`)."""
+    g, g32 = golden(case), golden(case + "_f32q")
+    nS, nA = g["pi"].shape
+    env = _env(g, n_buckets=nS, seed=int(g["sampler_seed"]), uniforms=O.FeedUniforms(g["U"]))
+    ties = O.FeedTies(g["T"])
+    eps, alpha = (0.2, 0.1) if tag == "const" else ((lambda e: 1.0 / (1 + e)), (lambda e: 0.5 / (1 + 0.1 * e)))
+    with np.errstate(all="ignore"):
+        Q, info = O.qlearn(env, 25, gamma=0.9, alpha=alpha, epsilon=eps, ties=ties, nS=nS, nA=nA, q_dtype=np.float32)
+    assert Q.dtype == np.float32 and np.array_equal(Q, g32[f"ql_{tag}_Q"])
+    assert np.array_equal(info["trace"], g32[f"ql_{tag}_trace"])
+    assert np.array_equal(info["TD_errors"], g32[f"ql_{tag}_TD"].astype(np.float64))
+    assert env.uniforms.k == int(g32[f"ql_{tag}_draws"]) and ties.k == int(g32[f"ql_{tag}_ties"])
+
+
+def test_back_to_back_drivers_on_one_env(golden):
+    """Several drivers on one env without reset_sampler (tests/golden/back_to_back.npz): every call counts its episodes from
+    0 and keeps consuming the queues and the streams where the previous call stopped."""
+    g = golden("back_to_back")
+    nS, nA = g["pi"].shape
+    env = _env(g, n_buckets=nS, seed=int(g["sampler_seed"]), uniforms=O.FeedUniforms(g["U"]))
+    ties = O.FeedTies(g["T"])
+    k1, k2, k3, k4, k5 = (int(v) for v in g["marks"])
+    eps_list, alpha_list = list(g["eps_list"]), list(g["alpha_list"])
+    Q1, i1 = O.qlearn(env, 10, gamma=0.9, alpha=lambda e: alpha_list[e], epsilon=lambda e: eps_list[e], ties=ties, nS=nS, nA=nA)
+    assert np.array_equal(i1["trace"], g["trace"][:k1]) and np.array_equal(Q1, g["Q1"]) and np.array_equal(i1["TD_errors"], g["TD1"])
+    assert env.uniforms.k == int(g["draws"][0]) and ties.k == int(g["ties"][0])
+    Gs2, len2, tr2 = O.evalmc(env, 12, pi=g["pi"], gamma=0.95)
+    assert np.array_equal(tr2, g["trace"][k1:k2]) and np.array_equal(len2, g["len2"])
+    np.testing.assert_allclose(Gs2, g["Gs2"], rtol=1e-5, atol=1e-5)
+    assert int(env.cur_s) == int(g["s_mid"])
+    row = env.step(g["pi"][int(env.cur_s)])
+    assert row == int(g["trace"][k2]) and int(env.cur_s) == int(g["s3"]) and env.uniforms.k == int(g["draws"][2])
+    Q4, i4 = O.qlearn(env, 6, gamma=0.9, alpha=0.2, epsilon=0.1, ties=ties, nS=nS, nA=nA, q_init=Q1)
+    assert np.array_equal(i4["trace"], g["trace"][k3:k4]) and np.array_equal(Q4, g["Q4"])
+    Q5, i5 = O.expsarsa(env, 5, pi=g["pi"], gamma=0.9, alpha=0.2, nS=nS, nA=nA)
+    assert np.array_equal(i5["trace"], g["trace"][k4:k5])
+    np.testing.assert_allclose(Q5, g["Q5"], rtol=1e-12, atol=1e-14)
+    assert env.uniforms.k == int(g["draws"][4])
