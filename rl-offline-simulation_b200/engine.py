@@ -541,8 +541,9 @@ class BatchedPSRS:
                 tab = aos if idx is None else aos[idx]
                 live = (tab.view(torch.int32)[:, :, 1] == epoch).unsqueeze(-1)
                 return torch.where(live, tab[:, :, 4:4 + nA], torch.zeros((), dtype=torch.float32, device=aos.device))
-            # the per-replica counters are SNAPSHOTS: a later run / restart on this block does not change a result already
-            # handed out (Gs, lengths and the trace buffers are the result's own unless passed back through `outputs=`)
+        # the per-replica counters are SNAPSHOTS: a later run / restart on this block does not change a result already
+        # handed out (Gs, lengths and the trace buffers are the result's own unless passed back through `outputs=`)
+        with torch.cuda.device(dev):
             return RunResult(_Q=Q, _q_fn=q_fn, Gs=Gs, lengths=lengths, n_returns=self.ep_index.clone(),
                              n_lengths=self.ep_len_count.clone(), status=self.status.clone(), accepted=self.accepted.clone(),
                              pops=self.pops.clone(), trace_row=trace_row, td_error=td)

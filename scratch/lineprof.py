@@ -2,8 +2,8 @@
 import csv, re, collections, subprocess, sys, os
 rep, so, kernel_substr = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 45
-os.system("rm -rf /root/repo/gpurun_out/elf2 && mkdir -p /root/repo/gpurun_out/elf2")
-subprocess.run(f"cd /root/repo/gpurun_out/elf2 && cuobjdump -xelf all {so} > /dev/null 2>&1", shell=True)
+ELF = "/tmp/ols_elf"; os.makedirs(ELF, exist_ok=True)
+subprocess.run(f"cd {ELF} && cuobjdump -xelf all {so} > /dev/null 2>&1", shell=True)
 src_csv = subprocess.run(f"ncu -i {rep} --page source --csv", shell=True, capture_output=True, text=True).stdout
 rows = list(csv.reader(src_csv.splitlines()))
 kname = rows[0][1]
@@ -12,15 +12,15 @@ h = rows[hi]; ci = h.index('Instructions Executed'); sm = h.index('# Samples')
 base = int(rows[hi + 1][0], 16)
 # find cubin + mangled name
 target = None
-for f in os.listdir("/root/repo/gpurun_out/elf2"):
+for f in os.listdir(ELF):
     if not f.endswith(".cubin"): continue
-    txt = subprocess.run(f"cuobjdump -elf /root/repo/gpurun_out/elf2/{f} | grep -o '\\.text\\.[A-Za-z0-9_$]*'", shell=True, capture_output=True, text=True).stdout
+    txt = subprocess.run(f"cuobjdump -elf " + ELF + f"/{f} | grep -o '\\.text\\.[A-Za-z0-9_$]*'", shell=True, capture_output=True, text=True).stdout
     for name in set(txt.split()):
         if kernel_substr in name:
             target = (f, name[len(".text."):])
 if not target:
     print("kernel not found"); sys.exit(1)
-dis = subprocess.run(f"nvdisasm -g /root/repo/gpurun_out/elf2/{target[0]}", shell=True, capture_output=True, text=True).stdout.split("\n")
+dis = subprocess.run("nvdisasm -g " + ELF + f"/{target[0]}", shell=True, capture_output=True, text=True).stdout.split("\n")
 start = [i for i, l in enumerate(dis) if l.strip().startswith('.section') and '.text.' + target[1] in l][0]
 end = [i for i in range(start + 1, len(dis)) if dis[i].strip().startswith('.section')][0]
 cur = None; a2l = {}
