@@ -323,6 +323,8 @@ def main():
     ap.add_argument("--prefetch", type=int, default=-1)
     ap.add_argument("--ppl", type=int, default=0, help="records per lane per round (0 = auto)")
     ap.add_argument("--slices", type=int, default=-1, help="time slices of the fused run: -1 auto, 0 off, k forced")
+    ap.add_argument("--hot-bytes", type=int, default=0, help="hot record size: 8 or 16 (0 = 16 for the one-lane Q-learner, else 8)")
+    ap.add_argument("--batch-lanes", type=int, default=0, help="one-lane learner: lanes per update batch (0 = library default)")
     ap.add_argument("--no-hot", action="store_true", help="pop from the 32-byte records only (no 8-byte hot records)")
     ap.add_argument("--no-aos", action="store_true", help="separate cursor / Q arrays instead of one 32-byte entry per (replica, state)")
     ap.add_argument("--no-ring", action="store_true", help="all replicas consume the queues from slot 0 (L2-resident gather)")
@@ -377,15 +379,17 @@ def main():
     torch.cuda.synchronize()
     # learners: hot records need the AoS state and give nothing when the state fits L2 (c2); fixed-policy evaluation (c5): always
     use_hot = nA <= 4 and not args.no_hot and ((qlearn and not args.no_aos and args.workload == "c4") or not qlearn)
+    # the one-thread-per-replica Q-learner reads 16-byte hot records (+ reward, next state, terminal); evaluation 8-byte ones
+    hot_kind = (args.hot_bytes or (16 if (qlearn and wl["lanes"] == 1) else 8)) if use_hot else False
     log = ob.BucketedLog(z=cols["z"], z_next=cols["z_next"], action=cols["action"], reward=cols["reward"],
                          terminal=cols["terminal"], p_log=cols["p_log"], steps=cols["steps"], n_buckets=nS, z_offset=0, device=dev,
-                         keep_columns=True, hot_records=use_hot)
+                         keep_columns=True, hot_records=hot_kind)
     bucket_ms = log.time_bucketing(3)       # ols_bucket + ols_init_queue, CUDA events on the launching stream
     log.drop_columns()
     rec_bytes = log.rec_bytes
     bucket_bytes = N * (12 + 17 + 4 * nA + rec_bytes)   # z twice + order, log columns once, record written once
     sim = ob.BatchedPSRS(log, R, rng="philox", seed=1234, ring=not args.no_ring, ring_seed=99, replica_id0=rank * R, lanes=wl["lanes"], prefetch=args.prefetch, pops_per_lane=args.ppl,
-                         aos_state=(qlearn and nA <= 4 and not args.no_aos), slices=args.slices)
+                         aos_state=(qlearn and nA <= 4 and not args.no_aos), slices=args.slices, batch_lanes=args.batch_lanes)
     use_aos = qlearn and nA <= 4 and not args.no_aos
     Q = torch.zeros((R, nS, nA), dtype=torch.float32, device=dev) if (qlearn and not use_aos) else None
     res = None
@@ -485,7 +489,7 @@ def main():
             c, ev = cur
             torch.cuda.current_stream().wait_event(ev)
             lg = ob.BucketedLog(z=c["z"], z_next=c["z_next"], action=c["action"], reward=c["reward"], terminal=c["terminal"],
-                                p_log=c["p_log"], steps=c["steps"], n_buckets=nS, z_offset=0, device=dev, hot_records=use_hot)
+                                p_log=c["p_log"], steps=c["steps"], n_buckets=nS, z_offset=0, device=dev, hot_records=hot_kind)
             sim.restart(lg)
             if Q is not None:
                 Q.zero_()

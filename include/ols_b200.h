@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define OLS_ABI_VERSION 1
+#define OLS_ABI_VERSION 2
 
 /* ---- return codes ------------------------------------------------------------------------- */
 enum {
@@ -117,6 +117,12 @@ typedef struct ols_queues {
                                  images of the record's probabilities plus its action — all the accept rule needs for
                                  all but ~5e-4 of the pops, so the fused run reads 8 instead of 32 bytes per rejected
                                  record.  Filled by ols_bucket / ols_shuffle_queues when non-NULL.               */
+  int32_t hot_bytes;          /* size of one hot record: 8 (above; 0 means 8), or 16 = the same 8 bytes followed by
+                                 { float reward; uint32 z_next (bits 0..30, two's complement) | terminal << 31 } — all an
+                                 ACCEPTED pop needs as well, so the one-lane float32 Q-learner (ols_run with lanes = 1,
+                                 state_aos, Philox uniforms) never reads the 32-byte record on its fast path.  Every other
+                                 kernel ignores 16-byte hot records and pops from the full records.                */
+  int32_t _pad;
 } ols_queues_t;
 
 /* ---- a block of independent simulation replicas ------------------------------------------ *
@@ -195,6 +201,10 @@ typedef struct ols_run {
                                  library decide.  Results do not depend on it.                                 */
   int32_t state_epoch;        /* state_aos: only entries whose epoch word equals this value are live, all others
                                  read as cursor 0 / Q 0 — a restart bumps the epoch instead of clearing the table */
+  int32_t batch_lanes;        /* one-lane learner over 16-byte hot records: the warp runs the update block once this many
+                                 of its 32 replicas hold an outcome (1..32; 0 = library default, 20).  Results do not
+                                 depend on it.                                                                    */
+  int32_t _pad1;
   int64_t max_steps;          /* > 0: every replica stops after this many accepted transitions in
                                  THIS call and stays resumable (not in the reference)            */
   double gamma;

@@ -10,7 +10,7 @@
  * golden vectors of the unmodified reference) this file is checked in tests/test_oracle_c.py.
  * Parity status: pinned (transitively, via the golden vectors).
  *
- * Uniform streams: either harness-fed arrays or Philox4x32-10 (Salmon et al., SC'11) with the same
+ * Uniform streams: either harness-fed arrays or Philox4x32-7 (Salmon et al., SC'11) with the same
  * (seed, replica, draw) -> value mapping the CUDA path documents, so that CPU and GPU replicas can be
  * compared draw for draw at sizes the python oracle cannot reach.  Replicas are independent: the
  * replicas are self-scheduled over POSIX threads (this is also the multi-core CPU baseline).
@@ -28,9 +28,16 @@ enum { ST_RUNNING = 0, ST_DONE = 1, ST_QUEUE_EMPTY = 2, ST_INIT_EMPTY = 3, ST_NO
 enum { AGENT_FIXED_PI = 0, AGENT_EXPSARSA = 1, AGENT_QLEARN = 2 };
 enum { RNG_FEED = 0, RNG_PHILOX = 2 };
 
-/* ------------------------------------------------------------------------------------------ Philox */
-static void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
-  for (int i = 0; i < 10; ++i) {
+/* ------------------------------------------------------------------------------------------ uniform streams */
+/* Philox4x32 (Salmon et al., SC'11) with 7 rounds.  Stream protocol v2, as documented in
+ * rl-offline-simulation_b200/csrc/ols_common.cuh: draw d of stream `which` of replica `stream` under key `seed` is
+ *     blk = d >> 2, w = d & 3
+ *     hi  = Philox4x32-7({blk_lo, blk_hi, stream_lo, stream_hi ^ (which << 28)},       seed)[w]
+ *     lo  = Philox4x32-7({blk_lo, blk_hi, stream_lo, stream_hi ^ ((which + 2) << 28)}, seed)[w] >> 11
+ *     u   = ((hi << 21) | lo) * 2^-53                       (rejection uniforms: which = 0)
+ * and an arg-max tie-break uses the high word alone: v = hi * 2^-32 (which = 1).                              */
+static void philox4x32_7(uint32_t c[4], uint32_t k0, uint32_t k1) {
+  for (int i = 0; i < 7; ++i) {
     uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
     uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
     uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
@@ -43,12 +50,20 @@ static void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
   }
 }
 
-static double philox_uniform(uint64_t seed, uint64_t stream, uint32_t which, uint64_t d) {
-  uint64_t blk = d >> 1;
+static uint32_t stream_word(uint64_t seed, uint64_t stream, uint32_t which, uint64_t d) {
+  uint64_t blk = d >> 2;
   uint32_t c[4] = {(uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)stream, (uint32_t)(stream >> 32) ^ (which << 28)};
-  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-  uint64_t v = (d & 1) ? (((uint64_t)c[3] << 32) | c[2]) : (((uint64_t)c[1] << 32) | c[0]);
-  return (double)(v >> 11) * (1.0 / 9007199254740992.0);
+  philox4x32_7(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  return c[d & 3];
+}
+
+static double philox_uniform(uint64_t seed, uint64_t stream, uint32_t which, uint64_t d) {
+  uint64_t hi = stream_word(seed, stream, which, d), lo = stream_word(seed, stream, which + 2u, d) >> 11;
+  return (double)((hi << 21) | lo) * (1.0 / 9007199254740992.0);
+}
+
+static double philox_tie(uint64_t seed, uint64_t stream, uint64_t t) {
+  return (double)stream_word(seed, stream, 1u, t) * (1.0 / 4294967296.0);
 }
 
 /* ring offsets (replica decorrelation): 32-bit murmur3-finaliser hashing, as documented in DESIGN.md §6 */
@@ -215,7 +230,7 @@ static void run_replica(const oracle_sim_t* S, int64_t r, int32_t* cursor) {
           if (S->tie_mode == RNG_FEED) {
             if ((int64_t)ties >= S->tie_feed_len) { status = ST_FEED_EMPTY; break; }
             v = S->tie_feed[r * S->tie_stride + (int64_t)ties];
-          } else v = philox_uniform(S->seed, rid, 1u, ties);
+          } else v = philox_tie(S->seed, rid, ties);
           ++ties;
           pick = (int)(v * (double)ncand);
           if (pick > ncand - 1) pick = ncand - 1;

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # OLS_B200_LIB overrides the library path (used to A/B differently tuned builds of the same ABI)
 LIB_PATH = os.environ.get("OLS_B200_LIB") or os.path.join(HERE, "libols_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # return codes
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = 0, 1, 2, 3
@@ -38,7 +38,7 @@ class Log(C.Structure):
 class Queues(C.Structure):
     _fields_ = [("n_rows", i64), ("n_init", i64), ("n_actions", i32), ("n_buckets", i32), ("z_offset", i32),
                 ("rec_bytes", i32), ("offsets", p), ("records", p), ("init_row", p), ("init_z", p),
-                ("init_s", p), ("s_next", p), ("p_log64", p), ("hot", p)]
+                ("init_s", p), ("s_next", p), ("p_log64", p), ("hot", p), ("hot_bytes", i32), ("_pad", i32)]
 
 
 class Replicas(C.Structure):
@@ -57,7 +57,7 @@ class StepOut(C.Structure):
 class Run(C.Structure):
     _fields_ = [("agent", i32), ("n_states", i32), ("q_is_f64", i32), ("pi_is_f64", i32), ("reject_mode", i32),
                 ("compute_mode", i32), ("lanes", i32), ("n_episodes", i32), ("ep_cap", i32), ("stage_smem", i32),
-                ("pops_per_lane", i32), ("prefetch", i32), ("slices", i32), ("state_epoch", i32), ("max_steps", i64), ("gamma", f64), ("alpha", p), ("epsilon", p), ("pi", p), ("Q", p), ("state_aos", p), ("sched", p), ("Gs", p),
+                ("pops_per_lane", i32), ("prefetch", i32), ("slices", i32), ("state_epoch", i32), ("batch_lanes", i32), ("_pad1", i32), ("max_steps", i64), ("gamma", f64), ("alpha", p), ("epsilon", p), ("pi", p), ("Q", p), ("state_aos", p), ("sched", p), ("Gs", p),
                 ("lengths", p), ("trace_row", p), ("td_error", p), ("trace_cap", i64)]
 
 

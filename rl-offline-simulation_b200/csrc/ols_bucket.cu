@@ -316,24 +316,32 @@ __global__ void __launch_bounds__(kBucketThreads, OLS_SCATTER_MINB) scatter_pack
 }
 
 // ---------------------------------------------------------------------------------------- hot records
-// One streaming pass over the packed queues: 32 bytes in, 8 bytes out per record (n_actions <= 4).
+// One streaming pass over the packed queues: 32 bytes in, 8 (or 16) bytes out per record (n_actions <= 4).
+template <int HOT_BYTES>
 __global__ void __launch_bounds__(256) hot_pack_kernel(ols_queues_t q) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < q.n_rows; i += stride) {
     const float4* rp = (const float4*)((const char*)q.records + (size_t)i * 32);
     const float4 p = __ldg(rp);
-    const uint32_t meta = __float_as_uint(__ldg(rp + 1).w);
-    ((uint2*)q.hot)[i] = ols_hot_pack(p, ols_meta_action(meta), q.n_actions);
+    const float4 tail = __ldg(rp + 1);
+    const uint32_t meta = __float_as_uint(tail.w);
+    if (HOT_BYTES == 16)
+      ((uint4*)q.hot)[i] = ols_hot16_pack(p, ols_meta_action(meta), q.n_actions, tail.x, __float_as_int(tail.y), ols_meta_terminal(meta));
+    else
+      ((uint2*)q.hot)[i] = ols_hot_pack(p, ols_meta_action(meta), q.n_actions);
   }
 }
 
 inline int pack_hot(const ols_queues_t* q, cudaStream_t stream) {
   if (q->hot == nullptr || q->n_rows == 0) return OLS_OK;
   OLS_REQUIRE(q->n_actions <= 4 && q->rec_bytes == 32, OLS_ERR_UNSUPPORTED, "hot records need n_actions <= 4");
-  OLS_REQUIRE((uintptr_t)q->hot % 8 == 0, OLS_ERR_INVALID, "hot records must be 8-byte aligned");
+  OLS_REQUIRE(q->hot_bytes == 0 || q->hot_bytes == 8 || q->hot_bytes == 16, OLS_ERR_INVALID, "hot_bytes must be 8 or 16");
+  const int hb = q->hot_bytes == 16 ? 16 : 8;
+  OLS_REQUIRE((uintptr_t)q->hot % hb == 0, OLS_ERR_INVALID, "hot records must be aligned to their size");
   int blocks = ols_div_up(q->n_rows, 256);
   if (blocks > OLS_SM_COUNT * 16) blocks = OLS_SM_COUNT * 16;
-  hot_pack_kernel<<<blocks, 256, 0, stream>>>(*q);
+  if (hb == 16) hot_pack_kernel<16><<<blocks, 256, 0, stream>>>(*q);
+  else hot_pack_kernel<8><<<blocks, 256, 0, stream>>>(*q);
   OLS_LAUNCH_CHECK();
   return OLS_OK;
 }

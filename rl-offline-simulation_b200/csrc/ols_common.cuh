@@ -77,6 +77,11 @@ __device__ __forceinline__ uint2 ols_hot_pack(float4 p, int action, int n_action
   h.y = c[2] | (c[3] << 16) | ((tame ? 1u : 0u) << 15);
   return h;
 }
+// 16-byte hot record: the 8 bytes above + what an ACCEPTED pop needs (reward, next state, terminal flag)
+__device__ __forceinline__ uint4 ols_hot16_pack(float4 p, int action, int n_actions, float reward, int z_next, int terminal) {
+  const uint2 h = ols_hot_pack(p, action, n_actions);
+  return make_uint4(h.x, h.y, __float_as_uint(reward), ((uint32_t)z_next & 0x7fffffffu) | ((terminal ? 1u : 0u) << 31));
+}
 __device__ __forceinline__ void ols_hot_unpack(uint2 h, float (&p)[4], int& action, bool& tame) {
   action = (int)(((h.x >> 15) & 1u) | ((h.x >> 31) << 1));
   tame = ((h.y >> 15) & 1u) != 0u;
@@ -112,8 +117,20 @@ __host__ __device__ inline ols_u4 ols_philox4x32_10(ols_u4 ctr, uint32_t k0, uin
   return ctr;
 }
 
-// The ten round keys of Philox4x32-10 depend on the seed only: the host computes them once per launch and
-// passes them as a kernel parameter, so the device reads them as constant-bank operands.
+// ---- the simulator's uniform streams (protocol v2; restated in oracle/ols_oracle.c and tests/helpers.py) ---------------
+// Draw d of stream `which` (0 = rejection uniforms, 1 = arg-max tie-breaks) of replica `rid` under key `seed` is a 53-bit
+// uniform assembled from two Philox4x32-7 words (7 rounds: the Crush-resistant minimum of Salmon et al.; counter-based, so
+// any lane can evaluate any draw):
+//     blk = d >> 2,  w = d & 3
+//     hi  = Philox4x32-7(ctr = {blk_lo, blk_hi, rid_lo, rid_hi ^ (which << 28)},       key = seed)[w]          32 bits
+//     lo  = Philox4x32-7(ctr = {blk_lo, blk_hi, rid_lo, rid_hi ^ ((which + 2) << 28)}, key = seed)[w] >> 11    21 bits
+//     u   = ((hi << 21) | lo) * 2^-53
+// One block of the first stream carries the high words of FOUR consecutive draws, and those 32 bits are all the accept
+// pre-filter needs (|float(hi) * 2^-32 - u| <= 2^-32 + 2^-24 u); the low word is generated only when a pop falls inside
+// the filter's band or hi < 2^20 — 3e-4 of the pops — so a pop costs a quarter of a 7-round block instead of half of a
+// 10-round one (protocol v1), with the exact float64 decision preserved.
+// The round keys depend on the seed only: the host computes them once per launch and passes them as a kernel parameter,
+// so the device reads them as constant-bank operands.
 struct ols_philox_keys {
   uint32_t k0[10], k1[10];
 };
@@ -128,10 +145,11 @@ inline ols_philox_keys ols_philox_make_keys(uint64_t seed) {
   }
   return K;
 }
-__device__ __forceinline__ ols_u4 ols_philox4x32_10_keyed(ols_u4 ctr, const ols_philox_keys& K) {
+constexpr int OLS_PHILOX_ROUNDS = 7;
+__device__ __forceinline__ ols_u4 ols_philox4x32_7_keyed(ols_u4 ctr, const ols_philox_keys& K) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
 #pragma unroll
-  for (int i = 0; i < 10; ++i) {
+  for (int i = 0; i < OLS_PHILOX_ROUNDS; ++i) {
     const uint64_t p0 = (uint64_t)M0 * ctr.x;  // one IMAD.WIDE each
     const uint64_t p1 = (uint64_t)M1 * ctr.z;
     ols_u4 n;
@@ -143,25 +161,43 @@ __device__ __forceinline__ ols_u4 ols_philox4x32_10_keyed(ols_u4 ctr, const ols_
   }
   return ctr;
 }
+// the block of stream `which` that holds draws 4 * blk .. 4 * blk + 3
+__device__ __forceinline__ ols_u4 ols_stream_block(const ols_philox_keys& K, uint64_t rid, uint32_t which, uint64_t blk) {
+  ols_u4 c;
+  c.x = (uint32_t)blk;
+  c.y = (uint32_t)(blk >> 32);
+  c.z = (uint32_t)rid;
+  c.w = (uint32_t)(rid >> 32) ^ (which << 28);
+  return ols_philox4x32_7_keyed(c, K);
+}
+__device__ __forceinline__ uint32_t ols_u4_word(const ols_u4& o, int w) { return w == 0 ? o.x : w == 1 ? o.y : w == 2 ? o.z : o.w; }
 
 // 53-bit uniform in [0,1) from 64 random bits — the same mapping NumPy's Generator.random() uses.
 __host__ __device__ inline double ols_u64_to_unit(uint64_t v) { return (double)(v >> 11) * (1.0 / 9007199254740992.0); }
+__host__ __device__ inline double ols_u53_to_unit(uint64_t v53) { return (double)v53 * (1.0 / 9007199254740992.0); }
 
-// ols_philox_uniform (below) with host-precomputed round keys
-__device__ __forceinline__ double ols_philox_uniform_keyed(const ols_philox_keys& K, uint64_t stream_id, uint32_t which,
-                                                           uint64_t d) {
-  ols_u4 c;
-  const uint64_t blk = d >> 1;
-  c.x = (uint32_t)blk;
-  c.y = (uint32_t)(blk >> 32);
-  c.z = (uint32_t)stream_id;
-  c.w = (uint32_t)(stream_id >> 32) ^ (which << 28);
-  const ols_u4 o = ols_philox4x32_10_keyed(c, K);
-  const uint64_t v = (d & 1) ? (((uint64_t)o.w << 32) | o.z) : (((uint64_t)o.y << 32) | o.x);
-  return ols_u64_to_unit(v);
+// the exact draw (cold paths: inside the filter's band, tie-breaks, the scalar step): both words
+static __device__ __noinline__ uint64_t ols_stream_u53(const ols_philox_keys& K, uint64_t rid, uint32_t which, uint64_t d) {
+  const uint32_t hi = ols_u4_word(ols_stream_block(K, rid, which, d >> 2), (int)(d & 3));
+  const uint32_t lo = ols_u4_word(ols_stream_block(K, rid, which + 2u, d >> 2), (int)(d & 3));
+  return ((uint64_t)hi << 21) | (uint64_t)(lo >> 11);
+}
+__device__ __forceinline__ double ols_stream_uniform(const ols_philox_keys& K, uint64_t rid, uint32_t which, uint64_t d) {
+  return ols_u53_to_unit(ols_stream_u53(K, rid, which, d));
+}
+// float image of a draw from its high word: |error| <= 2^-32 + 2^-24 u, i.e. < 2^-19 relative once u >= 2^-12; the rare
+// smaller draws (hi < 2^20: 2.4e-4) are converted from all 53 bits instead.  tiny: u < 2^-60, i.e. u == 0 on the 53-bit
+// grid — not resolved by a float32 pre-filter.
+__device__ __forceinline__ float ols_stream_float(const ols_philox_keys& K, uint64_t rid, uint32_t which, uint64_t d, uint32_t hi,
+                                                  bool& tiny) {
+  float f = __uint2float_rn(hi) * 2.3283064365386963e-10f;
+  if (hi < (1u << 20)) f = __ull2float_rn(ols_stream_u53(K, rid, which, d)) * 1.1102230246251565e-16f;
+  tiny = !(f >= 8.6736174e-19f);
+  return f;
 }
 
-// draw `d` of the stream (seed, stream_id, which): one Philox block yields two doubles
+// Philox4x32-10, two doubles per block: the SYNTHETIC-LOG generator's own stream (ols_synth.cu: row i of the benchmark log is a
+// pure function of (seed, i)); the simulator's streams are the 7-round protocol above
 __host__ __device__ inline double ols_philox_uniform(uint64_t seed, uint64_t stream_id, uint32_t which, uint64_t d) {
   ols_u4 c;
   uint64_t blk = d >> 1;

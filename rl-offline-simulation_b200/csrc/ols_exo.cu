@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(kThreads) exo_step_kernel(ols_queues_t qs, ols
         for (int t = 0; t <= L.sub; ++t) stepped = ols_pcg_step(stepped, pcg_inc);
         u = ols_u64_to_unit(ols_pcg_output(stepped));
       } else {
-        u = ols_philox_uniform_keyed(PK, rid, 0u, d);
+        u = ols_stream_uniform(PK, rid, 0u, d);
       }
     }
     bool acc = false;

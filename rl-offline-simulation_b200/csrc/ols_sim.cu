@@ -5,6 +5,9 @@
 
 using namespace ols_sim;
 
+// ols_learner.cu
+cudaError_t ols_launch_learner(const ols_queues_t&, const ols_replicas_t&, const ols_run_t&, const ols_sim::RunLaunch&);
+
 namespace {
 
 __global__ void __launch_bounds__(kThreads) replicas_init_kernel(ols_queues_t q, ols_replicas_t R, const uint64_t* seeds) {
@@ -204,7 +207,17 @@ extern "C" int ols_run(const ols_queues_t* q, const ols_replicas_t* r, const ols
   if (c->agent != OLS_AGENT_QLEARN) OLS_REQUIRE(c->pi, OLS_ERR_INVALID, "ols_run: fixed-policy agents need pi");
   OLS_REQUIRE((!c->trace_row && !c->td_error) || c->trace_cap > 0, OLS_ERR_INVALID, "ols_run: trace taps need trace_cap > 0");
   RunLaunch L;
-  // (the one-lane hot-record learner is built for OLS_MINB_G1 CTAs of OLS_G1_THREADS per SM, see run_kernel's launch bounds)
+  // 16-byte hot records serve the one-lane float32 Q-learner only (ols_learner.cu); every other kernel pops from the full
+  // records (8-byte hot records: the one-lane / lane-group AoS learners and fixed-policy evaluation, see ols_sim_kernels.cuh)
+  const bool hot16 = q->hot && q->hot_bytes == 16;
+  const bool fast_learner = hot16 && c->agent == OLS_AGENT_QLEARN && c->lanes == 1 && c->state_aos && r->rng_mode == OLS_RNG_PHILOX;
+  ols_queues_t q_plain = *q;
+  if (hot16 && !fast_learner) {
+    q_plain.hot = nullptr;
+    q = &q_plain;
+  }
+  OLS_REQUIRE(c->batch_lanes >= 0 && c->batch_lanes <= 32, OLS_ERR_INVALID, "ols_run: batch_lanes must be in [0, 32]");
+  // (the one-lane hot-record learners are built for OLS_MINB_G1 CTAs of OLS_G1_THREADS per SM, see their launch bounds)
   const bool g1_hot = c->lanes == 1 && c->state_aos && q->hot && r->rng_mode == OLS_RNG_PHILOX;
   L.threads = g1_hot ? OLS_G1_THREADS : kThreads;
   const int n_blocks = (int)((r->n_replicas * c->lanes + L.threads - 1) / L.threads);  // one lane group per replica
@@ -236,6 +249,12 @@ extern "C" int ols_run(const ols_queues_t* q, const ols_replicas_t* r, const ols
   int ppl = c->pops_per_lane;
   if (ppl == 0) ppl = (r->rng_mode == OLS_RNG_PCG64 || c->reject_mode == OLS_REJECT_ACCEPT_ALL) ? 1 : 2;
   cudaError_t e;
+  if (fast_learner) {
+    L.smem = 0;
+    e = ols_launch_learner(*q, *r, *c, L);
+    OLS_REQUIRE(e == cudaSuccess, OLS_ERR_CUDA, "ols_run: launch failed: %s", cudaGetErrorString(e));
+    return OLS_OK;
+  }
   switch ((q->n_actions + 3) / 4) {
     case 1: e = ols_launch_run_nv1(*q, *r, *c, L, ppl); break;
     case 2: e = ols_launch_run_nv2(*q, *r, *c, L, ppl); break;

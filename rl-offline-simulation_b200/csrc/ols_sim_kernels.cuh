@@ -261,7 +261,10 @@ __device__ __forceinline__ int pop_round(const ols_queues_t& q, const ols_replic
   constexpr int NA = 4 * NV;
   constexpr int kRec = 16 * (NV + 1);  // record bytes
   constexpr bool accept_all = (RNG == RNGT_NONE);
-  constexpr bool paired = (RNG == RNGT_PHILOX && PPL % 2 == 0);  // one Philox block serves two consecutive pops of a lane
+  // Philox (protocol v2, ols_common.cuh): one block of the stream carries the high words of four consecutive draws.  A
+  // round is aligned so that a lane's PPL pops fall inside ONE block (PPL = 4: a whole block, PPL = 2: half of one); the
+  // slots before `draws` are masked out.
+  constexpr bool blocked = (RNG == RNGT_PHILOX);
   static_assert(RNG != RNGT_PCG64 || PPL == 1, "PCG64 replay is sequential per lane group: one pop per lane");
   static_assert(!accept_all || PPL == 1, "accept-all examines one record per round");
   typedef typename std::conditional<RNG == RNGT_PHILOX, float, double>::type ustore_t;
@@ -273,9 +276,7 @@ __device__ __forceinline__ int pop_round(const ols_queues_t& q, const ols_replic
     result = OLS_QUEUE_EMPTY;
     active = false;
   }
-  // Philox yields two uniforms per block: a paired round is aligned to an even draw index and the slot before
-  // `draws` (if draws is odd) is masked out, so each lane needs exactly one block.
-  const int align = paired ? (int)(draws & 1) : 0;
+  const int align = blocked ? (int)(draws & (uint64_t)(PPL - 1)) : 0;
   const int n_eval = active ? min(accept_all ? 1 : G * PPL - align, remaining) : 0;
   const int k0 = sub * PPL - align;  // queue offset (from the cursor) of this lane's first pop; -1 = masked slot
 
@@ -325,26 +326,17 @@ __device__ __forceinline__ int pop_round(const ols_queues_t& q, const ols_replic
     lack[i] = tiny[i] = false;
   }
   ols_u128 stepped = pcg_s;
-  if (paired) {
+  if (blocked) {
+    bool any = false;
 #pragma unroll
-    for (int j = 0; j < PPL / 2; ++j) {
-      if (valid[2 * j] || valid[2 * j + 1]) {
-        const uint64_t blk = ((draws - (uint64_t)align) >> 1) + (uint64_t)(sub * (PPL / 2) + j);
-        ols_u4 c;
-        c.x = (uint32_t)blk;
-        c.y = (uint32_t)(blk >> 32);
-        c.z = (uint32_t)rid;
-        c.w = (uint32_t)(rid >> 32);
-        const ols_u4 o = ols_philox4x32_10_keyed(c, PK);
-        // float image of u from its top 32 bits: |error| <= 2^-32 + 2^-24 u, i.e. < 2^-19 relative once u >= 2^-12;
-        // the rare smaller draws (2.4e-4) are converted from all 53 bits instead
-        float f0 = __uint2float_rn(o.y) * 2.3283064365386963e-10f, f1 = __uint2float_rn(o.w) * 2.3283064365386963e-10f;
-        if (o.y < (1u << 20)) f0 = __ull2float_rn((((uint64_t)o.y << 32) | o.x) >> 11) * 1.1102230246251565e-16f;
-        if (o.w < (1u << 20)) f1 = __ull2float_rn((((uint64_t)o.w << 32) | o.z) >> 11) * 1.1102230246251565e-16f;
-        u[2 * j] = (ustore_t)f0;
-        u[2 * j + 1] = (ustore_t)f1;
-        tiny[2 * j] = !(f0 >= 8.6736174e-19f);  // u < 2^-60 (incl. 0): not resolved in float32
-        tiny[2 * j + 1] = !(f1 >= 8.6736174e-19f);
+    for (int i = 0; i < PPL; ++i) any = any || valid[i];
+    if (any) {
+      const uint64_t d0 = draws + (uint64_t)(int64_t)k0;      // this lane's first slot: a multiple of PPL
+      const ols_u4 o = ols_stream_block(PK, rid, 0u, d0 >> 2);
+#pragma unroll
+      for (int i = 0; i < PPL; ++i) {
+        const uint32_t hi = (PPL == 4) ? ols_u4_word(o, i) : ols_u4_word(o, (int)(d0 & 3) + i);
+        u[i] = (ustore_t)ols_stream_float(PK, rid, 0u, d0 + (uint64_t)i, hi, tiny[i]);
       }
     }
   } else if (!accept_all) {
@@ -360,8 +352,6 @@ __device__ __forceinline__ int pop_round(const ols_queues_t& q, const ols_replic
           // PCG64 always runs with PPL == 1: pop k needs the group's generator stepped k + 1 times
           for (int t = 0; t <= k; ++t) stepped = ols_pcg_step(stepped, pcg_inc);
           u[i] = (ustore_t)ols_u64_to_unit(ols_pcg_output(stepped));
-        } else {
-          u[i] = (ustore_t)(float)ols_philox_uniform_keyed(PK, rid, 0u, d);
         }
         tiny[i] = !((float)u[i] >= 8.6736174e-19f);  // u < 2^-60 (incl. 0): not resolved by the float32 filter
       }
@@ -391,7 +381,7 @@ __device__ __forceinline__ int pop_round(const ols_queues_t& q, const ols_replic
         const int k = k0 + i;
         uint32_t pos = B.start + (uint32_t)(B.cur + k);
         if (pos >= (uint32_t)B.len) pos -= (uint32_t)B.len;
-        const double ue = (RNG == RNGT_PHILOX) ? ols_philox_uniform_keyed(PK, rid, 0u, draws + (uint64_t)k) : (double)u[i];
+        const double ue = (RNG == RNGT_PHILOX) ? ols_stream_uniform(PK, rid, 0u, draws + (uint64_t)(int64_t)k) : (double)u[i];
         const double* p64 = q.p_log64 ? q.p_log64 + (int64_t)__float_as_int(tail[i].z) * nA : nullptr;
         dec = (int)accept_slow(pn_fn, (const float*)((const char*)q.records + (size_t)(uint32_t)(B.lo + (int32_t)pos) * kRec),
                                p64, nA, a, ue, compute_mode);
@@ -487,7 +477,7 @@ __device__ __forceinline__ int pop_round_hot(const ols_queues_t& q, int G, int s
     result = OLS_QUEUE_EMPTY;
     active = false;
   }
-  const int align = (int)(draws & 1);  // rounds are aligned to an even draw index: each lane needs exactly two Philox blocks
+  const int align = (int)(draws & 3);  // rounds are aligned to a multiple of four draws: each lane needs exactly ONE stream block
   const int n_eval = active ? min(G * PPL - align, remaining) : 0;
   const int k0 = sub * PPL - align;
   uint2 h[PPL];
@@ -509,24 +499,11 @@ __device__ __forceinline__ int pop_round_hot(const ols_queues_t& q, int G, int s
     u[i] = 0.f;
     tiny[i] = false;
   }
+  if (valid[0] || valid[1] || valid[2] || valid[3]) {
+    const uint64_t d0 = draws + (uint64_t)(int64_t)k0;  // a multiple of four
+    const ols_u4 o = ols_stream_block(PK, rid, 0u, d0 >> 2);
 #pragma unroll
-  for (int j = 0; j < PPL / 2; ++j) {
-    if (valid[2 * j] || valid[2 * j + 1]) {
-      const uint64_t blk = ((draws - (uint64_t)align) >> 1) + (uint64_t)(sub * (PPL / 2) + j);
-      ols_u4 c;
-      c.x = (uint32_t)blk;
-      c.y = (uint32_t)(blk >> 32);
-      c.z = (uint32_t)rid;
-      c.w = (uint32_t)(rid >> 32);
-      const ols_u4 o = ols_philox4x32_10_keyed(c, PK);
-      float f0 = __uint2float_rn(o.y) * 2.3283064365386963e-10f, f1 = __uint2float_rn(o.w) * 2.3283064365386963e-10f;
-      if (o.y < (1u << 20)) f0 = __ull2float_rn((((uint64_t)o.y << 32) | o.x) >> 11) * 1.1102230246251565e-16f;
-      if (o.w < (1u << 20)) f1 = __ull2float_rn((((uint64_t)o.w << 32) | o.z) >> 11) * 1.1102230246251565e-16f;
-      u[2 * j] = f0;
-      u[2 * j + 1] = f1;
-      tiny[2 * j] = !(f0 >= 8.6736174e-19f);
-      tiny[2 * j + 1] = !(f1 >= 8.6736174e-19f);
-    }
+    for (int i = 0; i < PPL; ++i) u[i] = ols_stream_float(PK, rid, 0u, d0 + (uint64_t)i, ols_u4_word(o, i), tiny[i]);
   }
   const Policy<NA> P = pol.get();
   bool acc[PPL];
@@ -550,7 +527,7 @@ __device__ __forceinline__ int pop_round_hot(const ols_queues_t& q, int G, int s
         const float full[NA] = {pf.x, pf.y, pf.z, pf.w};
         dec = accept_filter<NA>(P, full, ols_meta_action(meta), u[i], P.ok && !tiny[i] && ols_meta_tame(meta) != 0);
         if (dec == 2) {
-          const double ue = ols_philox_uniform_keyed(PK, rid, 0u, draws + (uint64_t)k);
+          const double ue = ols_stream_uniform(PK, rid, 0u, draws + (uint64_t)(int64_t)k);
           const double* p64 = q.p_log64 ? q.p_log64 + (int64_t)__float_as_int(tl.z) * nA : nullptr;
           dec = (int)accept_slow(pn_fn, (const float*)rp, p64, nA, ols_meta_action(meta), ue, compute_mode);
         }
@@ -978,7 +955,8 @@ __global__ void __launch_bounds__((GT == 1 ? OLS_G1_THREADS : kThreads), (NV == 
             if ((int64_t)ties0 < R.tie_feed_len) v = __ldg(R.tie_feed + rr * R.tie_stride + (int64_t)ties0);
             else have = false;
           } else {
-            v = ols_philox_uniform_keyed(PK, rid, 1u, ties0);
+            // stream 1, high word only: v = hi * 2^-32, so pick = floor(hi * ncand / 2^32) exactly
+            v = (double)ols_u4_word(ols_stream_block(PK, rid, 1u, ties0 >> 2), (int)(ties0 & 3)) * 2.3283064365386963e-10;
           }
           if (!have) {
             new_status = OLS_FEED_EMPTY;

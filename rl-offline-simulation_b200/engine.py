@@ -143,8 +143,13 @@ class BucketedLog:
             self.offsets = torch.empty(n_buckets + 1, dtype=torch.int32, device=dev)
             self.s_next = s_next            # kept resident only when the agent's observation id differs from z
             self.records = torch.empty(max(n, 1) * self.rec_bytes // 4, dtype=torch.float32, device=dev)
-            # 8-byte hot records next to the 32-byte ones (n_actions <= 4): what the fused AoS run reads per rejected pop
-            self.hot = torch.empty(max(n, 1), dtype=torch.int64, device=dev) if (hot_records and n_actions <= 4) else None
+            # hot records next to the 32-byte ones (n_actions <= 4): what the fused runs read per rejected pop.  True / 8 =
+            # 8 bytes (probabilities as halves + action); 16 = those + reward, next state, terminal flag, for the one-lane
+            # float32 Q-learner, which then never reads the 32-byte record on its fast path
+            if hot_records not in (False, True, None, 0, 8, 16):
+                raise ValueError("hot_records must be False, True (8-byte), 8 or 16")
+            self.hot_bytes = 0 if (not hot_records or n_actions > 4) else (16 if hot_records == 16 else 8)
+            self.hot = torch.empty(max(n, 1) * (self.hot_bytes // 8), dtype=torch.int64, device=dev) if self.hot_bytes else None
             init_row = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
             init_z = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
             init_s = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
@@ -159,7 +164,8 @@ class BucketedLog:
             q = abi.Queues(n_rows=n, n_init=0, n_actions=n_actions, n_buckets=n_buckets, z_offset=key_offset,
                            rec_bytes=self.rec_bytes, offsets=_ptr(self.offsets),
                            records=_ptr(self.records), init_row=_ptr(init_row), init_z=_ptr(init_z),
-                           init_s=_ptr(init_s), s_next=_ptr(s_next), p_log64=_ptr(p_log64), hot=_ptr(self.hot))
+                           init_s=_ptr(init_s), s_next=_ptr(s_next), p_log64=_ptr(p_log64), hot=_ptr(self.hot),
+                           hot_bytes=self.hot_bytes, _pad=0)
             abi.check(lib.ols_bucket(C.byref(log_key), C.byref(q), _ptr(scratch), sb, _stream_ptr()))
             abi.check(lib.ols_init_queue(C.byref(log), C.byref(q), _ptr(n_init_dev), _ptr(scratch), sb, _stream_ptr()))
             self.n_init = int(n_init_dev.item())        # one sync: construction is not the step path
@@ -215,7 +221,7 @@ class BucketedLog:
                           z_offset=self.z_offset, rec_bytes=self.rec_bytes, offsets=_ptr(self.offsets),
                           records=_ptr(self.records), init_row=_ptr(self.init_row), init_z=_ptr(self.init_z),
                           init_s=_ptr(self.init_s), s_next=_ptr(self.s_next), p_log64=_ptr(self.p_log64),
-                          hot=_ptr(getattr(self, "hot", None)))
+                          hot=_ptr(getattr(self, "hot", None)), hot_bytes=int(getattr(self, "hot_bytes", 0)), _pad=0)
 
     @property
     def order(self) -> torch.Tensor:
@@ -301,7 +307,7 @@ class BatchedPSRS:
     def __init__(self, log: BucketedLog, n_replicas: int, rng: str = "philox", seed: Optional[int] = 0,
                  seeds=None, u_feed=None, tie_feed=None, reject: str = "default", ring: bool = False,
                  ring_seed: int = 0, replica_id0: int = 0, lanes: int = 4, pops_per_lane: int = 0,
-                 stage_smem: bool = True, prefetch: int = -1, aos_state: bool = False, slices: int = -1):
+                 stage_smem: bool = True, prefetch: int = -1, aos_state: bool = False, slices: int = -1, batch_lanes: int = 0):
         self.lib = abi.load()
         self.log = log
         dev = log.device
@@ -317,6 +323,7 @@ class BatchedPSRS:
         self._epoch = 1                             # live epoch of the AoS entries (a zeroed table holds epoch 0: all stale)
         self.slices = int(slices)                   # time slices of a budgeted fused run: -1 auto, 0/1 off, k > 1 forced
         self._sched = None
+        self.batch_lanes = int(batch_lanes)         # one-lane learner over 16-byte hot records: lanes per update batch (0 = default)
         self.prefetch = int(prefetch)               # rounds ahead prefetched into L2 (<= 0: off; measured neutral on B200)
         self.rng_mode = {"feed": abi.RNG_FEED, "pcg64": abi.RNG_PCG64, "philox": abi.RNG_PHILOX}[rng]
         if seed is None:
@@ -521,7 +528,7 @@ class BatchedPSRS:
             if self._sched is None and self.slices not in (0, 1):
                 n_sched = int(self.lib.ols_run_sched_bytes(R, self.lanes)) // 4
                 self._sched = torch.zeros(max(n_sched, 1), dtype=torch.int32, device=dev)
-            cfg = abi.Run(agent=agent, n_states=n_states, state_epoch=self._epoch, slices=self.slices if max_steps > 0 else 0, sched=_ptr(self._sched), q_is_f64=int(Q is not None and Q.dtype == torch.float64),
+            cfg = abi.Run(agent=agent, n_states=n_states, state_epoch=self._epoch, batch_lanes=self.batch_lanes, _pad1=0, slices=self.slices if max_steps > 0 else 0, sched=_ptr(self._sched), q_is_f64=int(Q is not None and Q.dtype == torch.float64),
                           state_aos=_ptr(self.aos if use_aos else None),
                           pi_is_f64=pi_is_f64, reject_mode=self.reject_mode,
                           compute_mode=abi.COMPUTE_F32 if compute == "f32" else abi.COMPUTE_F64, lanes=self.lanes,

@@ -1,4 +1,4 @@
-"""Pure-python restatements of the product's counter-based streams (Philox4x32-10, ring offsets) as
+"""Pure-python restatements of the product's counter-based streams (Philox4x32-7 stream protocol v2, ring offsets) as
 documented in include/ols_b200.h / DESIGN.md — shared by CPU and GPU tests."""
 
 M32 = 0xFFFFFFFF
@@ -8,9 +8,9 @@ M64 = 0xFFFFFFFFFFFFFFFF
 import numpy as np
 
 
-def philox4x32_10(ctr, k0, k1):
+def philox4x32(ctr, k0, k1, rounds=7):
     c = list(ctr)
-    for _ in range(10):
+    for _ in range(rounds):
         p0 = 0xD2511F53 * c[0]
         p1 = 0xCD9E8D57 * c[2]
         c = [((p1 >> 32) ^ c[1] ^ k0) & M32, p1 & M32, ((p0 >> 32) ^ c[3] ^ k1) & M32, p0 & M32]
@@ -19,12 +19,23 @@ def philox4x32_10(ctr, k0, k1):
     return c
 
 
+def stream_word(seed, stream, which, d):
+    """Word d & 3 of block d >> 2 of stream `which` (protocol v2, csrc/ols_common.cuh): Philox4x32-7."""
+    blk = d >> 2
+    c = philox4x32([blk & M32, (blk >> 32) & M32, stream & M32, ((stream >> 32) & M32) ^ ((which << 28) & M32)],
+                   seed & M32, (seed >> 32) & M32)
+    return c[d & 3]
+
+
 def philox_uniform(seed, stream, which, d):
-    blk = d >> 1
-    c = philox4x32_10([blk & M32, (blk >> 32) & M32, stream & M32, ((stream >> 32) & M32) ^ ((which << 28) & M32)],
-                      seed & M32, (seed >> 32) & M32)
-    v = ((c[3] << 32) | c[2]) if (d & 1) else ((c[1] << 32) | c[0])
-    return (v >> 11) * (1.0 / 9007199254740992.0)
+    """Rejection uniform: 32 high bits from stream `which`, 21 low bits from stream `which + 2`."""
+    hi, lo = stream_word(seed, stream, which, d), stream_word(seed, stream, which + 2, d) >> 11
+    return ((hi << 21) | lo) * (1.0 / 9007199254740992.0)
+
+
+def philox_tie(seed, stream, t):
+    """Arg-max tie-break value: the high word of stream 1 alone."""
+    return stream_word(seed, stream, 1, t) * (1.0 / 4294967296.0)
 
 
 def fmix32(h):

@@ -444,9 +444,12 @@ def test_philox_replicas_match_c_oracle(ob, agent, lanes, ppl, ring):
 
 PROD_LAYOUTS = [
     # lanes, aos_state, hot_records, slices, R, budget
-    (1, True, True, 8, 3000, 900),          # the benchmarked kernel: one lane per replica, hot records, AoS state, time slices
-    (1, True, True, -1, 20000, 1100),       # ... with the library's own slicing decision (more CTAs than SMs -> 2 slices)
+    (1, True, 16, 8, 3000, 900),            # the benchmarked kernel: one thread per replica, 16-byte hot records, AoS state, time slices
+    (1, True, 16, -1, 20000, 1100),         # ... with the library's own slicing decision (more CTAs than SMs -> 2 slices)
+    (1, True, 16, 0, 777, 300),             # ... unsliced, a ragged last warp
+    (1, True, True, 8, 3000, 900),          # the one-lane learner over 8-byte hot records
     (2, True, True, 5, 3000, 700),
+    (2, True, 16, 5, 3000, 700),            # 16-byte hot records are ignored by every other kernel
     (32, True, True, 0, 1500, 400),
     (4, True, False, 3, 3000, 500),         # AoS state over the 32-byte records
     (4, False, False, 0, 3000, 500),        # plain layout
@@ -598,7 +601,7 @@ def test_learner_curve_agrees_with_the_reference_itself_under_independent_rngs_k
     """north_star's third bar for the LEARNER: tests/golden/learner_curves.npz holds the per-episode returns of 320 runs of
     the UNMODIFIED reference `qlearn_psrs` (psrs.py:119-185), each with the reference's own generators (NumPy PCG64
     rejection uniforms, MT19937 tie-breaks); here 6000 GPU replicas learn on the same log with Philox streams (float32 Q,
-    hot records, AoS state, one lane per replica — or the float64 plain layout).  Per episode index: two-sample KS on the
+    16-byte hot records, AoS state, one thread per replica: the benchmarked kernel — or the float64 plain layout).  Per episode index: two-sample KS on the
     returns, and the means of the learning curve within 4 standard errors."""
     import torch
     from scipy.stats import ks_2samp
@@ -608,7 +611,7 @@ def test_learner_curve_agrees_with_the_reference_itself_under_independent_rngs_k
     z = g["z"].astype(np.int64)
     prod = layout == "production"
     log = ob.BucketedLog(z=z, z_next=g["z_next"].astype(np.int64), action=g["a"].astype(np.int64), reward=g["r"], terminal=g["done"],
-                         p_log=g["pb_state"][z], steps=g["t"], n_buckets=nS, hot_records=prod)
+                         p_log=g["pb_state"][z], steps=g["t"], n_buckets=nS, hot_records=16 if prod else False)
     # GPU replica ids continue after the ids whose data order the reference runs followed (10**7 + i, i < 320)
     sim = ob.BatchedPSRS(log, R, rng="philox", seed=424242, ring=True, ring_seed=int(g["ring_seed"]),
                          replica_id0=int(g["replica_id0"]) + 1000, lanes=1 if prod else 4, aos_state=prod)

@@ -64,8 +64,19 @@ def test_c4_production_learner_matches_c_oracle_on_sampled_replicas(ob, c4, c4_h
     records, AoS state, one lane per replica, auto time slices) against the C oracle on 320 sampled global replica ids."""
     import torch
     from oracle import c_oracle as CO
-    cols, log = c4
+    cols, log8 = c4
     clog = c4_host
+    # the benchmark's own layout: 16-byte hot records (bench.py)
+    log = ob.BucketedLog(z=cols["z"], z_next=cols["z_next"], action=cols["action"], reward=cols["reward"],
+                         terminal=cols["terminal"], p_log=cols["p_log"], steps=cols["steps"], n_buckets=NS, z_offset=0,
+                         hot_records=16)
+    assert torch.equal(log.records, log8.records)
+    w16 = log.hot.view(torch.int32).view(-1, 4)[:N]
+    rec = log.records.view(torch.int32).view(-1, 8)[:N]
+    assert torch.equal(w16[:, :2], log8.hot.view(torch.int32).view(-1, 2)[:N])            # the 8-byte hot record ...
+    assert torch.equal(w16[:, 2], rec[:, 4])                                                # ... + reward
+    assert torch.equal(w16[:, 3] & 0x7FFFFFFF, rec[:, 5]) and torch.equal((w16[:, 3] >> 31) & 1, (rec[:, 7] >> 8) & 1)
+    del w16, rec
     assert np.array_equal(log.offsets.cpu().numpy(), clog.offsets)
     assert np.array_equal(log.order[:4096].cpu().numpy(), clog.order[:4096]) and np.array_equal(log.order[-4096:].cpu().numpy(), clog.order[N - 4096:N])
     R, T, id0 = 125_000, 300, 3 * 125_000                      # the shard of rank 3 of 8

@@ -116,11 +116,11 @@ def test_c_philox_ring_replicas_equal_python_oracle_with_same_streams():
                  ring_seed=5, trace_cap=N, threads=3)
     lib = CO.load()
     # restate the streams in python from the documented Philox / ring definitions, via the python oracle
-    from tests.helpers import philox_uniform, ring_start, init_ring_start
+    from tests.helpers import philox_uniform, philox_tie, ring_start, init_ring_start
     for rep in range(R):
         rid = 1000 + rep
         U = [philox_uniform(77, rid, 0, d) for d in range(int(out["draws"][rep]) + 8)]
-        T = [philox_uniform(77, rid, 1, d) for d in range(int(out["ties"][rep]) + 8)]
+        T = [philox_tie(77, rid, d) for d in range(int(out["ties"][rep]) + 8)]
         lens = np.diff(log.offsets)
         starts = [ring_start(5, rid, b, int(lens[b])) if lens[b] else 0 for b in range(nS)]
         env = O.OraclePSRS(z=z, z_next=zn, s=z, s_next=zn, action=a, reward=r, terminal=done, p_log=p_log, steps=t,
@@ -136,7 +136,7 @@ def test_c_agent_ids_sentinel_offset_and_budget_equal_python_oracle():
     """The checker semantics tests/test_gpu_configs.py leans on: agent ids distinct from the queue keys (s = z + 1), the
     CartPole sentinel as bucket 0 (z_offset = 1, z' = -1 on terminal rows) and the step budget — C replicas against
     python-oracle replicas fed the same Philox numbers."""
-    from tests.helpers import philox_uniform
+    from tests.helpers import philox_uniform, philox_tie
     rng = np.random.default_rng(8)
     N, nB, nA, R = 6000, 9, 2, 4
     z = rng.integers(0, nB - 1, N)
@@ -155,7 +155,7 @@ def test_c_agent_ids_sentinel_offset_and_budget_equal_python_oracle():
     for rep in range(R):
         rid = 40 + rep
         U = [philox_uniform(5, rid, 0, d) for d in range(int(out["draws"][rep]) + 8)]
-        T = [philox_uniform(5, rid, 1, d) for d in range(int(out["ties"][rep]) + 8)]
+        T = [philox_tie(5, rid, d) for d in range(int(out["ties"][rep]) + 8)]
         env = O.OraclePSRS(z=z, z_next=zn, s=s, s_next=sn, action=a, reward=r, terminal=done, p_log=p_log, steps=t,
                            n_buckets=nB, z_offset=1, uniforms=O.FeedUniforms(U))
         Q, info = O.qlearn(env, 50, gamma=0.9, alpha=0.2, epsilon=0.2, ties=O.FeedTies(T), nS=nS, nA=nA, max_steps=120)
