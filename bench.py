@@ -102,22 +102,39 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------- CPU legs
-def numpy_log(rows, states, actions, delta, seed=0, p_done=1 / 50):
-    rng = np.random.default_rng(seed + 1)
+def numpy_log(rows, states, actions, delta, seed=0, p_done=1 / 50, chunk=10_000_000):
+    """The synthetic log of the benchmark shape generated on the HOST (the reference arm touches no GPU), in chunks so that
+    the 1e8-row log needs no multi-GB temporaries."""
     pb = behaviour_table(states, actions, delta)
-    z = rng.integers(0, states, rows).astype(np.int32)
-    zn = rng.integers(0, states, rows).astype(np.int32)
-    a = (rng.random(rows)[:, None] > np.cumsum(pb[z], 1)).sum(1).clip(0, actions - 1).astype(np.int32)
-    done = rng.random(rows) < p_done
-    return dict(z=z, z_next=zn, action=a, reward=rng.normal(size=rows).astype(np.float32), terminal=done.astype(np.uint8),
-                p_log=pb[z], steps=np.where(np.r_[True, done[:-1]], 0, 1).astype(np.int32))
+    cum = np.cumsum(pb, 1)
+    out = dict(z=np.empty(rows, np.int32), z_next=np.empty(rows, np.int32), action=np.empty(rows, np.int32),
+               reward=np.empty(rows, np.float32), terminal=np.empty(rows, np.uint8), p_log=np.empty((rows, actions), np.float32),
+               steps=np.empty(rows, np.int32))
+    prev_done = True
+    for k, lo in enumerate(range(0, rows, chunk)):
+        n = min(chunk, rows - lo)
+        rng = np.random.default_rng([seed + 1, k])
+        z = rng.integers(0, states, n).astype(np.int32)
+        sl = slice(lo, lo + n)
+        out["z"][sl] = z
+        out["z_next"][sl] = rng.integers(0, states, n)
+        out["action"][sl] = (rng.random(n)[:, None] > cum[z]).sum(1).clip(0, actions - 1)
+        done = rng.random(n) < p_done
+        out["reward"][sl] = rng.normal(size=n)
+        out["terminal"][sl] = done
+        out["p_log"][sl] = pb[z]
+        out["steps"][sl] = np.where(np.r_[prev_done, done[:-1]], 0, 1)
+        prev_done = bool(done[-1]) if n else prev_done
+    return out
 
 
-def cpu_leg(cols, wl, seconds, threads):
-    """Time the C restatement of the reference's loop (oracle/ols_oracle.c) on `threads` host threads."""
+def cpu_leg(cols, wl, seconds, threads, log=None):
+    """Time the C restatement of the reference's loop (oracle/ols_oracle.c) on `threads` host threads.  Returns the
+    measurement and the bucketed host log (so that repeated legs bucket once; bucketing is untimed)."""
     from oracle import c_oracle as CO
-    log = CO.Log(z=cols["z"], z_next=cols["z_next"], action=cols["action"], reward=cols["reward"], terminal=cols["terminal"],
-                 p_log=cols["p_log"], steps=cols["steps"], n_buckets=wl["states"])
+    if log is None:
+        log = CO.Log(z=cols["z"], z_next=cols["z_next"], action=cols["action"], reward=cols["reward"], terminal=cols["terminal"],
+                     p_log=cols["p_log"], steps=cols["steps"], n_buckets=wl["states"])
     R = threads * 4
     budget = min(wl["budget"], 10_000)
     uniform = np.full((wl["states"], wl["actions"]), 1.0 / wl["actions"])
@@ -137,7 +154,97 @@ def cpu_leg(cols, wl, seconds, threads):
         if dt >= seconds:
             break
     return dict(value=total / dt, pops_per_s=pops / dt, seconds=dt, accepted=total, threads=out["threads"], replicas=R * calls,
-                budget=budget, rows=log.n_rows)
+                budget=budget, rows=log.n_rows), log
+
+
+REF_DIR = os.path.join(ROOT, "baseline", "_ref", "offsim4rl")
+
+
+def load_reference():
+    """The UNMODIFIED reference's evaluators/psrs.py and agents/tabular.py from baseline/_ref (installed by
+    __graft_entry__.build(); they import numpy / copy / itertools / tqdm only), loaded by file path because the package's
+    __init__ imports gym.  None when the install is absent."""
+    import importlib.util
+    mods = []
+    for rel in ("evaluators/psrs.py", "agents/tabular.py"):
+        path = os.path.join(REF_DIR, rel)
+        if not os.path.exists(path):
+            return None
+        spec = importlib.util.spec_from_file_location("offsim4rl_ref_" + os.path.basename(rel)[:-3], path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mods.append(mod)
+    return tuple(mods)
+
+
+def reference_python_leg(cols, wl, seconds, seed=0, rows=1_000_000, max_runs=6):
+    """The reference's OWN loop, unmodified: `PSRS` (psrs.py:5-57) driven by `qlearn_psrs` (psrs.py:119-185) with
+    `epsilon_greedy_policy` (tabular.py:24-32) — or `evalMC_psrs` (psrs.py:241-271) for the fixed-policy workload — on one
+    core, over the first `rows` rows of the same synthetic log (the reference holds ~0.75 KB of python objects per row).
+    Building the env is untimed; a run ends when a needed queue is exhausted (psrs.py:44-45) or at the deadline, which is
+    injected through the env's public `step` attribute (an exhausted-queue answer), not by touching reference code."""
+    ref = load_reference()
+    if ref is None:
+        return None
+    ref_psrs, ref_tabular = ref
+    n = min(len(cols["z"]), rows)
+    nS, nA = wl["states"], wl["actions"]
+    z, zn = cols["z"][:n].tolist(), cols["z_next"][:n].tolist()
+    p_rows = list(cols["p_log"][:n])
+    buf = [(zi, ai, ri, z2, di, pi, {"z": zi, "z_next": z2, "t": ti})
+           for zi, ai, ri, z2, di, pi, ti in zip(z, cols["action"][:n].tolist(), list(cols["reward"][:n]), zn,
+                                                 cols["terminal"][:n].astype(bool).tolist(), p_rows, cols["steps"][:n].tolist())]
+    env = ref_psrs.PSRS(buf, nS=nS, nA=nA)
+    timed, steps, runs = 0.0, 0, 0
+    while timed < seconds and runs < max_runs:     # every run re-buckets and re-shuffles the log (reset_sampler, ~1.5 s, untimed)
+        env.reset_sampler(seed=seed * 1000 + runs)
+        deadline = time.perf_counter() + (seconds - timed)
+        orig = type(env).step.__get__(env)
+        count = [0]
+
+        def step(p, _orig=orig, _count=count):
+            if time.perf_counter() > deadline:
+                return None, None, None, None
+            out = _orig(p)
+            _count[0] += out[0] is not None
+            return out
+        env.step = step
+        np.random.seed(seed * 1000 + runs)
+        t0 = time.perf_counter()
+        if wl["delta"] is None:
+            ref_psrs.qlearn_psrs(env, n_episodes=10**9, behavior_policy=ref_tabular.epsilon_greedy_policy, gamma=GAMMA, alpha=ALPHA,
+                                 epsilon=EPS)
+        else:
+            ref_psrs.evalMC_psrs(env, n_episodes=10**9, pi=np.full((nS, nA), 1.0 / nA), gamma=GAMMA)
+        timed += time.perf_counter() - t0
+        steps += count[0]
+        runs += 1
+        del env.step
+    return dict(value=steps / max(timed, 1e-9), seconds=timed, rows=n, runs=runs, accepted=steps)
+
+
+def reference_python_multiprocess(cols, wl, seconds, procs, workload, rows=1_000_000):
+    """The reference has no multi-process mode for PSRS (MPI is only used by its PPO agent); the closest equivalent is P
+    independent single-replica runs in P separate processes, rates summed.  Plain subprocesses
+    with a hard timeout: no fork of the CUDA-initialised parent, no pool."""
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "log.npz")
+        np.savez(path, **{k: v[:rows] for k, v in cols.items()})
+        cmd = [sys.executable, os.path.abspath(__file__), "--ref-worker", path, "--py-seconds", str(seconds), "--workload", workload]
+        ps = [subprocess.Popen(cmd + ["--ref-seed", str(i + 1)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+              for i in range(procs)]
+        vals = []
+        deadline = time.time() + seconds * 6 + 240
+        for pr in ps:
+            try:
+                out, _ = pr.communicate(timeout=max(1.0, deadline - time.time()))
+                vals.append(json.loads(out.strip().splitlines()[-1])["value"])
+            except Exception:
+                pr.kill()
+    if len(vals) != procs:
+        return None
+    return dict(value=float(sum(vals)), processes=procs, seconds=seconds, rows=rows)
 
 
 def python_port_leg(cols, wl, seconds):
@@ -188,30 +295,47 @@ def python_port_multiprocess(cols, wl, seconds, procs, workload):
 
 
 def run_reference(args, wl, rank, world):
-    """--impl reference: the CPU implementation of the path on this box's host cores (the oracle's C
-    restatement, all threads), same metric/config; rank 0 only."""
+    """--impl reference: the CPU implementation of the path on this box's host cores, same metric and config as the GPU
+    arm; rank 0 only.  `value` = oracle/ols_oracle.c (the C restatement of the reference's loop; the reference itself is
+    python and cannot hold the 1e8-row log) on ALL host threads over the FULL synthetic log of the workload; beside it the
+    UNMODIFIED reference (baseline/_ref: `PSRS` + `qlearn_psrs` / `evalMC_psrs`) timed on 1 process and on P processes over
+    the first 1e6 rows."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    rows = min(wl["rows"], 1_000_000)
+    rows = wl["rows"]
+    t0 = time.perf_counter()
     cols = numpy_log(rows, wl["states"], wl["actions"], wl["delta"])
+    gen_s = time.perf_counter() - t0
     per_step = 4.0
     vals = []
+    clog = None
     for i in range(args.warmup + args.steps):
-        leg = cpu_leg(cols, wl, per_step if i >= args.warmup else 1.0, threads)
+        leg, clog = cpu_leg(cols, wl, per_step if i >= args.warmup else 1.0, threads, log=clog)
         if i >= args.warmup:
             vals.append(leg)
     acc = sum(v["accepted"] for v in vals)
     secs = sum(v["seconds"] for v in vals)
     value = acc / secs
-    sample = (f"C restatement of psrs.py qlearn/evalMC loop, {vals[-1]['threads']} threads, log truncated to {rows} rows, "
-              f"{vals[-1]['budget']} accepted steps per replica, ~{per_step:.0f} s per step")
+    del clog
+    ref1 = refp = None
+    if not args.skip_cpu:
+        ref1 = reference_python_leg(cols, wl, 6.0)
+        refp = reference_python_multiprocess(cols, wl, 6.0, threads, args.workload) if ref1 is not None else None
+    sample = (f"oracle/ols_oracle.c (C restatement of psrs.py PSRS.step + qlearn/evalMC loop), {vals[-1]['threads']} threads, the full "
+              f"{rows}-row synthetic log (host-generated in {gen_s:.0f} s, untimed), {vals[-1]['budget']} accepted steps per replica, "
+              f"~{per_step:.0f} s per step")
     print(json.dumps({
         "impl": "reference", "metric": "simulated accepted transitions/sec", "value": value, "unit": "transitions/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, len(vals)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload + ": " + wl["desc"], "rows": rows, "states": wl["states"], "actions": wl["actions"]},
-        "cpu_baseline": {"value": value, "unit": "transitions/s", "cores": vals[-1]["threads"], "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "transitions/s", "cores": vals[-1]["threads"], "kind": "port", "sample": sample,
+                         "pops_per_s": sum(v["pops_per_s"] * v["seconds"] for v in vals) / secs,
+                         "reference_python": None if ref1 is None else {
+                             "kind": "reference", "what": "UNMODIFIED offsim4rl evaluators/psrs.py + agents/tabular.py from baseline/_ref, "
+                                                          "first 1e6 rows of the same log, env construction untimed",
+                             "one_process": ref1, "processes": refp}},
         "e2e": {"value": value, "unit": "transitions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -335,10 +459,16 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--py-worker", help=argparse.SUPPRESS)      # internal: one process of the multi-process python baseline
     ap.add_argument("--py-seconds", type=float, default=4.0, help=argparse.SUPPRESS)
+    ap.add_argument("--ref-worker", help=argparse.SUPPRESS)     # internal: one process of the multi-process reference baseline
+    ap.add_argument("--ref-seed", type=int, default=1, help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.py_worker:
         cols = dict(np.load(args.py_worker))
         print(json.dumps(python_port_leg(cols, dict(WORKLOADS[args.workload]), args.py_seconds)))
+        return
+    if args.ref_worker:
+        cols = dict(np.load(args.ref_worker))
+        print(json.dumps(reference_python_leg(cols, dict(WORKLOADS[args.workload]), args.py_seconds, seed=args.ref_seed)))
         return
     wl = dict(WORKLOADS[args.workload])
     for k in ("rows", "states", "replicas", "budget", "lanes"):
@@ -523,7 +653,7 @@ def main():
                "pipeline": "per step: H2D of the 7 log columns (pinned host, copy stream) -> bucketing -> fused run -> curve reduce -> "
                            "D2H of the curve; the H2D of step i+1 is issued behind the run launch of step i (double-buffered "
                            "columns); all %d uploads are inside the timed region" % args.e2e_steps}
-        cpu_cols = {k: v[:1_000_000].numpy().copy() for k, v in host.items()}
+        cpu_cols = {k: v.numpy() for k, v in host.items()}            # the full log, already on the host (pinned)
     else:
         cpu_cols = {k: v[:1_000_000].cpu().numpy() for k, v in cols.items()}
 
@@ -544,16 +674,22 @@ def main():
         cpu = None
         if not args.skip_cpu and world == 1:
             threads = os.cpu_count() or 1
-            leg = cpu_leg(cpu_cols, wl, args.cpu_seconds, threads)
-            py = python_port_leg(cpu_cols, wl, 4.0) if qlearn else None
-            py_mp = python_port_multiprocess(cpu_cols, wl, 4.0, threads, args.workload) if qlearn else None
+            leg, _clog = cpu_leg(cpu_cols, wl, args.cpu_seconds, threads)
+            del _clog
+            small = {k: v[:1_000_000] for k, v in cpu_cols.items()}
+            ref1 = reference_python_leg(small, wl, 5.0)
+            refp = reference_python_multiprocess(small, wl, 5.0, threads, args.workload) if ref1 is not None else None
+            py = python_port_leg(small, wl, 3.0) if (qlearn and ref1 is None) else None
             cpu = {"value": leg["value"], "unit": "transitions/s", "cores": leg["threads"], "kind": "port",
-                   "sample": (f"oracle/ols_oracle.c (C restatement of the reference's PSRS + learner loop), {leg['threads']} threads, same "
-                              f"synthetic log truncated to {leg['rows']} rows, {leg['replicas']} replicas x {leg['budget']} accepted steps, "
+                   "sample": (f"oracle/ols_oracle.c (C restatement of the reference's PSRS + learner loop), {leg['threads']} threads, the same "
+                              f"synthetic log ({leg['rows']} rows), {leg['replicas']} replicas x {leg['budget']} accepted steps, "
                               f"{leg['seconds']:.1f} s"),
                    "pops_per_s": leg["pops_per_s"],
-                   "python_port_1core": None if py is None else {"value": py["value"], "rows": py["rows"], "seconds": py["seconds"]},
-                   "python_port_multiprocess": py_mp}
+                   "reference_python": None if ref1 is None else {
+                       "kind": "reference", "what": "UNMODIFIED offsim4rl evaluators/psrs.py + agents/tabular.py (baseline/_ref): PSRS + "
+                                                    "qlearn_psrs / evalMC_psrs, first 1e6 rows of the same log, env construction untimed",
+                       "one_process": ref1, "processes": refp},
+                   "python_port_1core": None if py is None else {"value": py["value"], "rows": py["rows"], "seconds": py["seconds"]}}
         out = {
             "metric": "simulated accepted transitions/sec", "value": value, "unit": "transitions/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
