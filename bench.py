@@ -447,7 +447,7 @@ def main():
     ap.add_argument("--prefetch", type=int, default=-1)
     ap.add_argument("--ppl", type=int, default=0, help="records per lane per round (0 = auto)")
     ap.add_argument("--slices", type=int, default=-1, help="time slices of the fused run: -1 auto, 0 off, k forced")
-    ap.add_argument("--hot-bytes", type=int, default=0, help="hot record size: 8 or 16 (0 = 16 for the one-lane Q-learner, else 8)")
+    ap.add_argument("--hot", choices=["probs", "tail"], help="hot record format (default: tail for the one-lane Q-learner, else probs)")
     ap.add_argument("--batch-lanes", type=int, default=0, help="one-lane learner: lanes per update batch (0 = library default)")
     ap.add_argument("--no-hot", action="store_true", help="pop from the 32-byte records only (no 8-byte hot records)")
     ap.add_argument("--no-aos", action="store_true", help="separate cursor / Q arrays instead of one 32-byte entry per (replica, state)")
@@ -509,8 +509,9 @@ def main():
     torch.cuda.synchronize()
     # learners: hot records need the AoS state and give nothing when the state fits L2 (c2); fixed-policy evaluation (c5): always
     use_hot = nA <= 4 and not args.no_hot and ((qlearn and not args.no_aos and args.workload == "c4") or not qlearn)
-    # the one-thread-per-replica Q-learner reads 16-byte hot records (+ reward, next state, terminal); evaluation 8-byte ones
-    hot_kind = (args.hot_bytes or (16 if (qlearn and wl["lanes"] == 1) else 8)) if use_hot else False
+    # the one-thread-per-replica Q-learner reads TAIL hot records (reward, next state, action, terminal: the synthetic
+    # behaviour distribution is a function of the state, so the accept rule needs only the action); evaluation PROBS ones
+    hot_kind = (args.hot or ("tail" if (qlearn and wl["lanes"] == 1) else "probs")) if use_hot else False
     log = ob.BucketedLog(z=cols["z"], z_next=cols["z_next"], action=cols["action"], reward=cols["reward"],
                          terminal=cols["terminal"], p_log=cols["p_log"], steps=cols["steps"], n_buckets=nS, z_offset=0, device=dev,
                          keep_columns=True, hot_records=hot_kind)

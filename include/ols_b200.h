@@ -59,6 +59,7 @@ enum { OLS_COMPUTE_F64 = 0,      /* NumPy promotion when either distribution is 
 enum { OLS_RNG_FEED = 0,         /* u = u_feed[replica*stride + draw]  (harness-fed, parity tests)  */
        OLS_RNG_PCG64 = 1,        /* np.random.default_rng(seed).random() replayed bit for bit        */
        OLS_RNG_PHILOX = 2        /* Philox4x32-10 keyed by (seed, replica id), counter = draw index  */ };
+enum { OLS_HOT_PROBS = 0, OLS_HOT_TAIL = 1 };   /* ols_queues_t.hot_kind */
 enum { OLS_AGENT_FIXED_PI = 0,   /* psrs.py:241-271 evalMC_psrs                                     */
        OLS_AGENT_EXPSARSA = 1,   /* psrs.py:187-239 expSARSA_psrs                                   */
        OLS_AGENT_QLEARN = 2      /* psrs.py:119-185 qlearn_psrs + tabular.py:24-32 epsilon-greedy    */ };
@@ -117,12 +118,22 @@ typedef struct ols_queues {
                                  images of the record's probabilities plus its action — all the accept rule needs for
                                  all but ~5e-4 of the pops, so the fused run reads 8 instead of 32 bytes per rejected
                                  record.  Filled by ols_bucket / ols_shuffle_queues when non-NULL.               */
-  int32_t hot_bytes;          /* size of one hot record: 8 (above; 0 means 8), or 16 = the same 8 bytes followed by
-                                 { float reward; uint32 z_next (bits 0..30, two's complement) | terminal << 31 } — all an
-                                 ACCEPTED pop needs as well, so the one-lane float32 Q-learner (ols_run with lanes = 1,
-                                 state_aos, Philox uniforms) never reads the 32-byte record on its fast path.  Every other
-                                 kernel ignores 16-byte hot records and pops from the full records.                */
+  int32_t hot_kind;           /* what the 8-byte hot records hold:
+                                 OLS_HOT_PROBS (0)  the logged probabilities as halves + the action (above): any log;
+                                 OLS_HOT_TAIL  (1)  { float reward; uint32 z_next (bits 0..28, two's complement) | action << 29
+                                                    | terminal << 31 } — for a log whose behaviour distribution is a function
+                                                    of the state, i.e. every queue holds ONE logged distribution (queue_dist):
+                                                    the accept rule then depends on a record only through its action, and
+                                                    the one-thread-per-replica float32 Q-learner (ols_run with lanes = 1,
+                                                    state_aos, Philox uniforms) never reads the 32-byte record.  Every other
+                                                    kernel ignores TAIL hot records and pops from the full records.        */
   int32_t _pad;
+  float* queue_dist;          /* NULL, or [n_buckets][8] written by ols_bucket / ols_shuffle_queues: floats 0..3 the logged
+                                 distribution of the queue's FIRST record (padded with 1.0), word 4 (int32) flags: bit 0 =
+                                 every record of the queue holds exactly that distribution (bitwise), bit 1 = tame (all
+                                 in [2^-40, 2^40]); words 5..7 zero.  Empty queues count as constant.                      */
+  int32_t* const_info;        /* NULL, or [1] written with queue_dist: the number of queues that are NOT constant — hot_kind
+                                 OLS_HOT_TAIL is only valid when it is 0 (and p_log64 is NULL)                             */
 } ols_queues_t;
 
 /* ---- a block of independent simulation replicas ------------------------------------------ *
@@ -201,7 +212,7 @@ typedef struct ols_run {
                                  library decide.  Results do not depend on it.                                 */
   int32_t state_epoch;        /* state_aos: only entries whose epoch word equals this value are live, all others
                                  read as cursor 0 / Q 0 — a restart bumps the epoch instead of clearing the table */
-  int32_t batch_lanes;        /* one-lane learner over 16-byte hot records: the warp runs the update block once this many
+  int32_t batch_lanes;        /* one-thread-per-replica learner (OLS_HOT_TAIL): the warp runs the update block once this many
                                  of its 32 replicas hold an outcome (1..32; 0 = library default, 20).  Results do not
                                  depend on it.                                                                    */
   int32_t _pad1;
@@ -266,6 +277,10 @@ int ols_init_queue(const ols_log_t* log, const ols_queues_t* q, int64_t* n_init_
  * the log-order CSR; dst->offsets may alias src->offsets).  perm_scratch: n_rows + n_init int32.  */
 int ols_shuffle_queues(const ols_queues_t* src, const ols_queues_t* dst, uint64_t seed, int32_t* perm_scratch,
                        void* stream);
+/* (Re)build the derived arrays q points to — hot (in the format q->hot_kind names), queue_dist, const_info — from
+ * q->offsets and q->records.  ols_bucket and ols_shuffle_queues call it themselves; a caller uses it to switch the hot
+ * format of a bucketed log (e.g. to OLS_HOT_PROBS after const_info reported a queue with several distributions).        */
+int ols_pack_hot(const ols_queues_t* q, void* stream);
 
 /* ---- replicas ----------------------------------------------------------------------------- */
 /* Zero cursors/counters, status = OLS_IDLE, and (PCG64 mode) seed every replica's generator with

@@ -25,6 +25,7 @@ REJECT_DEFAULT, REJECT_ACCEPT_ALL = 0, 1
 COMPUTE_F64, COMPUTE_F32 = 0, 1
 RNG_FEED, RNG_PCG64, RNG_PHILOX = 0, 1, 2
 AGENT_FIXED_PI, AGENT_EXPSARSA, AGENT_QLEARN = 0, 1, 2
+HOT_PROBS, HOT_TAIL = 0, 1
 
 p = C.c_void_p
 i32, i64, u64, f64 = C.c_int32, C.c_int64, C.c_uint64, C.c_double
@@ -38,7 +39,7 @@ class Log(C.Structure):
 class Queues(C.Structure):
     _fields_ = [("n_rows", i64), ("n_init", i64), ("n_actions", i32), ("n_buckets", i32), ("z_offset", i32),
                 ("rec_bytes", i32), ("offsets", p), ("records", p), ("init_row", p), ("init_z", p),
-                ("init_s", p), ("s_next", p), ("p_log64", p), ("hot", p), ("hot_bytes", i32), ("_pad", i32)]
+                ("init_s", p), ("s_next", p), ("p_log64", p), ("hot", p), ("hot_kind", i32), ("_pad", i32), ("queue_dist", p), ("const_info", p)]
 
 
 class Replicas(C.Structure):
@@ -76,6 +77,7 @@ SIGNATURES = {
     "ols_bucket": (C.c_int, [C.POINTER(Log), C.POINTER(Queues), p, C.c_size_t, p]),
     "ols_init_queue": (C.c_int, [C.POINTER(Log), C.POINTER(Queues), p, p, C.c_size_t, p]),
     "ols_shuffle_queues": (C.c_int, [C.POINTER(Queues), C.POINTER(Queues), u64, p, p]),
+    "ols_pack_hot": (C.c_int, [C.POINTER(Queues), p]),
     "ols_replicas_init": (C.c_int, [C.POINTER(Queues), C.POINTER(Replicas), p, p]),
     "ols_reset": (C.c_int, [C.POINTER(Queues), C.POINTER(Replicas), p, p]),
     "ols_step": (C.c_int, [C.POINTER(Queues), C.POINTER(Replicas), p, p, i32, i64, i32, i32, i32,

@@ -316,8 +316,7 @@ __global__ void __launch_bounds__(kBucketThreads, OLS_SCATTER_MINB) scatter_pack
 }
 
 // ---------------------------------------------------------------------------------------- hot records
-// One streaming pass over the packed queues: 32 bytes in, 8 (or 16) bytes out per record (n_actions <= 4).
-template <int HOT_BYTES>
+// One streaming pass over the packed queues: 32 bytes in, 8 bytes out per record (n_actions <= 4).
 __global__ void __launch_bounds__(256) hot_pack_kernel(ols_queues_t q) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < q.n_rows; i += stride) {
@@ -325,24 +324,68 @@ __global__ void __launch_bounds__(256) hot_pack_kernel(ols_queues_t q) {
     const float4 p = __ldg(rp);
     const float4 tail = __ldg(rp + 1);
     const uint32_t meta = __float_as_uint(tail.w);
-    if (HOT_BYTES == 16)
-      ((uint4*)q.hot)[i] = ols_hot16_pack(p, ols_meta_action(meta), q.n_actions, tail.x, __float_as_int(tail.y), ols_meta_terminal(meta));
+    if (q.hot_kind == OLS_HOT_TAIL)
+      ((uint2*)q.hot)[i] = ols_hot_tail_pack(ols_meta_action(meta), tail.x, __float_as_int(tail.y), ols_meta_terminal(meta));
     else
       ((uint2*)q.hot)[i] = ols_hot_pack(p, ols_meta_action(meta), q.n_actions);
   }
 }
 
+// Per queue: does every record hold the distribution of the first one (bitwise)?  One CTA per queue (grid-strided).
+__global__ void __launch_bounds__(256) queue_dist_kernel(ols_queues_t q) {
+  __shared__ int s_diff;
+  for (int b = blockIdx.x; b < q.n_buckets; b += gridDim.x) {
+    const int lo = __ldg(q.offsets + b), hi = __ldg(q.offsets + b + 1);
+    if (threadIdx.x == 0) s_diff = 0;
+    __syncthreads();
+    float4 p0 = make_float4(1.f, 1.f, 1.f, 1.f);
+    int diff = 0;
+    if (hi > lo) {
+      p0 = __ldg((const float4*)((const char*)q.records + (size_t)lo * 32));
+      for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const float4 p = __ldg((const float4*)((const char*)q.records + (size_t)i * 32));
+        diff |= (__float_as_uint(p.x) != __float_as_uint(p0.x)) | (__float_as_uint(p.y) != __float_as_uint(p0.y)) |
+                (__float_as_uint(p.z) != __float_as_uint(p0.z)) | (__float_as_uint(p.w) != __float_as_uint(p0.w));
+      }
+    }
+    if (diff) s_diff = 1;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const float v[4] = {p0.x, p0.y, p0.z, p0.w};
+      bool tame = true;
+      for (int j = 0; j < q.n_actions && j < 4; ++j) tame = tame && (v[j] >= 9.094947e-13f && v[j] <= 1.0995116e12f);
+      float* out = q.queue_dist + 8 * (size_t)b;
+      out[0] = p0.x; out[1] = p0.y; out[2] = p0.z; out[3] = p0.w;
+      ((int*)out)[4] = (s_diff ? 0 : 1) | (tame ? 2 : 0);
+      ((int*)out)[5] = ((int*)out)[6] = ((int*)out)[7] = 0;
+      if (s_diff && q.const_info) atomicAdd(q.const_info, 1);
+    }
+    __syncthreads();
+  }
+}
+
 inline int pack_hot(const ols_queues_t* q, cudaStream_t stream) {
-  if (q->hot == nullptr || q->n_rows == 0) return OLS_OK;
+  if (q->n_rows == 0 || (q->hot == nullptr && q->queue_dist == nullptr)) {
+    if (q->const_info) OLS_CUDA_CHECK(cudaMemsetAsync(q->const_info, 0, sizeof(int32_t), stream));
+    return OLS_OK;
+  }
   OLS_REQUIRE(q->n_actions <= 4 && q->rec_bytes == 32, OLS_ERR_UNSUPPORTED, "hot records need n_actions <= 4");
-  OLS_REQUIRE(q->hot_bytes == 0 || q->hot_bytes == 8 || q->hot_bytes == 16, OLS_ERR_INVALID, "hot_bytes must be 8 or 16");
-  const int hb = q->hot_bytes == 16 ? 16 : 8;
-  OLS_REQUIRE((uintptr_t)q->hot % hb == 0, OLS_ERR_INVALID, "hot records must be aligned to their size");
-  int blocks = ols_div_up(q->n_rows, 256);
-  if (blocks > OLS_SM_COUNT * 16) blocks = OLS_SM_COUNT * 16;
-  if (hb == 16) hot_pack_kernel<16><<<blocks, 256, 0, stream>>>(*q);
-  else hot_pack_kernel<8><<<blocks, 256, 0, stream>>>(*q);
-  OLS_LAUNCH_CHECK();
+  OLS_REQUIRE(q->hot_kind == OLS_HOT_PROBS || q->hot_kind == OLS_HOT_TAIL, OLS_ERR_INVALID, "bad hot_kind");
+  if (q->queue_dist) {
+    OLS_REQUIRE((uintptr_t)q->queue_dist % 32 == 0, OLS_ERR_INVALID, "queue_dist must be 32-byte aligned");
+    if (q->const_info) OLS_CUDA_CHECK(cudaMemsetAsync(q->const_info, 0, sizeof(int32_t), stream));
+    int blocks = q->n_buckets < OLS_SM_COUNT * 8 ? q->n_buckets : OLS_SM_COUNT * 8;
+    queue_dist_kernel<<<blocks, 256, 0, stream>>>(*q);
+    OLS_LAUNCH_CHECK();
+  }
+  if (q->hot) {
+    OLS_REQUIRE(q->hot_kind != OLS_HOT_TAIL || q->queue_dist, OLS_ERR_INVALID, "OLS_HOT_TAIL needs queue_dist");
+    OLS_REQUIRE((uintptr_t)q->hot % 8 == 0, OLS_ERR_INVALID, "hot records must be 8-byte aligned");
+    int blocks = ols_div_up(q->n_rows, 256);
+    if (blocks > OLS_SM_COUNT * 16) blocks = OLS_SM_COUNT * 16;
+    hot_pack_kernel<<<blocks, 256, 0, stream>>>(*q);
+    OLS_LAUNCH_CHECK();
+  }
   return OLS_OK;
 }
 
@@ -671,6 +714,12 @@ extern "C" int ols_bucket(const ols_log_t* log, const ols_queues_t* q, void* scr
 #undef OLS_SCATTER
   OLS_LAUNCH_CHECK();
   return pack_hot(q, stream);
+}
+
+extern "C" int ols_pack_hot(const ols_queues_t* q, void* stream_) {
+  int rc = check_queues(q, "ols_pack_hot");
+  if (rc) return rc;
+  return pack_hot(q, (cudaStream_t)stream_);
 }
 
 extern "C" int ols_init_queue(const ols_log_t* log, const ols_queues_t* q, int64_t* n_init_dev, void* scratch,

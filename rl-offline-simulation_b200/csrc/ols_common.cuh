@@ -77,10 +77,11 @@ __device__ __forceinline__ uint2 ols_hot_pack(float4 p, int action, int n_action
   h.y = c[2] | (c[3] << 16) | ((tame ? 1u : 0u) << 15);
   return h;
 }
-// 16-byte hot record: the 8 bytes above + what an ACCEPTED pop needs (reward, next state, terminal flag)
-__device__ __forceinline__ uint4 ols_hot16_pack(float4 p, int action, int n_actions, float reward, int z_next, int terminal) {
-  const uint2 h = ols_hot_pack(p, action, n_actions);
-  return make_uint4(h.x, h.y, __float_as_uint(reward), ((uint32_t)z_next & 0x7fffffffu) | ((terminal ? 1u : 0u) << 31));
+// TAIL hot record (OLS_HOT_TAIL): what a pop needs of a record whose queue holds one distribution — the action for the
+// accept rule, and reward / next state / terminal flag if it is accepted
+__device__ __forceinline__ uint2 ols_hot_tail_pack(int action, float reward, int z_next, int terminal) {
+  return make_uint2(__float_as_uint(reward),
+                    ((uint32_t)z_next & 0x1fffffffu) | (((uint32_t)action & 3u) << 29) | ((terminal ? 1u : 0u) << 31));
 }
 __device__ __forceinline__ void ols_hot_unpack(uint2 h, float (&p)[4], int& action, bool& tame) {
   action = (int)(((h.x >> 15) & 1u) | ((h.x >> 31) << 1));
@@ -176,11 +177,35 @@ __device__ __forceinline__ uint32_t ols_u4_word(const ols_u4& o, int w) { return
 __host__ __device__ inline double ols_u64_to_unit(uint64_t v) { return (double)(v >> 11) * (1.0 / 9007199254740992.0); }
 __host__ __device__ inline double ols_u53_to_unit(uint64_t v53) { return (double)v53 * (1.0 / 9007199254740992.0); }
 
-// the exact draw (cold paths: inside the filter's band, tie-breaks, the scalar step): both words
-static __device__ __noinline__ uint64_t ols_stream_u53(const ols_philox_keys& K, uint64_t rid, uint32_t which, uint64_t d) {
-  const uint32_t hi = ols_u4_word(ols_stream_block(K, rid, which, d >> 2), (int)(d & 3));
-  const uint32_t lo = ols_u4_word(ols_stream_block(K, rid, which + 2u, d >> 2), (int)(d & 3));
-  return ((uint64_t)hi << 21) | (uint64_t)(lo >> 11);
+// the exact draw (cold paths: inside the filter's band, the scalar step): both words.  Out of line, and keyed by the SEED
+// (round keys re-derived on the fly): taking the address of the kernel's key parameter would move it from the constant bank
+// to local memory for the hot path as well.
+static __device__ __noinline__ uint64_t ols_stream_u53_seed(uint64_t seed, uint64_t rid, uint32_t which, uint64_t d) {
+  uint32_t w[2];
+#pragma unroll 1
+  for (int s = 0; s < 2; ++s) {
+    const uint64_t blk = d >> 2;
+    uint32_t c0 = (uint32_t)blk, c1 = (uint32_t)(blk >> 32), c2 = (uint32_t)rid, c3 = (uint32_t)(rid >> 32) ^ ((which + 2u * s) << 28);
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll 1
+    for (int i = 0; i < OLS_PHILOX_ROUNDS; ++i) {
+      const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+      const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+      c1 = (uint32_t)p1;
+      c3 = (uint32_t)p0;
+      c0 = n0;
+      c2 = n2;
+      k0 += 0x9E3779B9u;
+      k1 += 0xBB67AE85u;
+    }
+    const int wi = (int)(d & 3);
+    w[s] = wi == 0 ? c0 : wi == 1 ? c1 : wi == 2 ? c2 : c3;
+  }
+  return ((uint64_t)w[0] << 21) | (uint64_t)(w[1] >> 11);
+}
+__device__ __forceinline__ uint64_t ols_keys_seed(const ols_philox_keys& K) { return (uint64_t)K.k0[0] | ((uint64_t)K.k1[0] << 32); }
+__device__ __forceinline__ uint64_t ols_stream_u53(const ols_philox_keys& K, uint64_t rid, uint32_t which, uint64_t d) {
+  return ols_stream_u53_seed(ols_keys_seed(K), rid, which, d);
 }
 __device__ __forceinline__ double ols_stream_uniform(const ols_philox_keys& K, uint64_t rid, uint32_t which, uint64_t d) {
   return ols_u53_to_unit(ols_stream_u53(K, rid, which, d));

@@ -1,20 +1,26 @@
 // The production learner: psrs.py:119-185 `qlearn_psrs` + agents/tabular.py:4-5,24-32 epsilon-greedy, ONE THREAD per
 // replica, for the shape the benchmark names (BASELINE.json configs[3]): float32 Q, <= 4 actions, the agent's observation
-// id is the state id, AoS replica state {cursor, epoch, Q row} per (replica, state), Philox streams (protocol v2), 16-byte
-// hot records.  Same semantics, statement for statement, as run_kernel<1, QLEARN, float, PHILOX, 4, AOS, 1, HOT> in
-// ols_sim_kernels.cuh (the tests compare both with oracle/ols_oracle.c draw for draw); what differs is the schedule:
+// id is the state id, AoS replica state {cursor, epoch, Q row} per (replica, state), Philox streams (protocol v2), and a log
+// whose behaviour distribution is a function of the state: every queue holds ONE logged distribution (checked bit for bit
+// when the log is bucketed: ols_queues_t.queue_dist / hot_kind = OLS_HOT_TAIL).  Same semantics, statement for statement,
+// as run_kernel<1, QLEARN, float, PHILOX, 4, AOS, 1, HOT> in ols_sim_kernels.cuh (the tests compare both with
+// oracle/ols_oracle.c draw for draw); what differs is the schedule:
 //
-//   * 16-byte hot records (ols_queues_t.hot, hot_bytes = 16): the four half-precision probabilities + action of the 8-byte
-//     format AND the reward, the next state and the terminal flag.  The full 32-byte record is no longer on the path of an
-//     accepted pop (only the ~5e-4 undecided pops and the optional row trace read it), so a transition's dependent DRAM
+//   * the accept rule psrs.py:53-57 depends on a record only through its ACTION once the queue's distribution is known, so
+//     the per-record work of the float32 pre-filter (four products, the min, the reciprocal) moves out of the pop loop: per
+//     STEP and action, the band around the estimated threshold as two 32-bit limits for the high word of the uniform
+//     (make_limits; same error budget as accept_filter); per POP, one shared-memory load and two integer compares, and the
+//     exact rule inside the band.
+//   * 8-byte TAIL hot records { reward; next state | action | terminal }: everything a pop needs, rejected or accepted.
+//     The 32-byte record is no longer on the path (only the optional row trace reads it), so a transition's dependent DRAM
 //     chain is   hot span -> AoS entry of the next state   instead of   hot span -> record -> AoS entry.
 //   * one stream block per four draws, carried from round to round (a round examines four VALID records whatever the
 //     draw counter's alignment; the block holding the next draw is kept in shared memory), ~0.75 seven-round Philox blocks
 //     per round instead of two ten-round ones.
 //   * batched updates: a lane that has an outcome (accepted record / exhausted queue) parks it — its next state's AoS
 //     entry is prefetched into L2 at that moment — and the warp runs the update + next-action block only once
-//     `batch_lanes` lanes (default 20 of 32) hold one, so that block's instructions serve ~20 replicas instead of ~14 and the
-//     parked lanes' DRAM latency overlaps the other lanes' pop rounds.
+//     `batch_lanes` lanes hold one, so that block's instructions serve more replicas and the parked lanes' DRAM latency
+//     overlaps the other lanes' pop rounds.
 //   * per-replica cold registers live in shared memory as structure-of-arrays (bank-conflict free; one owner thread per
 //     slot, so no phasing / __syncwarp between reads and writes).
 #include "ols_sim_kernels.cuh"
@@ -27,21 +33,66 @@ struct LearnerCold {
   double ep_G[kLT], ep_disc[kLT];
   unsigned long long ties[kLT], accepted0[kLT];
   float4 qrow[kLT];   // Q[S, :] of the current state (the bootstrap row of the previous step)
+  float4 qdist[kLT];  // the logged distribution of the current state's queue
+  uint2 lim[4][kLT];  // per action: accept below .x, reject above .y (high word of the uniform), see make_limits
+  uint2 park[kLT];    // a parked outcome: reward bits, next state | action | terminal
   uint4 blk[kLT];     // the rejection stream's block that holds draw `draws` (block index draws >> 2)
   int ep_index[kLT], ep_len_count[kLT], ep_t[kLT], ep_open[kLT], init_cursor[kLT], status[kLT], n_acc[kLT], pn_ok[kLT],
-      eps_episode[kLT], budget[kLT];
+      eps_episode[kLT], budget[kLT], qtame[kLT];
   float ipn_base[kLT], ipn_top[kLT];
   unsigned h_rep[kLT];
 };
 
-// 16-byte hot record (ols_common.cuh ols_hot16_pack): x, y = the 8-byte hot record; z = reward; w = next state | terminal << 31
-__device__ __forceinline__ uint4 ld_hot16(const uint4* p) {
-  uint4 v;
-  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
-  return v;
+// What the pop loop needs of the agent's distribution and the queue's.  With t_j = p_j / pi_j and inv_m = min_j t_j the
+// threshold of a record with action a is thr_a = inv_m / t_a (psrs.py:55-57 rearranged), and a pop's uniform is known to the
+// pre-filter through its high word hi (u in [hi, hi + 1) * 2^-32).  Per STEP and action the band around the float32 estimate
+// of thr_a (within 2^-19 relative of the exact value under the guards; band 2^-16) becomes two 32-bit limits:
+//     hi <  lo32[a]  ==>  u <  thr_a: accept          hi >  hi32[a]  ==>  u >  thr_a: reject          else: the exact rule
+// so a pop costs an 8-byte shared-memory load and two integer compares.  A failed guard (untamed queue distribution, policy
+// entry outside {0} U [2^-40, 1]) sets lo32 = 0, hi32 = 2^32 - 1: every pop goes to the exact rule.
+__device__ __forceinline__ void make_limits(float4 p, bool ok, float ib, float it, int a_star, int nA, uint2 (&lim)[4]) {
+  const float inf = __int_as_float(0x7f800000);
+  float t[4];
+  // padding entries (j >= n_actions) hold p = 1 in the queue's distribution and 1/pi = +inf: t_j = +inf never wins the min
+  t[0] = p.x * ((a_star == 0) ? it : ib);
+  t[1] = p.y * ((nA <= 1) ? inf : (a_star == 1) ? it : ib);
+  t[2] = p.z * ((nA <= 2) ? inf : (a_star == 2) ? it : ib);
+  t[3] = p.w * ((nA <= 3) ? inf : (a_star == 3) ? it : ib);
+  const float inv_m = fminf(fminf(t[0], t[1]), fminf(t[2], t[3]));
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const float thr = __fdiv_rn(inv_m, t[a]);  // 0 when pi_a = 0 (t_a = +inf); NaN / inf only when a guard failed
+    // in units of 2^-32, with one unit of slack on either side for the truncation of u to hi
+    const double lo = (double)thr * (1.0 - 1.52587890625e-5) * 4294967296.0 - 2.0;
+    const double hi = (double)thr * (1.0 + 1.52587890625e-5) * 4294967296.0 + 2.0;
+    const bool fine = ok && (thr == thr);
+    lim[a].x = !fine ? 0u : (lo <= 0.0) ? 0u : (lo >= 4294967295.0) ? 0xffffffffu : __double2uint_rd(lo);
+    lim[a].y = !fine ? 0xffffffffu : (hi >= 4294967295.0) ? 0xffffffffu : __double2uint_ru(hi);
+  }
 }
 
-__global__ void __launch_bounds__(kLT, OLS_MINB_G1) learner_kernel(ols_queues_t q, ols_replicas_t R, ols_run_t cfg, ols_philox_keys PK) {
+// The cold end of a pop round: slots whose high word fell inside the band are decided by the exact rule psrs.py:53-57 on
+// the queue's distribution, in queue order; returns the first accepting slot (4 = none).
+__device__ __noinline__ int resolve_round(const float* dist, const double* eps_ptr, uint64_t seed, uint64_t rid, uint64_t draws,
+                                          unsigned decs, unsigned acts, int a_star, int nA, int compute_mode) {
+  for (int i = 0; i < 4; ++i) {
+    unsigned dec = (decs >> (2 * i)) & 3u;
+    if (dec == 2u) {
+      const double ue = ols_u53_to_unit(ols_stream_u53_seed(seed, rid, 0u, draws + (uint64_t)i));
+      auto pn_fn = [=](int j) -> double {
+        const double eps = __ldg(eps_ptr);
+        const double base = __ddiv_rn(eps, (double)nA);           // ones * eps / nA          (tabular.py:27)
+        const double top = __dadd_rn(__dsub_rn(1.0, eps), base);  // 1 - eps + eps / nA       (tabular.py:30)
+        return (j == a_star) ? top : base;
+      };
+      dec = accept_slow(pn_fn, dist, nullptr, nA, (int)((acts >> (2 * i)) & 3u), ue, compute_mode) ? 1u : 0u;
+    }
+    if (dec == 1u) return i;
+  }
+  return 4;
+}
+
+__global__ void __launch_bounds__(kLT, OLS_LEARNER_MINB) learner_kernel(ols_queues_t q, ols_replicas_t R, ols_run_t cfg, ols_philox_keys PK) {
   constexpr int NA = 4;
   __shared__ LearnerCold C;
   __shared__ int s_ticket;
@@ -72,10 +123,10 @@ __global__ void __launch_bounds__(kLT, OLS_MINB_G1) learner_kernel(ols_queues_t 
   const int64_t rr = exists ? r : 0;
   const uint64_t rid = (uint64_t)(R.replica_id0 + rr);
   unsigned char* const aos = (unsigned char*)cfg.state_aos + (size_t)rr * (size_t)nS * 32;
-  const uint4* const hot = (const uint4*)q.hot;
+  const uint2* const hot = (const uint2*)q.hot;
 
   int cur_z = 0;
-  uint64_t draws = 0, draws0 = 0;
+  uint64_t draws = 0;
   bool live = false;
   C.n_acc[tid] = 0;
   C.eps_episode[tid] = -1;
@@ -85,7 +136,7 @@ __global__ void __launch_bounds__(kLT, OLS_MINB_G1) learner_kernel(ols_queues_t 
   if (exists) {
     const int status = __ldcg(R.status + r);
     cur_z = __ldcg(R.cur_z + r);
-    draws = draws0 = __ldcg(R.draws + r);
+    draws = __ldcg(R.draws + r);
     C.status[tid] = status;
     C.init_cursor[tid] = __ldcg(R.init_cursor + r);
     C.ties[tid] = __ldcg(R.ties + r);
@@ -109,8 +160,7 @@ __global__ void __launch_bounds__(kLT, OLS_MINB_G1) learner_kernel(ols_queues_t 
   // a parked outcome: what the round that ended the step found
   bool pend = false;
   int p_res = 0;           // OLS_RUNNING = a record was accepted, else OLS_QUEUE_EMPTY
-  uint32_t p_rw = 0, p_zw = 0, p_slot = 0;  // accepted record: reward bits, next state | terminal << 31, queue slot (ring position)
-  int p_A = 0;
+  uint32_t p_slot = 0;     // queue slot of the accepted record (for the row trace)
   bool need_step = live;
 
   const int batch = cfg.batch_lanes > 0 ? min(cfg.batch_lanes, 32) : 20;
@@ -150,6 +200,10 @@ __global__ void __launch_bounds__(kLT, OLS_MINB_G1) learner_kernel(ols_queues_t 
         b_cur = B.b; b_lo = B.lo; b_len = B.len; b_pos = B.cur; b_start = B.start;
         prow = make_float4(e.q[0], nA > 1 ? e.q[1] : -INFINITY, nA > 2 ? e.q[2] : -INFINITY, nA > 3 ? e.q[3] : -INFINITY);
         fresh = true;
+        if (new_status < 0) {
+          C.qdist[tid] = __ldg((const float4*)q.queue_dist + 2 * (size_t)b_cur);
+          C.qtame[tid] = __ldg((const int*)q.queue_dist + 8 * (size_t)b_cur + 4) & 2;
+        }
       }
       if (new_status < 0) {
         // tabular.py:24-32 epsilon_greedy_policy on the single row Q[[S], :] (psrs.py:158)
@@ -188,6 +242,10 @@ __global__ void __launch_bounds__(kLT, OLS_MINB_G1) learner_kernel(ols_queues_t 
           C.pn_ok[tid] = (okb && okt && (base > 0.f || top > 0.f)) ? 1 : 0;
           C.eps_episode[tid] = ep_index0;
         }
+        uint2 lim[4];
+        make_limits(C.qdist[tid], C.qtame[tid] != 0 && C.pn_ok[tid] != 0, C.ipn_base[tid], C.ipn_top[tid], a_star, nA, lim);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) C.lim[a][tid] = lim[a];
       }
       if (fresh) {
         C.qrow[tid] = prow;
@@ -207,20 +265,20 @@ __global__ void __launch_bounds__(kLT, OLS_MINB_G1) learner_kernel(ols_queues_t 
         p_res = OLS_QUEUE_EMPTY;  // psrs.py:44-45
       } else {
         const int n_eval = min(4, remaining);
-        // ---- the four hot records (one 64-byte span unless the ring wraps inside it)
+        // ---- the four hot records (one 32-byte span unless the ring wraps inside it)
         uint32_t pos0 = b_start + (uint32_t)b_pos;
         if (pos0 >= (uint32_t)b_len) pos0 -= (uint32_t)b_len;
-        uint4 h[4];
+        uint2 h[4];
         if (pos0 + 3u < (uint32_t)b_len) {
-          const uint4* hp = hot + (size_t)(uint32_t)(b_lo + (int)pos0);
+          const uint2* hp = hot + (size_t)(uint32_t)(b_lo + (int)pos0);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) h[i] = ld_hot16(hp + i);
+          for (int i = 0; i < 4; ++i) h[i] = __ldg(hp + i);
         } else {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             uint32_t pos = pos0 + (uint32_t)i;
             if (pos >= (uint32_t)b_len) pos -= (uint32_t)b_len;
-            h[i] = (i < n_eval) ? ld_hot16(hot + (size_t)(uint32_t)(b_lo + (int)pos)) : make_uint4(0u, 0u, 0u, 0u);
+            h[i] = (i < n_eval) ? __ldg(hot + (size_t)(uint32_t)(b_lo + (int)pos)) : make_uint2(0u, 0u);
           }
         }
         // ---- uniforms: draw d + i is word (d & 3) + i of the carried block, continued in the next block
@@ -233,56 +291,25 @@ __global__ void __launch_bounds__(kLT, OLS_MINB_G1) learner_kernel(ols_queues_t 
         hi[1] = a0 == 0 ? o0.y : a0 == 1 ? o0.z : a0 == 2 ? o0.w : o1.x;
         hi[2] = a0 == 0 ? o0.z : a0 == 1 ? o0.w : a0 == 2 ? o1.x : o1.y;
         hi[3] = a0 == 0 ? o0.w : a0 == 1 ? o1.x : a0 == 2 ? o1.y : o1.z;
-        // ---- the policy as the filter needs it: two cached reciprocals and which action holds the larger probability
-        Policy<NA> P;
-        {
-          const float ib = C.ipn_base[tid], it = C.ipn_top[tid];
+        // ---- accept rule per record: u * t_a against the band around inv_m; inside the band (or when a guard fails, or for
+        // the 2.4e-4 of the draws below 2^-12, whose float image needs the low word) the exact rule on the queue's distribution
+        // 2 bits per slot: 0 reject, 1 accept, 2 undecided
+        unsigned decs = 0;
 #pragma unroll
-          for (int j = 0; j < NA; ++j) P.ipn[j] = (j >= nA) ? __int_as_float(0x7f800000) : ((j == a_star) ? it : ib);
-          P.ok = C.pn_ok[tid] != 0;
+        for (int i = 0; i < 4; ++i) {
+          const uint2 lm = C.lim[(h[i].y >> 29) & 3u][tid];
+          const unsigned dec = (i >= n_eval || hi[i] > lm.y) ? 0u : (hi[i] < lm.x) ? 1u : 2u;
+          decs |= dec << (2 * i);
         }
-        // ---- accept rule per record: half-precision estimate (2^-9 band) -> float32 estimate from the full record
-        // (2^-16 band) -> exact rule
-        int first = 4;
-#pragma unroll
-        for (int i = 3; i >= 0; --i) {
-          float plf[NA];
-          int a;
-          bool tame, tiny;
-          ols_hot_unpack(make_uint2(h[i].x, h[i].y), plf, a, tame);
-          const float u = ols_stream_float(PK, rid, 0u, draws + (uint64_t)i, hi[i], tiny);
-          int dec = accept_filter<NA>(P, plf, a, u, P.ok && !tiny && tame, 1.953125e-3f /* 2^-9 */);
-          if (i >= n_eval) dec = 0;
-          if (dec == 2) {
-            uint32_t pos = pos0 + (uint32_t)i;
-            if (pos >= (uint32_t)b_len) pos -= (uint32_t)b_len;
-            const float4* rp = (const float4*)((const char*)q.records + (size_t)(uint32_t)(b_lo + (int)pos) * 32);
-            float4 pf, tl;
-            load_record32(rp, pf, tl);
-            const uint32_t meta = __float_as_uint(tl.w);
-            const float full[NA] = {pf.x, pf.y, pf.z, pf.w};
-            dec = accept_filter<NA>(P, full, ols_meta_action(meta), u, P.ok && !tiny && ols_meta_tame(meta) != 0);
-            if (dec == 2) {
-              const double ue = ols_stream_uniform(PK, rid, 0u, draws + (uint64_t)i);
-              const double* p64 = q.p_log64 ? q.p_log64 + (int64_t)__float_as_int(tl.z) * nA : nullptr;
-              const double* eps_tab = cfg.epsilon;
-              const int ep_now = C.ep_index[tid], a_now = a_star;
-              auto pn_fn = [=](int j) -> double {
-                const double eps = __ldg(eps_tab + ep_now);
-                const double base = __ddiv_rn(eps, (double)nA);           // ones * eps / nA          (tabular.py:27)
-                const double top = __dadd_rn(__dsub_rn(1.0, eps), base);  // 1 - eps + eps / nA       (tabular.py:30)
-                return (j == a_now) ? top : base;
-              };
-              dec = (int)accept_slow(pn_fn, (const float*)rp, p64, nA, ols_meta_action(meta), ue, cfg.compute_mode);
-            }
-          }
-          if (dec == 1) {
-            first = i;
-            p_rw = h[i].z;
-            p_zw = h[i].w;
-            p_A = a;
-          }
+        // the first slot that is not a plain reject ends the round if it is an accept; an undecided one (3e-5 of the pops)
+        // sends the round to the exact rule, out of line
+        int first = decs ? (__ffs(decs) - 1) >> 1 : 4;
+        if (first < 4 && ((decs >> (2 * first)) & 3u) == 2u) {
+          const unsigned acts = ((h[0].y >> 29) & 3u) | (((h[1].y >> 29) & 3u) << 2) | (((h[2].y >> 29) & 3u) << 4) | (((h[3].y >> 29) & 3u) << 6);
+          first = resolve_round(q.queue_dist + 8 * (size_t)b_cur, cfg.epsilon + C.ep_index[tid], ols_keys_seed(PK), rid, draws, decs, acts,
+                                a_star, nA, cfg.compute_mode);
         }
+        const uint2 won = (first == 0) ? h[0] : (first == 1) ? h[1] : (first == 2) ? h[2] : h[3];
         const int consumed = (first < 4) ? first + 1 : n_eval;
         if (first < 4) {
           pend = true;
@@ -291,7 +318,8 @@ __global__ void __launch_bounds__(kLT, OLS_MINB_G1) learner_kernel(ols_queues_t 
           if (pos >= (uint32_t)b_len) pos -= (uint32_t)b_len;
           p_slot = (uint32_t)b_lo + pos;
           // the next state is known: pull its AoS entry (cursor + Q row) toward L2 while other lanes keep popping
-          const int z2 = ((int)(p_zw << 1)) >> 1;
+          C.park[tid] = won;
+          const int z2 = ((int)(won.y << 3)) >> 3;
           if (z2 >= 0 && z2 < nS) asm volatile("prefetch.global.L2 [%0];" ::"l"(aos + (size_t)z2 * 32));
         }
         // ---- carry the block that holds the next draw
@@ -326,9 +354,11 @@ __global__ void __launch_bounds__(kLT, OLS_MINB_G1) learner_kernel(ols_queues_t 
       float qn = 0.f, td = 0.f;
       double G_new = G_old;
       int t_new = t_old;
-      const int Z2 = ((int)(p_zw << 1)) >> 1;
+      const uint2 won = C.park[tid];
+      const uint32_t p_rw = won.x, p_zw = won.y;
+      const int Z2 = ((int)(p_zw << 3)) >> 3;
       const int done = (int)(p_zw >> 31);
-      const int A = p_A;
+      const int A = (int)((p_zw >> 29) & 3u);
       if (accepted) {
         const double Rw = (double)__uint_as_float(p_rw);
         AosEntry e2;
@@ -337,7 +367,13 @@ __global__ void __launch_bounds__(kLT, OLS_MINB_G1) learner_kernel(ols_queues_t 
         if (Z2 >= 0 && Z2 < nS) e2 = load_aos(aos, Z2, cfg.state_epoch);  // the next state's cursor AND Q row: one sector
         Bucket B;
         const bool next_ok = done ? false : load_bucket(q, R, C.h_rep[tid], nullptr, Z2, B, true, e2.cursor);
-        if (!done) { b_cur = B.b; b_lo = B.lo; b_len = B.len; b_pos = B.cur; b_start = B.start; }
+        if (!done) {
+          b_cur = B.b; b_lo = B.lo; b_len = B.len; b_pos = B.cur; b_start = B.start;
+          if (next_ok) {
+            C.qdist[tid] = __ldg((const float4*)q.queue_dist + 2 * (size_t)b_cur);
+            C.qtame[tid] = __ldg((const int*)q.queue_dist + 8 * (size_t)b_cur + 4) & 2;
+          }
+        }
         if (next_ok && b_cur == b_done) b_pos = cur_done;  // a self-loop: the cursor in memory is still the old one
         bucket_valid = next_ok;
         need_step = true;
@@ -419,9 +455,9 @@ __global__ void __launch_bounds__(kLT, OLS_MINB_G1) learner_kernel(ols_queues_t 
     R.cur_z[r] = cur_z;
     R.cur_s[r] = cur_z;
     R.init_cursor[r] = C.init_cursor[tid];
+    R.pops[r] = __ldcg(R.pops + r) + (unsigned long long)(draws - __ldcg(R.draws + r));
     R.draws[r] = draws;
     R.ties[r] = C.ties[tid];
-    R.pops[r] = __ldcg(R.pops + r) + (unsigned long long)(draws - draws0);
     R.accepted[r] = C.accepted0[tid] + (unsigned long long)C.n_acc[tid];
     R.ep_index[r] = C.ep_index[tid];
     R.ep_len_count[r] = C.ep_len_count[tid];

@@ -207,12 +207,13 @@ extern "C" int ols_run(const ols_queues_t* q, const ols_replicas_t* r, const ols
   if (c->agent != OLS_AGENT_QLEARN) OLS_REQUIRE(c->pi, OLS_ERR_INVALID, "ols_run: fixed-policy agents need pi");
   OLS_REQUIRE((!c->trace_row && !c->td_error) || c->trace_cap > 0, OLS_ERR_INVALID, "ols_run: trace taps need trace_cap > 0");
   RunLaunch L;
-  // 16-byte hot records serve the one-lane float32 Q-learner only (ols_learner.cu); every other kernel pops from the full
-  // records (8-byte hot records: the one-lane / lane-group AoS learners and fixed-policy evaluation, see ols_sim_kernels.cuh)
-  const bool hot16 = q->hot && q->hot_bytes == 16;
-  const bool fast_learner = hot16 && c->agent == OLS_AGENT_QLEARN && c->lanes == 1 && c->state_aos && r->rng_mode == OLS_RNG_PHILOX;
+  // TAIL hot records serve the one-thread-per-replica float32 Q-learner only (ols_learner.cu); every other kernel pops from
+  // the full records (PROBS hot records: the lane-group AoS learners and fixed-policy evaluation, see ols_sim_kernels.cuh)
+  const bool hot_tail = q->hot && q->hot_kind == OLS_HOT_TAIL;
+  const bool fast_learner = hot_tail && q->queue_dist && !q->p_log64 && c->agent == OLS_AGENT_QLEARN && c->lanes == 1 && c->state_aos &&
+                            r->rng_mode == OLS_RNG_PHILOX;
   ols_queues_t q_plain = *q;
-  if (hot16 && !fast_learner) {
+  if (hot_tail && !fast_learner) {
     q_plain.hot = nullptr;
     q = &q_plain;
   }
@@ -229,7 +230,7 @@ extern "C" int ols_run(const ols_queues_t* q, const ols_replicas_t* r, const ols
   int slices = c->slices > 1 ? c->slices : 1;
   if (c->slices == -1 && c->sched && c->max_steps > 0 && L.plan.slot_bytes == 0) {
     // resident CTAs per wave under the kernels' launch bounds; slice when the last wave would run part-empty
-    const int resident = OLS_SM_COUNT * (q->n_actions <= 4 ? (g1_hot ? OLS_MINB_G1 : OLS_MINB) : 2);
+    const int resident = OLS_SM_COUNT * (q->n_actions <= 4 ? (fast_learner ? OLS_LEARNER_MINB : g1_hot ? OLS_MINB_G1 : OLS_MINB) : 2);
     const int full = n_blocks / resident, rest = n_blocks % resident;
     // the one-lane learner is also sliced when every block is resident at once: its 6.6 CTAs per SM are 6 on some SMs and 7
     // on others, and slices re-deal the blocks to whichever SM has room (C4: 207.9 ms unsliced, 187.8 ms in 16 slices)

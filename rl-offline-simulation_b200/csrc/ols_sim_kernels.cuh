@@ -45,6 +45,12 @@ constexpr int kThreads = 256;
 #ifndef OLS_G1_THREADS
 #define OLS_G1_THREADS 128
 #endif
+// the one-thread-per-replica learner over TAIL hot records (ols_learner.cu) needs ~96 registers: 5 CTAs of 128 threads per SM
+// without spills beat 7 with them (C4 kernel 156 ms against 162 ms; 6: 162 ms, 4: 182 ms — spilled registers travel through
+// an L1 that the random record stream keeps flushing)
+#ifndef OLS_LEARNER_MINB
+#define OLS_LEARNER_MINB 5
+#endif
 
 // RNGT_NONE: the accept-all baselines (trivial_baselines.py:8-10,22-24) draw no uniform at all
 enum { RNGT_FEED = OLS_RNG_FEED, RNGT_PCG64 = OLS_RNG_PCG64, RNGT_PHILOX = OLS_RNG_PHILOX, RNGT_NONE = 3 };

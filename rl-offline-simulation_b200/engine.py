@@ -143,13 +143,18 @@ class BucketedLog:
             self.offsets = torch.empty(n_buckets + 1, dtype=torch.int32, device=dev)
             self.s_next = s_next            # kept resident only when the agent's observation id differs from z
             self.records = torch.empty(max(n, 1) * self.rec_bytes // 4, dtype=torch.float32, device=dev)
-            # hot records next to the 32-byte ones (n_actions <= 4): what the fused runs read per rejected pop.  True / 8 =
-            # 8 bytes (probabilities as halves + action); 16 = those + reward, next state, terminal flag, for the one-lane
-            # float32 Q-learner, which then never reads the 32-byte record on its fast path
-            if hot_records not in (False, True, None, 0, 8, 16):
-                raise ValueError("hot_records must be False, True (8-byte), 8 or 16")
-            self.hot_bytes = 0 if (not hot_records or n_actions > 4) else (16 if hot_records == 16 else 8)
-            self.hot = torch.empty(max(n, 1) * (self.hot_bytes // 8), dtype=torch.int64, device=dev) if self.hot_bytes else None
+            # 8-byte hot records next to the 32-byte ones (n_actions <= 4): what the fused runs read per popped record.
+            # True / "probs": the logged probabilities as halves + the action (any log).  "tail": reward, next state, action
+            # and terminal flag — for a log whose behaviour distribution is a function of the state (every queue holds ONE
+            # distribution; checked bitwise on the device), where the accept rule needs only the record's action; falls back
+            # to "probs" when the log does not qualify.
+            if hot_records not in (False, True, None, "probs", "tail"):
+                raise ValueError("hot_records must be False, True / 'probs', or 'tail'")
+            want_hot = bool(hot_records) and n_actions <= 4
+            self.hot_kind = abi.HOT_TAIL if (want_hot and hot_records == "tail" and p_log64 is None) else abi.HOT_PROBS
+            self.hot = torch.empty(max(n, 1), dtype=torch.int64, device=dev) if want_hot else None
+            self.queue_dist = torch.zeros((n_buckets, 8), dtype=torch.float32, device=dev) if self.hot_kind == abi.HOT_TAIL else None
+            self._const_info = torch.zeros(1, dtype=torch.int32, device=dev) if self.hot_kind == abi.HOT_TAIL else None
             init_row = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
             init_z = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
             init_s = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
@@ -165,10 +170,15 @@ class BucketedLog:
                            rec_bytes=self.rec_bytes, offsets=_ptr(self.offsets),
                            records=_ptr(self.records), init_row=_ptr(init_row), init_z=_ptr(init_z),
                            init_s=_ptr(init_s), s_next=_ptr(s_next), p_log64=_ptr(p_log64), hot=_ptr(self.hot),
-                           hot_bytes=self.hot_bytes, _pad=0)
+                           hot_kind=self.hot_kind, _pad=0, queue_dist=_ptr(self.queue_dist), const_info=_ptr(self._const_info))
             abi.check(lib.ols_bucket(C.byref(log_key), C.byref(q), _ptr(scratch), sb, _stream_ptr()))
             abi.check(lib.ols_init_queue(C.byref(log), C.byref(q), _ptr(n_init_dev), _ptr(scratch), sb, _stream_ptr()))
             self.n_init = int(n_init_dev.item())        # one sync: construction is not the step path
+            if self.hot_kind == abi.HOT_TAIL and int(self._const_info.item()) != 0:
+                # some queue holds several distributions: the accept rule needs each record's own probabilities
+                self.hot_kind, self.queue_dist, self._const_info = abi.HOT_PROBS, None, None
+                q.hot_kind, q.queue_dist, q.const_info = abi.HOT_PROBS, None, None
+                abi.check(lib.ols_pack_hot(C.byref(q), _stream_ptr()))
             dropped = n - int(self.offsets[-1].item())   # ols_bucket skips rows whose key is outside [0, n_buckets)
             if dropped:
                 raise ValueError(f"{dropped} rows have a state id outside [-z_offset, n_buckets - z_offset)")
@@ -221,7 +231,8 @@ class BucketedLog:
                           z_offset=self.z_offset, rec_bytes=self.rec_bytes, offsets=_ptr(self.offsets),
                           records=_ptr(self.records), init_row=_ptr(self.init_row), init_z=_ptr(self.init_z),
                           init_s=_ptr(self.init_s), s_next=_ptr(self.s_next), p_log64=_ptr(self.p_log64),
-                          hot=_ptr(getattr(self, "hot", None)), hot_bytes=int(getattr(self, "hot_bytes", 0)), _pad=0)
+                          hot=_ptr(getattr(self, "hot", None)), hot_kind=int(getattr(self, "hot_kind", 0)), _pad=0,
+                          queue_dist=_ptr(getattr(self, "queue_dist", None)), const_info=_ptr(getattr(self, "_const_info", None)))
 
     @property
     def order(self) -> torch.Tensor:
@@ -242,6 +253,7 @@ class BucketedLog:
         with torch.cuda.device(base.device):
             out.records = torch.empty_like(base.records)
             out.hot = None if base.hot is None else torch.empty_like(base.hot)
+            out.queue_dist = None if base.queue_dist is None else torch.empty_like(base.queue_dist)
             out.init_row = torch.empty_like(base.init_row)
             out.init_z = torch.empty_like(base.init_z)
             out.init_s = torch.empty_like(base.init_s)
@@ -323,7 +335,7 @@ class BatchedPSRS:
         self._epoch = 1                             # live epoch of the AoS entries (a zeroed table holds epoch 0: all stale)
         self.slices = int(slices)                   # time slices of a budgeted fused run: -1 auto, 0/1 off, k > 1 forced
         self._sched = None
-        self.batch_lanes = int(batch_lanes)         # one-lane learner over 16-byte hot records: lanes per update batch (0 = default)
+        self.batch_lanes = int(batch_lanes)         # one-thread-per-replica learner ("tail" hot records): lanes per update batch
         self.prefetch = int(prefetch)               # rounds ahead prefetched into L2 (<= 0: off; measured neutral on B200)
         self.rng_mode = {"feed": abi.RNG_FEED, "pcg64": abi.RNG_PCG64, "philox": abi.RNG_PHILOX}[rng]
         if seed is None:

@@ -5,7 +5,10 @@ mkdir -p gpurun_out
 : > gpurun_out/${tag}_sweep.jsonl
 for a in "$@"; do
   echo "### $a" >> gpurun_out/${tag}_sweep.jsonl
-  timeout 300 python bench.py --steps 3 --warmup 2 --skip-cpu --skip-e2e --skip-stress $a >> gpurun_out/${tag}_sweep.jsonl 2>> gpurun_out/${tag}_sweep.err
+  # an item may start with VAR=value settings (e.g. OLS_B200_LIB=variants/libols_b200_mb6.so)
+  envs=""; rest="$a"
+  while [[ "$rest" == [A-Z_]*=* ]]; do envs="$envs ${rest%% *}"; rest="${rest#* }"; done
+  env $envs timeout 300 python bench.py --steps 3 --warmup 2 --skip-cpu --skip-e2e --skip-stress $rest >> gpurun_out/${tag}_sweep.jsonl 2>> gpurun_out/${tag}_sweep.err
 done
 python - <<PY
 import json

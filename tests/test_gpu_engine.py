@@ -444,12 +444,12 @@ def test_philox_replicas_match_c_oracle(ob, agent, lanes, ppl, ring):
 
 PROD_LAYOUTS = [
     # lanes, aos_state, hot_records, slices, R, budget
-    (1, True, 16, 8, 3000, 900),            # the benchmarked kernel: one thread per replica, 16-byte hot records, AoS state, time slices
-    (1, True, 16, -1, 20000, 1100),         # ... with the library's own slicing decision (more CTAs than SMs -> 2 slices)
-    (1, True, 16, 0, 777, 300),             # ... unsliced, a ragged last warp
+    (1, True, "tail", 8, 3000, 900),        # the benchmarked kernel: one thread per replica, TAIL hot records, AoS state, time slices
+    (1, True, "tail", -1, 20000, 1100),     # ... with the library's own slicing decision (more CTAs than SMs -> 2 slices)
+    (1, True, "tail", 0, 777, 300),         # ... unsliced, a ragged last warp
     (1, True, True, 8, 3000, 900),          # the one-lane learner over 8-byte hot records
     (2, True, True, 5, 3000, 700),
-    (2, True, 16, 5, 3000, 700),            # 16-byte hot records are ignored by every other kernel
+    (2, True, "tail", 5, 3000, 700),        # TAIL hot records are ignored by every other kernel
     (32, True, True, 0, 1500, 400),
     (4, True, False, 3, 3000, 500),         # AoS state over the 32-byte records
     (4, False, False, 0, 3000, 500),        # plain layout
@@ -492,6 +492,39 @@ def test_float32_production_learner_matches_c_oracle(ob, lanes, aos, hot, slices
     sample = [0, 17, R - 1]
     assert np.array_equal(res.q_rows(sample).cpu().numpy(), ref["Q"][sample])
     assert int((ref["accepted"] == budget).sum()) > 0.9 * R                             # the budget, not exhaustion, ended the runs
+
+
+def test_tail_hot_records_need_one_distribution_per_queue(ob):
+    """hot_records='tail' is for logs whose behaviour distribution is a function of the state: the device checks every queue
+    bitwise (queue_dist), and a log that does not qualify falls back to the probability hot records — results unchanged."""
+    import torch
+    from offsim4rl_b200 import _abi as abi
+    g = make_log(91, 60000, 40, 4, ep_len=20)
+    nS = 40
+    log = device_log(ob, g, n_buckets=nS, hot_records="tail")
+    assert log.hot_kind == abi.HOT_TAIL
+    off, order = O.bucket(g["z"], nS)
+    qd = log.queue_dist.cpu().numpy()
+    first = order[off[:-1]]
+    assert np.array_equal(qd[:, :4], g["p_log"][first])                               # the queue's distribution, bit for bit
+    assert np.array_equal(qd[:, 4].view(np.int32), np.full(nS, 3))                    # constant + tame
+    w = log.hot.view(torch.int32).view(-1, 2).cpu().numpy()
+    assert np.array_equal(w[:, 0].view(np.float32), g["r"][order])
+    assert np.array_equal(w[:, 1] & 0x1FFFFFFF, g["z_next"][order]) and np.array_equal((w[:, 1] >> 29) & 3, g["a"][order])
+    assert np.array_equal((w[:, 1] >> 31) & 1, g["done"][order].astype(np.int32))
+    assert log.seeded(3).hot_kind == abi.HOT_TAIL
+    # one record with another distribution: the log no longer qualifies
+    g2 = dict(g)
+    g2["p_log"] = g["p_log"].copy()
+    g2["p_log"][12345] = np.array([0.4, 0.3, 0.2, 0.1], dtype=np.float32)
+    log2 = device_log(ob, g2, n_buckets=nS, hot_records="tail")
+    assert log2.hot_kind == abi.HOT_PROBS and log2.queue_dist is None
+    plain = device_log(ob, g2, n_buckets=nS)
+    runs = []
+    for lg, aos in ((log2, True), (plain, False)):
+        sim = ob.BatchedPSRS(lg, 500, rng="philox", seed=8, ring=True, ring_seed=2, lanes=1, aos_state=aos)
+        runs.append(sim.run_qlearn(nS, 30, gamma=0.9, alpha=0.1, epsilon=0.2, max_steps=200, trace_cap=200))
+    assert torch.equal(runs[0].trace_row, runs[1].trace_row) and torch.equal(runs[0].Q, runs[1].Q)
 
 
 def test_accept_filter_never_changes_a_decision(ob):
@@ -601,7 +634,7 @@ def test_learner_curve_agrees_with_the_reference_itself_under_independent_rngs_k
     """north_star's third bar for the LEARNER: tests/golden/learner_curves.npz holds the per-episode returns of 320 runs of
     the UNMODIFIED reference `qlearn_psrs` (psrs.py:119-185), each with the reference's own generators (NumPy PCG64
     rejection uniforms, MT19937 tie-breaks); here 6000 GPU replicas learn on the same log with Philox streams (float32 Q,
-    16-byte hot records, AoS state, one thread per replica: the benchmarked kernel — or the float64 plain layout).  Per episode index: two-sample KS on the
+    TAIL hot records, AoS state, one thread per replica: the benchmarked kernel — or the float64 plain layout).  Per episode index: two-sample KS on the
     returns, and the means of the learning curve within 4 standard errors."""
     import torch
     from scipy.stats import ks_2samp
@@ -611,7 +644,7 @@ def test_learner_curve_agrees_with_the_reference_itself_under_independent_rngs_k
     z = g["z"].astype(np.int64)
     prod = layout == "production"
     log = ob.BucketedLog(z=z, z_next=g["z_next"].astype(np.int64), action=g["a"].astype(np.int64), reward=g["r"], terminal=g["done"],
-                         p_log=g["pb_state"][z], steps=g["t"], n_buckets=nS, hot_records=16 if prod else False)
+                         p_log=g["pb_state"][z], steps=g["t"], n_buckets=nS, hot_records="tail" if prod else False)
     # GPU replica ids continue after the ids whose data order the reference runs followed (10**7 + i, i < 320)
     sim = ob.BatchedPSRS(log, R, rng="philox", seed=424242, ring=True, ring_seed=int(g["ring_seed"]),
                          replica_id0=int(g["replica_id0"]) + 1000, lanes=1 if prod else 4, aos_state=prod)

@@ -66,17 +66,21 @@ def test_c4_production_learner_matches_c_oracle_on_sampled_replicas(ob, c4, c4_h
     from oracle import c_oracle as CO
     cols, log8 = c4
     clog = c4_host
-    # the benchmark's own layout: 16-byte hot records (bench.py)
+    # the benchmark's own layout: TAIL hot records (bench.py) — the synthetic behaviour policy is a function of the state
+    from offsim4rl_b200 import _abi as abi
     log = ob.BucketedLog(z=cols["z"], z_next=cols["z_next"], action=cols["action"], reward=cols["reward"],
                          terminal=cols["terminal"], p_log=cols["p_log"], steps=cols["steps"], n_buckets=NS, z_offset=0,
-                         hot_records=16)
-    assert torch.equal(log.records, log8.records)
-    w16 = log.hot.view(torch.int32).view(-1, 4)[:N]
+                         hot_records="tail")
+    assert log.hot_kind == abi.HOT_TAIL and torch.equal(log.records, log8.records)
+    w = log.hot.view(torch.int32).view(-1, 2)[:N]
     rec = log.records.view(torch.int32).view(-1, 8)[:N]
-    assert torch.equal(w16[:, :2], log8.hot.view(torch.int32).view(-1, 2)[:N])            # the 8-byte hot record ...
-    assert torch.equal(w16[:, 2], rec[:, 4])                                                # ... + reward
-    assert torch.equal(w16[:, 3] & 0x7FFFFFFF, rec[:, 5]) and torch.equal((w16[:, 3] >> 31) & 1, (rec[:, 7] >> 8) & 1)
-    del w16, rec
+    assert torch.equal(w[:, 0], rec[:, 4])                                                 # reward
+    assert torch.equal(w[:, 1] & 0x1FFFFFFF, rec[:, 5]) and torch.equal((w[:, 1] >> 29) & 3, rec[:, 7] & 0xFF)
+    assert torch.equal((w[:, 1] >> 31) & 1, (rec[:, 7] >> 8) & 1)
+    first = log.offsets[:-1].long()
+    assert torch.equal(log.queue_dist[:, :4].view(torch.int32), rec[first, :4])           # every queue's one distribution
+    assert bool((log.queue_dist[:, 4].view(torch.int32) == 3).all())
+    del w, rec
     assert np.array_equal(log.offsets.cpu().numpy(), clog.offsets)
     assert np.array_equal(log.order[:4096].cpu().numpy(), clog.order[:4096]) and np.array_equal(log.order[-4096:].cpu().numpy(), clog.order[N - 4096:N])
     R, T, id0 = 125_000, 300, 3 * 125_000                      # the shard of rank 3 of 8
