@@ -36,6 +36,9 @@ struct LearnerCold {
   float4 qdist[kLT];  // the logged distribution of the current state's queue
   uint2 lim[4][kLT];  // per action: accept below .x, reject above .y (high word of the uniform), see make_limits
   uint2 park[kLT];    // a parked outcome: reward bits, next state | action | terminal
+  float4 nq[kLT];     // staged next state: its Q row ...
+  int4 nb[kLT];       // ... and its queue {bucket or -1, CSR start, length, this replica's cursor}
+  unsigned nstart[kLT];  // ... ring offset
   uint4 blk[kLT];     // the rejection stream's block that holds draw `draws` (block index draws >> 2)
   int ep_index[kLT], ep_len_count[kLT], ep_t[kLT], ep_open[kLT], init_cursor[kLT], status[kLT], n_acc[kLT], pn_ok[kLT],
       eps_episode[kLT], budget[kLT], qtame[kLT];
@@ -46,7 +49,7 @@ struct LearnerCold {
 // What the pop loop needs of the agent's distribution and the queue's.  With t_j = p_j / pi_j and inv_m = min_j t_j the
 // threshold of a record with action a is thr_a = inv_m / t_a (psrs.py:55-57 rearranged), and a pop's uniform is known to the
 // pre-filter through its high word hi (u in [hi, hi + 1) * 2^-32).  Per STEP and action the band around the float32 estimate
-// of thr_a (within 2^-19 relative of the exact value under the guards; band 2^-16) becomes two 32-bit limits:
+// of thr_a (within 2^-19 relative of the exact value under the guards; band 2^-15) becomes two 32-bit limits:
 //     hi <  lo32[a]  ==>  u <  thr_a: accept          hi >  hi32[a]  ==>  u >  thr_a: reject          else: the exact rule
 // so a pop costs an 8-byte shared-memory load and two integer compares.  A failed guard (untamed queue distribution, policy
 // entry outside {0} U [2^-40, 1]) sets lo32 = 0, hi32 = 2^32 - 1: every pop goes to the exact rule.
@@ -61,13 +64,14 @@ __device__ __forceinline__ void make_limits(float4 p, bool ok, float ib, float i
   const float inv_m = fminf(fminf(t[0], t[1]), fminf(t[2], t[3]));
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
-    const float thr = __fdiv_rn(inv_m, t[a]);  // 0 when pi_a = 0 (t_a = +inf); NaN / inf only when a guard failed
-    // in units of 2^-32, with one unit of slack on either side for the truncation of u to hi
-    const double lo = (double)thr * (1.0 - 1.52587890625e-5) * 4294967296.0 - 2.0;
-    const double hi = (double)thr * (1.0 + 1.52587890625e-5) * 4294967296.0 + 2.0;
+    const float thr = __fdiv_rn(inv_m, t[a]);  // 0 when pi_a = 0 (t_a = +inf); NaN only when a guard failed; <= 1 otherwise
+    // in units of 2^-32, rounded outward, with two units of slack on either side for the truncation of u to hi; the
+    // float32 products are exact to 2^-24 relative, which the 2^-15 factors absorb (band 2^-16 + rounding)
+    const float lo = __fmul_rd(thr, 4294836224.0f /* (1 - 2^-15) 2^32 */), hi = __fmul_ru(thr, 4295098368.0f /* (1 + 2^-15) 2^32 */);
     const bool fine = ok && (thr == thr);
-    lim[a].x = !fine ? 0u : (lo <= 0.0) ? 0u : (lo >= 4294967295.0) ? 0xffffffffu : __double2uint_rd(lo);
-    lim[a].y = !fine ? 0xffffffffu : (hi >= 4294967295.0) ? 0xffffffffu : __double2uint_ru(hi);
+    const unsigned lo32 = __float2uint_rd(lo), hi32 = __float2uint_ru(hi);  // saturating conversions
+    lim[a].x = !fine ? 0u : (lo32 > 2u ? lo32 - 2u : 0u);
+    lim[a].y = !fine ? 0xffffffffu : (hi32 < 0xfffffffdu ? hi32 + 2u : 0xffffffffu);
   }
 }
 
@@ -165,6 +169,46 @@ __global__ void __launch_bounds__(kLT, OLS_LEARNER_MINB) learner_kernel(ols_queu
 
   const int batch = cfg.batch_lanes > 0 ? min(cfg.batch_lanes, 32) : 20;
 
+  // Stage the next state of a parked, accepted transition: its AoS entry (cursor + Q row), its queue and that queue's
+  // distribution go to shared memory, and the hot span the next step will pop first is pulled toward L2.  Runs right before
+  // the update (the entry was prefetched at the accept, so for lanes parked a round or more the loads hit L2).  All loads are
+  // issued before any is consumed.  Tried and dropped: staging one loop iteration after the accept, while the lane is still
+  // parked (the extra divergent block costs more issue slots than the hidden latency buys: 165 ms against 150 ms), and
+  // prefetching the span a rejected round would continue with (173 ms).
+  auto stage_next = [&]() {
+    const uint32_t zw = C.park[tid].y;
+    const int Z2 = ((int)(zw << 3)) >> 3;
+    const bool inr = (Z2 >= 0 && Z2 < nS), want_q = inr && !(zw >> 31);
+    float4 ea = make_float4(0.f, 0.f, 0.f, 0.f), eb = ea, qd = ea;
+    int lo = 0, hi = 0, qf = 0;
+    if (inr)
+      asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=f"(ea.x), "=f"(ea.y), "=f"(ea.z), "=f"(ea.w), "=f"(eb.x), "=f"(eb.y), "=f"(eb.z), "=f"(eb.w)
+                   : "l"(aos + (size_t)Z2 * 32));
+    if (want_q) {
+      lo = __ldg(q.offsets + Z2);
+      hi = __ldg(q.offsets + Z2 + 1);
+      qd = __ldg((const float4*)q.queue_dist + 2 * (size_t)Z2);
+      qf = __ldg((const int*)q.queue_dist + 8 * (size_t)Z2 + 4);
+    }
+    const bool fresh = (__float_as_int(ea.y) == cfg.state_epoch);  // stale entries read as cursor 0 / Q 0
+    const int cur = fresh ? __float_as_int(ea.x) : 0;
+    C.nq[tid] = fresh ? eb : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int len = hi - lo;
+    const bool next_ok = want_q && len > 0;   // psrs.py:44 — a state never logged as a from-state has no queue
+    unsigned start = 0;
+    if (next_ok) {
+      if (R.ring_mode) start = ols_ring_start(C.h_rep[tid], (uint32_t)Z2, (uint32_t)len);
+      C.qdist[tid] = qd;
+      C.qtame[tid] = qf & 2;
+      uint32_t pos = start + (uint32_t)cur;
+      if (pos >= (uint32_t)len) pos -= (uint32_t)len;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(hot + (size_t)(uint32_t)(lo + (int)pos)));
+    }
+    C.nb[tid] = make_int4(next_ok ? Z2 : -1, next_ok ? lo : 0, next_ok ? len : 0, next_ok ? cur : 0);
+    C.nstart[tid] = start;
+  };
+
   while (__any_sync(kFull, live)) {
     // =========================================================== the step block: episode start + the agent's action choice
     if (live && need_step) {
@@ -256,6 +300,7 @@ __global__ void __launch_bounds__(kLT, OLS_LEARNER_MINB) learner_kernel(ols_queu
         live = false;
       }
     }
+
 
     // =========================================================== one pop round: psrs.py:39-57 over four queue records
     if (live && !pend) {
@@ -361,18 +406,12 @@ __global__ void __launch_bounds__(kLT, OLS_LEARNER_MINB) learner_kernel(ols_queu
       const int A = (int)((p_zw >> 29) & 3u);
       if (accepted) {
         const double Rw = (double)__uint_as_float(p_rw);
-        AosEntry e2;
-        e2.cursor = 0;
-        e2.q[0] = e2.q[1] = e2.q[2] = e2.q[3] = 0.f;
-        if (Z2 >= 0 && Z2 < nS) e2 = load_aos(aos, Z2, cfg.state_epoch);  // the next state's cursor AND Q row: one sector
-        Bucket B;
-        const bool next_ok = done ? false : load_bucket(q, R, C.h_rep[tid], nullptr, Z2, B, true, e2.cursor);
+        stage_next();
+        const float4 nq = C.nq[tid];
+        const int4 nb = C.nb[tid];
+        const bool next_ok = nb.x >= 0;
         if (!done) {
-          b_cur = B.b; b_lo = B.lo; b_len = B.len; b_pos = B.cur; b_start = B.start;
-          if (next_ok) {
-            C.qdist[tid] = __ldg((const float4*)q.queue_dist + 2 * (size_t)b_cur);
-            C.qtame[tid] = __ldg((const int*)q.queue_dist + 8 * (size_t)b_cur + 4) & 2;
-          }
+          b_cur = nb.x; b_lo = nb.y; b_len = nb.z; b_pos = nb.w; b_start = C.nstart[tid];
         }
         if (next_ok && b_cur == b_done) b_pos = cur_done;  // a self-loop: the cursor in memory is still the old one
         bucket_valid = next_ok;
@@ -381,7 +420,7 @@ __global__ void __launch_bounds__(kLT, OLS_LEARNER_MINB) learner_kernel(ols_queu
           new_status = OLS_NO_QUEUE;
         } else {
           const double alpha = __ldg(cfg.alpha + ep_index);
-          const float n0 = e2.q[0], n1 = nA > 1 ? e2.q[1] : -INFINITY, n2 = nA > 2 ? e2.q[2] : -INFINITY, n3 = nA > 3 ? e2.q[3] : -INFINITY;
+          const float n0 = nq.x, n1 = nA > 1 ? nq.y : -INFINITY, n2 = nA > 2 ? nq.z : -INFINITY, n3 = nA > 3 ? nq.w : -INFINITY;
           float boot = n0;  // Q[S_].max(), left to right
           boot = (n1 > boot) ? n1 : boot;
           boot = (n2 > boot) ? n2 : boot;

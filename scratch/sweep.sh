@@ -7,7 +7,10 @@ for a in "$@"; do
   echo "### $a" >> gpurun_out/${tag}_sweep.jsonl
   # an item may start with VAR=value settings (e.g. OLS_B200_LIB=variants/libols_b200_mb6.so)
   envs=""; rest="$a"
-  while [[ "$rest" == [A-Z_]*=* ]]; do envs="$envs ${rest%% *}"; rest="${rest#* }"; done
+  while [[ "$rest" == [A-Z_]*=* ]]; do
+    envs="$envs ${rest%% *}"
+    if [[ "$rest" == *" "* ]]; then rest="${rest#* }"; else rest=""; fi
+  done
   env $envs timeout 300 python bench.py --steps 3 --warmup 2 --skip-cpu --skip-e2e --skip-stress $rest >> gpurun_out/${tag}_sweep.jsonl 2>> gpurun_out/${tag}_sweep.err
 done
 python - <<PY
