@@ -341,7 +341,7 @@ def run_reference(args, wl, rank, world):
     }))
 
 
-def gather_stress_leg(ob, torch, dev, hbm_peak, launches=5, warm=3, hot=True):
+def gather_stress_leg(ob, torch, dev, hbm_peak, launches=5, warm=3, hot="tail"):
     """Second half of the BASELINE metric ("PSRS gather HBM GB/s vs peak"): the rejection-heavy configuration
     (BASELINE.json configs[4], workload c5) is the streaming-gather regime.  Rank 0, one GPU, a few launches."""
     wl = WORKLOADS["c5"]
@@ -447,7 +447,7 @@ def main():
     ap.add_argument("--prefetch", type=int, default=-1)
     ap.add_argument("--ppl", type=int, default=0, help="records per lane per round (0 = auto)")
     ap.add_argument("--slices", type=int, default=-1, help="time slices of the fused run: -1 auto, 0 off, k forced")
-    ap.add_argument("--hot", choices=["probs", "tail"], help="hot record format (default: tail for the one-lane Q-learner, else probs)")
+    ap.add_argument("--hot", choices=["probs", "tail"], help="hot record format (default: tail for the one-lane Q-learner and for evaluation, else probs)")
     ap.add_argument("--batch-lanes", type=int, default=0, help="one-lane learner: lanes per update batch (0 = library default)")
     ap.add_argument("--no-hot", action="store_true", help="pop from the 32-byte records only (no 8-byte hot records)")
     ap.add_argument("--no-aos", action="store_true", help="separate cursor / Q arrays instead of one 32-byte entry per (replica, state)")
@@ -511,7 +511,7 @@ def main():
     use_hot = nA <= 4 and not args.no_hot and ((qlearn and not args.no_aos and args.workload == "c4") or not qlearn)
     # the one-thread-per-replica Q-learner reads TAIL hot records (reward, next state, action, terminal: the synthetic
     # behaviour distribution is a function of the state, so the accept rule needs only the action); evaluation PROBS ones
-    hot_kind = (args.hot or ("tail" if (qlearn and wl["lanes"] == 1) else "probs")) if use_hot else False
+    hot_kind = (args.hot or ("tail" if (not qlearn or wl["lanes"] == 1) else "probs")) if use_hot else False
     log = ob.BucketedLog(z=cols["z"], z_next=cols["z_next"], action=cols["action"], reward=cols["reward"],
                          terminal=cols["terminal"], p_log=cols["p_log"], steps=cols["steps"], n_buckets=nS, z_offset=0, device=dev,
                          keep_columns=True, hot_records=hot_kind)
@@ -663,7 +663,7 @@ def main():
         sim = Q = res = None        # release the c4 state (25 GB) before building the c5 log
         torch.cuda.empty_cache()
         try:
-            stress = gather_stress_leg(ob, torch, dev, hbm_peak, hot=not args.no_hot)
+            stress = gather_stress_leg(ob, torch, dev, hbm_peak, hot=False if args.no_hot else (args.hot or "tail"))
         except Exception as exc:   # a side leg must never take the headline line down
             stress = {"error": repr(exc)}
         torch.cuda.empty_cache()

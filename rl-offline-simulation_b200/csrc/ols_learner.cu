@@ -46,35 +46,6 @@ struct LearnerCold {
   unsigned h_rep[kLT];
 };
 
-// What the pop loop needs of the agent's distribution and the queue's.  With t_j = p_j / pi_j and inv_m = min_j t_j the
-// threshold of a record with action a is thr_a = inv_m / t_a (psrs.py:55-57 rearranged), and a pop's uniform is known to the
-// pre-filter through its high word hi (u in [hi, hi + 1) * 2^-32).  Per STEP and action the band around the float32 estimate
-// of thr_a (within 2^-19 relative of the exact value under the guards; band 2^-15) becomes two 32-bit limits:
-//     hi <  lo32[a]  ==>  u <  thr_a: accept          hi >  hi32[a]  ==>  u >  thr_a: reject          else: the exact rule
-// so a pop costs an 8-byte shared-memory load and two integer compares.  A failed guard (untamed queue distribution, policy
-// entry outside {0} U [2^-40, 1]) sets lo32 = 0, hi32 = 2^32 - 1: every pop goes to the exact rule.
-__device__ __forceinline__ void make_limits(float4 p, bool ok, float ib, float it, int a_star, int nA, uint2 (&lim)[4]) {
-  const float inf = __int_as_float(0x7f800000);
-  float t[4];
-  // padding entries (j >= n_actions) hold p = 1 in the queue's distribution and 1/pi = +inf: t_j = +inf never wins the min
-  t[0] = p.x * ((a_star == 0) ? it : ib);
-  t[1] = p.y * ((nA <= 1) ? inf : (a_star == 1) ? it : ib);
-  t[2] = p.z * ((nA <= 2) ? inf : (a_star == 2) ? it : ib);
-  t[3] = p.w * ((nA <= 3) ? inf : (a_star == 3) ? it : ib);
-  const float inv_m = fminf(fminf(t[0], t[1]), fminf(t[2], t[3]));
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const float thr = __fdiv_rn(inv_m, t[a]);  // 0 when pi_a = 0 (t_a = +inf); NaN only when a guard failed; <= 1 otherwise
-    // in units of 2^-32, rounded outward, with two units of slack on either side for the truncation of u to hi; the
-    // float32 products are exact to 2^-24 relative, which the 2^-15 factors absorb (band 2^-16 + rounding)
-    const float lo = __fmul_rd(thr, 4294836224.0f /* (1 - 2^-15) 2^32 */), hi = __fmul_ru(thr, 4295098368.0f /* (1 + 2^-15) 2^32 */);
-    const bool fine = ok && (thr == thr);
-    const unsigned lo32 = __float2uint_rd(lo), hi32 = __float2uint_ru(hi);  // saturating conversions
-    lim[a].x = !fine ? 0u : (lo32 > 2u ? lo32 - 2u : 0u);
-    lim[a].y = !fine ? 0xffffffffu : (hi32 < 0xfffffffdu ? hi32 + 2u : 0xffffffffu);
-  }
-}
-
 // The cold end of a pop round: slots whose high word fell inside the band are decided by the exact rule psrs.py:53-57 on
 // the queue's distribution, in queue order; returns the first accepting slot (4 = none).
 __device__ __noinline__ int resolve_round(const float* dist, const double* eps_ptr, uint64_t seed, uint64_t rid, uint64_t draws,
@@ -286,8 +257,13 @@ __global__ void __launch_bounds__(kLT, OLS_LEARNER_MINB) learner_kernel(ols_queu
           C.pn_ok[tid] = (okb && okt && (base > 0.f || top > 0.f)) ? 1 : 0;
           C.eps_episode[tid] = ep_index0;
         }
+        // the accept rule of this step as per-action limits (make_limits, ols_sim_kernels.cuh): the queue's one distribution
+        // against the epsilon-greedy policy — two cached reciprocals and which action holds the larger probability
         uint2 lim[4];
-        make_limits(C.qdist[tid], C.qtame[tid] != 0 && C.pn_ok[tid] != 0, C.ipn_base[tid], C.ipn_top[tid], a_star, nA, lim);
+        const float inf = __int_as_float(0x7f800000), ib = C.ipn_base[tid], it = C.ipn_top[tid];
+        const float ipn4[4] = {(a_star == 0) ? it : ib, (nA <= 1) ? inf : (a_star == 1) ? it : ib, (nA <= 2) ? inf : (a_star == 2) ? it : ib,
+                               (nA <= 3) ? inf : (a_star == 3) ? it : ib};
+        make_limits(C.qdist[tid], C.qtame[tid] != 0 && C.pn_ok[tid] != 0, ipn4, lim);
 #pragma unroll
         for (int a = 0; a < 4; ++a) C.lim[a][tid] = lim[a];
       }

@@ -212,8 +212,11 @@ extern "C" int ols_run(const ols_queues_t* q, const ols_replicas_t* r, const ols
   const bool hot_tail = q->hot && q->hot_kind == OLS_HOT_TAIL;
   const bool fast_learner = hot_tail && q->queue_dist && !q->p_log64 && c->agent == OLS_AGENT_QLEARN && c->lanes == 1 && c->state_aos &&
                             r->rng_mode == OLS_RNG_PHILOX;
+  // ... and fixed-policy evaluation (run_kernel<..., HOT = 2>)
+  const bool tail_eval = hot_tail && q->queue_dist && !q->p_log64 && c->agent == OLS_AGENT_FIXED_PI && r->rng_mode == OLS_RNG_PHILOX &&
+                         c->reject_mode == OLS_REJECT_DEFAULT;
   ols_queues_t q_plain = *q;
-  if (hot_tail && !fast_learner) {
+  if (hot_tail && !fast_learner && !tail_eval) {
     q_plain.hot = nullptr;
     q = &q_plain;
   }

@@ -578,6 +578,118 @@ __device__ __forceinline__ int pop_round_hot(const ols_queues_t& q, int G, int s
   return result;
 }
 
+// ---- logs whose behaviour distribution is a function of the state (every queue holds ONE distribution, ols_queues_t.queue_dist)
+// With t_j = p_j / pi_j and inv_m = min_j t_j the threshold of a record with action a is thr_a = inv_m / t_a (psrs.py:55-57
+// rearranged): it depends on the record only through its ACTION.  A pop's uniform is known to the pre-filter through its
+// high word hi (u in [hi, hi + 1) * 2^-32).  Per STEP and action the band around the float32 estimate of thr_a (within 2^-19
+// relative of the exact value under the guards; band 2^-15) becomes two 32-bit limits:
+//     hi <  lim.x  ==>  u <  thr_a: accept          hi >  lim.y  ==>  u >  thr_a: reject          else: the exact rule
+// so a pop costs an 8-byte shared-memory load and two integer compares.  A failed guard (untamed queue distribution, policy
+// entry outside {0} U [2^-40, 1]) sets lim = {0, 2^32 - 1}: every pop goes to the exact rule.
+__device__ __forceinline__ void make_limits(float4 p, bool ok, const float (&ipn)[4], uint2 (&lim)[4]) {
+  // padding entries (j >= n_actions) hold p = 1 in the queue's distribution and 1/pi = +inf: t_j = +inf never wins the min
+  const float t[4] = {p.x * ipn[0], p.y * ipn[1], p.z * ipn[2], p.w * ipn[3]};
+  const float inv_m = fminf(fminf(t[0], t[1]), fminf(t[2], t[3]));
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const float thr = __fdiv_rn(inv_m, t[a]);  // 0 when pi_a = 0 (t_a = +inf); NaN only when a guard failed; <= 1 otherwise
+    // in units of 2^-32, rounded outward, with two units of slack on either side for the truncation of u to hi; the
+    // float32 products are exact to 2^-24 relative, which the 2^-15 factors absorb (band 2^-16 + rounding)
+    const float lo = __fmul_rd(thr, 4294836224.0f /* (1 - 2^-15) 2^32 */), hi = __fmul_ru(thr, 4295098368.0f /* (1 + 2^-15) 2^32 */);
+    const bool fine = ok && (thr == thr);
+    const unsigned lo32 = __float2uint_rd(lo), hi32 = __float2uint_ru(hi);  // saturating conversions
+    lim[a].x = !fine ? 0u : (lo32 > 2u ? lo32 - 2u : 0u);
+    lim[a].y = !fine ? 0xffffffffu : (hi32 < 0xfffffffdu ? hi32 + 2u : 0xffffffffu);
+  }
+}
+
+// ONE pop round over TAIL hot records (OLS_HOT_TAIL: { reward; next state | action | terminal }, 8 bytes per record): same
+// contract as pop_round_hot, but the accept rule is the per-step limits `lim` (the group's Cold block) applied to the
+// record's action — no per-record arithmetic — and the accepted pop's fields come from the hot record itself; the full
+// record is read only inside the band (the exact rule needs nothing of it but the queue's distribution) or when the caller
+// needs the log row (`need_row`: row trace, or agent observation ids distinct from the state ids).
+template <typename PnFn>
+__device__ __forceinline__ int pop_round_tail(const ols_queues_t& q, int G, int sub, int gbase, unsigned gmask, bool active,
+                                              uint64_t rid, const volatile uint2* lim, PnFn pn_fn, const ols_philox_keys& PK,
+                                              int compute_mode, bool need_row, Bucket& B, uint64_t& draws, float4& win_tail) {
+  constexpr int PPL = 4, kRec = 32;
+  const int nA = q.n_actions;
+  int result = active ? kPopContinue : kPopIdle;
+  const int remaining = B.len - B.cur;
+  if (active && remaining <= 0) {
+    result = OLS_QUEUE_EMPTY;
+    active = false;
+  }
+  const int align = (int)(draws & 3);  // rounds are aligned to a multiple of four draws: each lane needs exactly ONE stream block
+  const int n_eval = active ? min(G * PPL - align, remaining) : 0;
+  const int k0 = sub * PPL - align;
+  uint2 h[PPL];
+  bool valid[PPL];
+#pragma unroll
+  for (int i = 0; i < PPL; ++i) {
+    valid[i] = (unsigned)(k0 + i) < (unsigned)n_eval;
+    h[i] = make_uint2(0u, 0u);
+    if (valid[i]) {
+      uint32_t pos = B.start + (uint32_t)(B.cur + k0 + i);
+      if (pos >= (uint32_t)B.len) pos -= (uint32_t)B.len;
+      h[i] = __ldg((const uint2*)q.hot + (size_t)(uint32_t)(B.lo + (int32_t)pos));
+    }
+  }
+  ols_u4 o = {0u, 0u, 0u, 0u};
+  if (valid[0] || valid[1] || valid[2] || valid[3]) o = ols_stream_block(PK, rid, 0u, (draws + (uint64_t)(int64_t)k0) >> 2);
+  int mine = PPL;
+#pragma unroll
+  for (int i = PPL - 1; i >= 0; --i) {
+    const unsigned a = (h[i].y >> 29) & 3u;
+    const uint2 lm = make_uint2(lim[a].x, lim[a].y);
+    const uint32_t hi = ols_u4_word(o, i);
+    int dec = (!valid[i] || hi > lm.y) ? 0 : (hi < lm.x) ? 1 : 2;
+    if (dec == 2) {
+      const double ue = ols_stream_uniform(PK, rid, 0u, draws + (uint64_t)(int64_t)(k0 + i));
+      dec = (int)accept_slow(pn_fn, q.queue_dist + 8 * (size_t)B.b, nullptr, nA, (int)a, ue, compute_mode);
+    }
+    mine = (dec == 1) ? i : mine;
+  }
+  // ---- first accepting pop of the group, in queue order; its hot record goes to every lane of the group
+  int first_acc = 1 << 20;
+  uint2 won = (mine == 0) ? h[0] : (mine == 1) ? h[1] : (mine == 2) ? h[2] : h[3];
+  if (G == 1) {
+    if (mine < PPL) first_acc = mine - align;
+  } else {
+    const unsigned g_any = (__ballot_sync(kFull, mine < PPL) >> gbase) & gmask;
+    const int w = g_any ? __ffs(g_any) - 1 : 0;
+    const int wi = __shfl_sync(kFull, mine, gbase + w);
+    won.x = __shfl_sync(kFull, won.x, gbase + w);
+    won.y = __shfl_sync(kFull, won.y, gbase + w);
+    if (g_any) first_acc = w * PPL + wi - align;
+  }
+  int consumed = 0;
+  bool took = false;
+  if (active) {
+    if (first_acc < (1 << 20)) {
+      consumed = first_acc + 1;
+      took = true;
+    } else {
+      consumed = n_eval;
+    }
+  }
+  if (took) {
+    const int z2 = ((int)(won.y << 3)) >> 3;
+    const int action = (int)((won.y >> 29) & 3u), term = (int)(won.y >> 31);
+    int row = -1;
+    if (need_row) {
+      uint32_t pos = B.start + (uint32_t)(B.cur + first_acc);
+      if (pos >= (uint32_t)B.len) pos -= (uint32_t)B.len;
+      row = __ldg((const int32_t*)((const char*)q.records + (size_t)(uint32_t)(B.lo + (int32_t)pos) * kRec) + 6);
+    }
+    win_tail = make_float4(__uint_as_float(won.x), __int_as_float(z2), __int_as_float(row), __uint_as_float(ols_pack_meta(action, term, 1)));
+    result = OLS_RUNNING;
+  }
+  B.cur += consumed;
+  draws += (uint64_t)consumed;
+  return result;
+}
+
 // ------------------------------------------------------------------------------------------ kernels: step
 template <int NV, int RNG>
 __global__ void __launch_bounds__(kThreads) step_kernel(ols_queues_t q, ols_replicas_t R, const uint8_t* mask,
@@ -719,6 +831,7 @@ struct __align__(16) Cold {
   float qrow[4];            // AoS Q-learning: Q[S, :] of the current state (the bootstrap row of the previous step)
   unsigned h_rep;           // ring hash of the replica
   int pad[3];
+  uint2 lim[4];             // TAIL hot records: per action, accept below .x / reject above .y (high word of the uniform)
 };
 
 // 128-bit accesses to a group's Cold block (the struct is volatile for the scalar fields)
@@ -755,7 +868,7 @@ struct EpsGreedySource {
 // The run loop.  Lane groups of a warp are DECOUPLED: every iteration each live group executes one pop round
 // against its own queue; a group whose round accepted a record runs the learner update and prepares its next
 // step in the same iteration (predicated), so no group waits for the longest reject chain in its warp.
-template <int NV, int AGENT, typename QT, int RNG, int PPL, bool AOS = false, int GT = 0, bool HOT = false>
+template <int NV, int AGENT, typename QT, int RNG, int PPL, bool AOS = false, int GT = 0, int HOT = 0>
 __global__ void __launch_bounds__((GT == 1 ? OLS_G1_THREADS : kThreads), (NV == 1 ? (GT == 1 ? OLS_MINB_G1 : OLS_MINB) : 2)) run_kernel(ols_queues_t q, ols_replicas_t R, ols_run_t cfg,
                                                                                   StagePlan plan, ols_philox_keys PK) {
   constexpr int NA = 4 * NV;
@@ -765,6 +878,7 @@ __global__ void __launch_bounds__((GT == 1 ? OLS_G1_THREADS : kThreads), (NV == 
   constexpr bool QCARRY = AOS && AGENT == OLS_AGENT_QLEARN;
   static_assert(!AOS || (NV == 1 && sizeof(QT) == 4 && AGENT != OLS_AGENT_FIXED_PI), "AoS state: float32 learners, <= 4 actions");
   static_assert(!HOT || (NV == 1 && RNG == RNGT_PHILOX && PPL == 4), "hot records: <= 4 actions, Philox uniforms, 4 per lane");
+  static_assert(HOT != 2 || (AGENT == OLS_AGENT_FIXED_PI && !AOS), "TAIL hot records: fixed-policy evaluation here, the Q-learner in ols_learner.cu");
   extern __shared__ __align__(16) unsigned char s_mem[];
   const int nA = q.n_actions;
   const int nS = cfg.n_states;
@@ -928,6 +1042,10 @@ __global__ void __launch_bounds__((GT == 1 ? OLS_G1_THREADS : kThreads), (NV == 
       float ib = 0.f, it = 0.f;
       int pn_ok = 0;
       bool new_eps = false;
+      uint2 step_lim[4];
+      bool have_lim = false;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) step_lim[a] = make_uint2(0u, 0xffffffffu);
       if (AGENT == OLS_AGENT_QLEARN && new_status < 0) {
         // tabular.py:24-32 epsilon_greedy_policy on the single row Q[[S], :] (psrs.py:158)
         if (!row_valid && !fresh) {
@@ -1003,6 +1121,14 @@ __global__ void __launch_bounds__((GT == 1 ? OLS_G1_THREADS : kThreads), (NV == 
         finish_policy<NA>(P, [=](int j) -> double {
           return is64 ? __ldg((const double*)pi_tab + off + j) : (double)__ldg((const float*)pi_tab + off + j);
         }, nA);
+        if constexpr (HOT == 2) {
+          // the accept rule of this step as per-action limits: the queue's one distribution against pi[S]
+          const float4 qd = __ldg((const float4*)q.queue_dist + 2 * (size_t)B.b);
+          const bool tame = (__ldg((const int*)q.queue_dist + 8 * (size_t)B.b + 4) & 2) != 0;
+          const float ipn4[4] = {P.ipn[0], P.ipn[1 % NA], P.ipn[2 % NA], P.ipn[3 % NA]};
+          make_limits(qd, P.ok && tame, ipn4, step_lim);
+          have_lim = true;
+        }
       }
       __syncwarp(gm);
       // ---------------- phase 2: writes
@@ -1022,6 +1148,13 @@ __global__ void __launch_bounds__((GT == 1 ? OLS_G1_THREADS : kThreads), (NV == 
         C->ep_disc = 1.0;
       }
       if (used_tie) C->ties = ties0 + 1;
+      if (have_lim) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          C->lim[a].x = step_lim[a].x;
+          C->lim[a].y = step_lim[a].y;
+        }
+      }
       if (new_eps) {
         C->ipn_base = ib;
         C->ipn_top = it;
@@ -1053,7 +1186,10 @@ __global__ void __launch_bounds__((GT == 1 ? OLS_G1_THREADS : kThreads), (NV == 
     // ---- env.step(p), one round of it: psrs.py:39-57
     float4 tail = make_float4(0.f, 0.f, 0.f, 0.f);
     int res;
-    if constexpr (HOT) {
+    if constexpr (HOT == 2) {
+      res = pop_round_tail(q, G, sub, gbase, gmask, live, rid, C->lim, pn_fn, PK, cfg.compute_mode,
+                           cfg.trace_row != nullptr || q.s_next != nullptr, B, draws, tail);
+    } else if constexpr (HOT == 1) {
       if (AGENT == OLS_AGENT_QLEARN) {
         EpsGreedySource<NA> src;
         src.C = C;
@@ -1332,7 +1468,9 @@ inline cudaError_t launch_run_rng(const ols_queues_t& q, const ols_replicas_t& r
   if constexpr (NV == 1 && AGENT == OLS_AGENT_FIXED_PI) {
     // fixed-policy evaluation over hot records (the streaming-reject regime reads 8 instead of 32 bytes per pop)
     if (q.hot != nullptr && r.rng_mode == OLS_RNG_PHILOX && c.reject_mode == OLS_REJECT_DEFAULT && (ppl == 2 || ppl == 4)) {
-      auto k = run_kernel<NV, AGENT, QT, RNGT_PHILOX, 4, false, 0, true>;
+      auto kt = run_kernel<NV, AGENT, QT, RNGT_PHILOX, 4, false, 0, 2>;
+      auto kp = run_kernel<NV, AGENT, QT, RNGT_PHILOX, 4, false, 0, 1>;
+      auto k = (q.hot_kind == OLS_HOT_TAIL) ? kt : kp;
       if (L.smem > 40 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.smem);
         if (e != cudaSuccess) return e;

@@ -879,15 +879,19 @@ def test_hot_records_never_change_an_evaluation(ob, lanes, ring, seeded, pi_dtyp
     g["a"] = (rng.random(N)[:, None] > np.cumsum(pb[g["z"]], 1)).sum(1).clip(0, nA - 1)
     pi = np.full((nS, nA), 0.25, dtype=pi_dtype)
     pi[::7] = np.array([0.7, 0.1, 0.1, 0.1], dtype=pi_dtype)
+    from offsim4rl_b200 import _abi as abi
     outs = []
-    for hot in (False, True):
+    for hot, trace in ((False, 64), (True, 64), ("tail", 64), ("tail", 0)):     # trace 0: the TAIL path never reads a full record
         log = device_log(ob, g, n_buckets=nS, hot_records=hot).seeded(seeded)
+        assert hot != "tail" or log.hot_kind == abi.HOT_TAIL                    # the behaviour distribution is a function of the state
         sim = ob.BatchedPSRS(log, R, rng="philox", seed=8, ring=ring, ring_seed=5, lanes=lanes)
         res = None
         for budget in (25, 15):
-            res = sim.run_evalmc(nS, 40, pi=pi, gamma=0.95, max_steps=budget, trace_cap=64, outputs=res)
+            res = sim.run_evalmc(nS, 40, pi=pi, gamma=0.95, max_steps=budget, trace_cap=trace, outputs=res)
         outs.append((res, sim.draws.clone()))
-    (a, da), (b, db) = outs
-    assert torch.equal(a.trace_row, b.trace_row) and torch.equal(a.accepted, b.accepted) and torch.equal(a.pops, b.pops)
-    assert torch.equal(da, db) and torch.equal(a.status, b.status) and torch.equal(a.Gs, b.Gs) and torch.equal(a.lengths, b.lengths)
+    (a, da) = outs[0]
+    for b, db in outs[1:]:
+        assert b.trace_row is None or torch.equal(a.trace_row, b.trace_row)
+        assert torch.equal(a.accepted, b.accepted) and torch.equal(a.pops, b.pops)
+        assert torch.equal(da, db) and torch.equal(a.status, b.status) and torch.equal(a.Gs, b.Gs) and torch.equal(a.lengths, b.lengths)
     assert int(a.accepted.sum()) > 0.5 * R * 40 and int(a.pops.sum()) > 20 * int(a.accepted.sum())
