@@ -39,11 +39,16 @@ WORKLOADS = {
     "c2": dict(rows=1_000_000, states=162, actions=2, replicas=10_000, budget=2_000, delta=None, lanes=8,
                desc="cartpole-shaped: 1M-transition log, 162 states, 2 actions, eps-greedy Q-learning, 10k replicas"),
 }
-# DRAM bytes (read + write) per accepted transition of the fused run kernel, from the committed `ncu --set full`
-# captures (profiles/r01n_ncu_full_run_kernel_c4.txt, r01j_ncu_full_run_kernel_c5.txt): dram__bytes_read.sum + dram__bytes_write.sum divided by the
-# accepted transitions of the captured launch.  Used to report `roofline.traffic` per launch.
-NCU_DRAM_BYTES_PER_ACCEPTED = {"c4": (16.764115e9 + 1.279550e9) / 3.75e7, "c5": (18.883526e9 + 0.301427e9) / 3.2e6,
-                               "c5_full_records": (78.641898e9 + 1.658046e9) / 3.2e6}
+# DRAM bytes (read + write) of the dominant kernels, measured by `ncu --set full` on the build that is benchmarked and kept
+# in profiles/ncu_traffic.json (bytes per accepted transition for the c4 learner, per pop for the c5 evaluation, with the
+# capture each number comes from).  Used to report `roofline.traffic` per launch.
+def load_traffic():
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        return {}
+
+
 EPS, ALPHA, GAMMA = 0.1, 0.1, 0.99
 EP_CAP = 512
 
@@ -366,12 +371,20 @@ def gather_stress_leg(ob, torch, dev, hbm_peak, launches=5, warm=3, hot="tail"):
             pops = float(sim.pops.sum())
     t = sum(ms) / len(ms) / 1e3
     gbs = pops * log.rec_bytes / t / 1e9
+    read_per_pop = 8 if hot else log.rec_bytes
+    kind = {False: "2 full records of 32 bytes", True: "4 PROBS hot records of 8 bytes", "probs": "4 PROBS hot records of 8 bytes",
+            "tail": "4 TAIL hot records of 8 bytes"}[hot]
+    tr = load_traffic().get("c5_" + ("tail" if hot == "tail" else "probs" if hot else "full"), {})
     return {"workload": "c5: " + wl["desc"],
-            "kernel": "run_kernel (fixed-policy evaluation, lanes=32 x %s)" % ("4 hot records of 8 bytes" if hot else "2 records"),
-            "bytes_read_per_rejected_pop": 8 if hot else log.rec_bytes, "pops_per_s": pops / t,
+            "kernel": "run_kernel (fixed-policy evaluation, lanes=32 x %s per round)" % kind,
+            "bytes_read_per_rejected_pop": read_per_pop, "pops_per_s": pops / t,
             "accepted_per_s": float(sim.accepted.sum()) / t, "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+            "frac_note": "contract bytes (SURVEY 8d: 32 B per popped record) / time / measured HBM copy peak; the kernel itself reads "
+                         "%d B per popped record: see dram_achieved / dram_frac" % read_per_pop,
+            "dram_achieved": pops * read_per_pop / t / 1e9, "dram_frac": pops * read_per_pop / t / 1e9 / hbm_peak,
             "kernel_ms": 1e3 * t, "launches": launches,
-            "traffic": NCU_DRAM_BYTES_PER_ACCEPTED["c5" if hot else "c5_full_records"] * float(sim.accepted.sum()), "algorithmic_bytes_per_launch": pops * log.rec_bytes}
+            "traffic": (tr["dram_bytes_per_pop"] * pops) if tr else None, "traffic_source": tr.get("capture"),
+            "algorithmic_bytes_per_launch": pops * log.rec_bytes}
 
 
 def queue_evaluator_leg(ob, torch, dev, hbm_peak, steps=40, warm=5):
@@ -456,7 +469,7 @@ def main():
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-stress", action="store_true", help="skip the c5 streaming-gather measurement appended to a c4 run")
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="end-to-end steps (0 = --steps)")
     ap.add_argument("--py-worker", help=argparse.SUPPRESS)      # internal: one process of the multi-process python baseline
     ap.add_argument("--py-seconds", type=float, default=4.0, help=argparse.SUPPRESS)
     ap.add_argument("--ref-worker", help=argparse.SUPPRESS)     # internal: one process of the multi-process reference baseline
@@ -470,6 +483,8 @@ def main():
         cols = dict(np.load(args.ref_worker))
         print(json.dumps(reference_python_leg(cols, dict(WORKLOADS[args.workload]), args.py_seconds, seed=args.ref_seed)))
         return
+    if args.e2e_steps <= 0:
+        args.e2e_steps = args.steps
     wl = dict(WORKLOADS[args.workload])
     for k in ("rows", "states", "replicas", "budget", "lanes"):
         if getattr(args, k) is not None:
@@ -515,6 +530,9 @@ def main():
     log = ob.BucketedLog(z=cols["z"], z_next=cols["z_next"], action=cols["action"], reward=cols["reward"],
                          terminal=cols["terminal"], p_log=cols["p_log"], steps=cols["steps"], n_buckets=nS, z_offset=0, device=dev,
                          keep_columns=True, hot_records=hot_kind)
+    from offsim4rl_b200 import _abi as _abi_mod
+    hot_in_effect = None if log.hot is None else ("tail" if log.hot_kind == _abi_mod.HOT_TAIL else "probs")
+    default_shape = args.ppl == 0 and args.lanes is None and args.batch_lanes == 0
     bucket_ms = log.time_bucketing(3)       # ols_bucket + ols_init_queue, CUDA events on the launching stream
     log.drop_columns()
     rec_bytes = log.rec_bytes
@@ -563,12 +581,14 @@ def main():
     sampler.begin()
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     acc_total = torch.zeros(2, dtype=torch.float64, device=dev)
+    launches0 = int(ob._abi.load().ols_kernel_launches())
     t0.record()
     for _ in range(args.steps):
         one_step(True)
         acc_total[0] += sim.accepted.sum()
         acc_total[1] += sim.pops.sum()
     t1.record()
+    launches_timed = int(ob._abi.load().ols_kernel_launches()) - launches0
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     elapsed_ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
@@ -589,30 +609,48 @@ def main():
     # ---- e2e: host-resident log -> H2D -> bucket -> run -> curve -> D2H, every step
     e2e = None
     if not args.skip_e2e:
-        host = {k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in cols.items()}
+        # The job's input is ONE host-resident log.  With N ranks each rank keeps 1/N of the rows in pinned host memory,
+        # uploads that shard over its own PCIe link and the shards are all-gathered over NVLink (parallel.all_gather_columns):
+        # the host side moves 3.7 GB per step in total instead of 3.7 GB per rank.
+        from offsim4rl_b200 import parallel as par
+        sharded = world > 1 and N % world == 0
+        lo_r, hi_r = par.row_shard(N, rank, world) if sharded else (0, N)
+        host = {k: torch.empty(v[lo_r:hi_r].shape, dtype=v.dtype, pin_memory=True) for k, v in cols.items()}
         for k, v in cols.items():
-            host[k].copy_(v)
+            host[k].copy_(v[lo_r:hi_r])
         h2d = sum(v.numel() * v.element_size() for v in host.values())
+        full_host = None
+        if rank == 0 and not args.skip_cpu and world == 1:
+            full_host = host                                           # the CPU baseline below reads the same host copy
+        col_meta = {k: (v.shape, v.dtype) for k, v in cols.items()}
         del cols, log
         sim.log = None
         torch.cuda.synchronize()
         e_acc, d2h = 0.0, 0
 
         copy_stream = torch.cuda.Stream(device=dev)
-        dev_cols = [{k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in host.items()} for _ in range(2)]
+        dev_cols = [{k: torch.empty(shp, dtype=dt, device=dev) for k, (shp, dt) in col_meta.items()} for _ in range(2)]
+        dev_shard = [{k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in host.items()} for _ in range(2)] if sharded else None
         n_up = 0
 
         def upload():
-            """H2D of one step's log columns from pinned host memory into one of two resident column sets, on the copy
-            stream.  (A set is reused two steps later; every step ends with a blocking D2H read, so it is free by then.)"""
+            """H2D of one step's log columns (this rank's row shard) from pinned host memory, then the all-gather of the
+            shards, into one of two resident column sets, on the copy stream.  (A set is reused two steps later; every step
+            ends with a blocking D2H read, so it is free by then.)"""
             nonlocal n_up
             c = dev_cols[n_up % 2]
-            n_up += 1
             with torch.cuda.stream(copy_stream):
-                for k, v in host.items():
-                    c[k].copy_(v, non_blocking=True)
+                if sharded:
+                    sh = dev_shard[n_up % 2]
+                    for k, v in host.items():
+                        sh[k].copy_(v, non_blocking=True)
+                    par.all_gather_columns(sh, c)
+                else:
+                    for k, v in host.items():
+                        c[k].copy_(v, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
+            n_up += 1
             return c, ev
 
         def e2e_step(cur, prefetch_next):
@@ -651,10 +689,14 @@ def main():
             dist.all_reduce(e_tot, op=dist.ReduceOp.SUM)
         e2e = {"value": float(e_tot) / (float(e_ms) / 1e3), "unit": "transitions/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": float(e_ms) / args.e2e_steps, "steps": args.e2e_steps,
+               "h2d_note": ("per rank: its 1/%d row shard of the 7 log columns; the shards are all-gathered over NVLink (NCCL), so the "
+                            "host moves the %.1f GB log once per step in total" % (world, h2d * world / 1e9)) if sharded
+                           else "per rank: the 7 log columns of the whole log",
+               "d2h_note": "the learning curve (sum, sumsq, count per episode) and the accepted count; Q tables stay on the device",
                "pipeline": "per step: H2D of the 7 log columns (pinned host, copy stream) -> bucketing -> fused run -> curve reduce -> "
                            "D2H of the curve; the H2D of step i+1 is issued behind the run launch of step i (double-buffered "
                            "columns); all %d uploads are inside the timed region" % args.e2e_steps}
-        cpu_cols = {k: v.numpy() for k, v in host.items()}            # the full log, already on the host (pinned)
+        cpu_cols = None if full_host is None else {k: v.numpy() for k, v in full_host.items()}   # the full log, already on the host
     else:
         cpu_cols = {k: v[:1_000_000].cpu().numpy() for k, v in cols.items()}
 
@@ -673,7 +715,7 @@ def main():
             next_rows = {"queue_evaluator": {"error": repr(exc)}}
     if rank == 0:
         cpu = None
-        if not args.skip_cpu and world == 1:
+        if not args.skip_cpu and world == 1 and cpu_cols is not None:
             threads = os.cpu_count() or 1
             leg, _clog = cpu_leg(cpu_cols, wl, args.cpu_seconds, threads)
             del _clog
@@ -691,6 +733,27 @@ def main():
                                                     "qlearn_psrs / evalMC_psrs, first 1e6 rows of the same log, env construction untimed",
                        "one_process": ref1, "processes": refp},
                    "python_port_1core": None if py is None else {"value": py["value"], "rows": py["rows"], "seconds": py["seconds"]}}
+        tail_on = hot_in_effect == "tail"
+        traffic = load_traffic().get(("c4_" if qlearn else "c5_") + (hot_in_effect or "full"), {}) if default_shape else {}
+        per_unit = traffic.get("dram_bytes_per_accepted" if qlearn else "dram_bytes_per_pop")
+        units = last_accepted if qlearn else my_pops
+        read_per_pop = 8 if hot_in_effect else rec_bytes
+        roofline = {
+            "bound": "hbm",
+            "kernel": ("learner_kernel (one thread per replica: PSRS pops over TAIL hot records + epsilon-greedy Q-learning update, ols_learner.cu)"
+                       if (qlearn and tail_on and wl["lanes"] == 1) else "run_kernel (fused PSRS step + agent update / return evaluator)"),
+            "achieved": gather_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gather_gbs / hbm_peak,
+            "frac_note": "contract bytes (SURVEY 8d: 32 B per popped record) / kernel time / measured HBM copy peak",
+            "traffic": per_unit * units if per_unit else None,
+            "traffic_note": ("DRAM read+write bytes per launch = %s of the same build (%s) x this launch's count"
+                             % ("ncu bytes per accepted transition" if qlearn else "ncu bytes per pop", traffic.get("capture"))) if per_unit else None,
+            "algorithmic_bytes_per_launch": my_pops * rec_bytes, "peak_source": peak_src,
+            "algorithmic_bytes_per_pop": rec_bytes, "bytes_read_per_pop_by_the_kernel": read_per_pop,
+            "dram_achieved": (per_unit * units / run_s / 1e9) if per_unit else None,
+            "dram_frac": (per_unit * units / run_s / 1e9 / hbm_peak) if per_unit else None,
+            "agent_state_GBps": agent_gbs, "kernel_ms": float(run_ms),
+            "dram_sectors_per_s": (traffic["dram_sectors_per_accepted"] * last_accepted / run_s)
+                                  if (qlearn and traffic.get("dram_sectors_per_accepted")) else None}
         out = {
             "metric": "simulated accepted transitions/sec", "value": value, "unit": "transitions/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
@@ -698,33 +761,25 @@ def main():
             "data": "synthetic",
             "config": {"workload": args.workload + ": " + wl["desc"], "rows": N, "states": nS, "actions": nA,
                        "replicas_per_gpu": R, "accepted_per_replica_per_step": T, "lanes": wl["lanes"],
-                       "time_slices": ("auto (16 per replica block: the one-lane learner is sliced whenever the launch holds more CTAs than SMs, the others when their blocks are not a whole number of waves)" if args.slices == -1 else args.slices),
-                       "hot_records": ("8-byte half-precision images of the records decide all but ~5e-4 of the pops; the 32-byte record is "
-                                       "read for the accepted pop and for the undecided ones" if use_hot else "off"),
+                       "time_slices": ("auto (16 per replica block: the one-lane learners are sliced whenever the launch holds more CTAs than SMs, the others when their blocks are not a whole number of waves)" if args.slices == -1 else args.slices),
+                       "hot_records": {"tail": "8-byte TAIL records {reward; next state | action | terminal}: the behaviour distribution is a function "
+                                               "of the state (checked bitwise per queue on the device), so the accept rule needs only the "
+                                               "record's action; per-step accept/reject limits decide all but ~6e-5 of the pops",
+                                       "probs": "8-byte half-precision images of the records decide all but ~5e-4 of the pops; the 32-byte record "
+                                                "is read for the accepted pop and for the undecided ones", None: "off"}[hot_in_effect],
                        "replica_state": ("one 32-byte entry {cursor, Q row} per (replica, state)" if use_aos else "separate cursor and Q arrays"),
                        "queue_order": "log order" + ("" if args.no_ring else " + per-(replica,state) ring offset"),
                        "l2": "working set (records %.1f GB + replica state %.1f GB) >> 126 MB L2; no flush" % (
                            N * rec_bytes / 1e9, (R * nS * 32 / 1e9) if use_aos else (R * nS * 4 / 1e9 + (R * nS * nA * 4 / 1e9 if qlearn else 0.0)))},
             "pops_per_s": pops / secs,
-            "roofline": {"bound": "hbm", "kernel": "run_kernel (fused PSRS step + agent update)", "achieved": gather_gbs, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": gather_gbs / hbm_peak,
-                         "traffic": (NCU_DRAM_BYTES_PER_ACCEPTED[args.workload] * last_accepted
-                                     if (args.workload in NCU_DRAM_BYTES_PER_ACCEPTED and use_hot and args.ppl == 0 and args.lanes is None)
-                                     else None),   # the captures are of the default configuration
-                         "traffic_note": "DRAM read+write bytes per launch = ncu bytes per accepted transition (profiles/r01n_ncu_full_run_kernel_c4.txt) x accepted per launch",
-                         "algorithmic_bytes_per_launch": my_pops * rec_bytes, "peak_source": peak_src,
-                         "algorithmic_bytes_per_pop": rec_bytes, "agent_state_GBps": agent_gbs, "kernel_ms": float(run_ms),
-                         "random_access": ({"dram_transactions_per_s": (NCU_DRAM_BYTES_PER_ACCEPTED["c4"] / 128.0) * last_accepted / run_s,
-                                            "ceiling_per_s": 3.6e10,
-                                            "note": "c4 is bound by isolated DRAM transactions (whole 128-byte lines per random sector), "
-                                                    "not by bytes: ncu traffic / 128 B per launch against the 3.6e10/s that "
-                                                    "scratch/randbw.cu sustains on this box (DESIGN.md 4.3)"}
-                                           if (args.workload == "c4" and use_hot and args.ppl == 0 and args.lanes is None) else None)},
+            "roofline": roofline,
             "bucketing": {"rows": N, "ms": bucket_ms, "GBps": bucket_bytes / bucket_ms / 1e6, "frac": bucket_bytes / bucket_ms / 1e6 / hbm_peak,
                           "note": "ols_bucket + ols_init_queue kernels; bytes = z twice + order + log columns + packed record per row"},
             "step_breakdown_ms": {k: sum(a.elapsed_time(b) for a, b in v) / max(1, len(v)) for k, v in k_ev.items()},
             "gather_stress": stress, "next_rows": next_rows,
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 4 * args.steps, "clocks": clocks,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches_timed),
+            "gpu_launches_note": "kernels of libols_b200.so launched inside the timed region, counted by the library (ols_kernel_launches)",
+            "clocks": clocks,
         }
         print(json.dumps(out))
     if world > 1:

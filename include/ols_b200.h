@@ -243,6 +243,9 @@ const char* ols_last_error(void);                          /* HOST string, threa
 /* sizeof() of each struct as compiled, indexed 0..4 = log, queues, replicas, step_out, run —
  * lets a binding verify its mirror of the layouts.                                            */
 size_t ols_struct_bytes(int which);
+/* kernels this library has launched in this process so far (every entry point counts its own launches; memsets and the
+ * caller's kernels are not included) — lets a benchmark report how many of its launches were this library's.          */
+uint64_t ols_kernel_launches(void);
 
 /* ---- state encoders: observation -> integer state id (the queue key) ---------------------- */
 /* Grid discretiser for MyGridNaviCoords observations (envs/gridworld.py:205-211,123-124):

@@ -69,6 +69,7 @@ SIGNATURES = {
     "ols_abi_version": (C.c_int, []),
     "ols_last_error": (C.c_char_p, []),
     "ols_struct_bytes": (C.c_size_t, [C.c_int]),
+    "ols_kernel_launches": (C.c_uint64, []),
     "ols_encode_grid": (C.c_int, [p, i64, i32, i32, p, p]),
     "ols_encode_cartpole_box": (C.c_int, [p, i32, i64, p, p]),
     "ols_encode_mlp": (C.c_int, [p, i64, i32, p, p, i32, p, p, i32, C.c_float, p, p]),

@@ -14,6 +14,7 @@
 
 // ------------------------------------------------------------------------------------------ errors
 void ols_set_error(const char* fmt, ...);
+void ols_note_launch(int n);  // process-wide count of the library's own kernel launches (ols_kernel_launches)
 
 #define OLS_REQUIRE(cond, code, ...)      \
   do {                                    \
@@ -34,6 +35,7 @@ void ols_set_error(const char* fmt, ...);
 
 #define OLS_LAUNCH_CHECK()                                                                \
   do {                                                                                    \
+    ols_note_launch(1);                                                                   \
     cudaError_t _e = cudaGetLastError();                                                  \
     if (_e != cudaSuccess) {                                                              \
       ols_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
@@ -41,7 +43,10 @@ void ols_set_error(const char* fmt, ...);
     }                                                                                     \
   } while (0)
 
-constexpr int OLS_SM_COUNT = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+// SMs of the current device, queried once per device at run time (B200: 148 = 2 dies x 74; that is also the fallback when
+// no device answers); grids are sized in multiples of this
+int ols_sm_count(void);
+#define OLS_SM_COUNT ols_sm_count()
 constexpr int OLS_MAX_ACTIONS = 16;
 
 static inline int ols_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

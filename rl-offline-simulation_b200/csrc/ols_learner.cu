@@ -495,5 +495,6 @@ __global__ void __launch_bounds__(kLT, OLS_LEARNER_MINB) learner_kernel(ols_queu
 
 cudaError_t ols_launch_learner(const ols_queues_t& q, const ols_replicas_t& r, const ols_run_t& c, const ols_sim::RunLaunch& L) {
   ols_sim::learner_kernel<<<L.grid, ols_sim::kLT, 0, L.stream>>>(q, r, c, L.keys);
+  ols_note_launch(1);
   return cudaGetLastError();
 }

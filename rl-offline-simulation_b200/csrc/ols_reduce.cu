@@ -49,21 +49,36 @@ __global__ void __launch_bounds__(256) curve_partial_kernel(const double* __rest
   }
 }
 
-__global__ void __launch_bounds__(256) curve_fold_kernel(const double* __restrict__ partial, int n_slabs, int n_episodes,
-                                                         double* __restrict__ sum, double* __restrict__ sumsq,
-                                                         double* __restrict__ count) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= n_episodes) return;
+// block = 32 episodes (x) by 32 slab stripes (y): stripe y folds slabs y, y + 32, ... in order, then the stripes are folded in
+// order — a fixed summation tree, so the curve is deterministic (and independent of the launch geometry)
+__global__ void __launch_bounds__(1024) curve_fold_kernel(const double* __restrict__ partial, int n_slabs, int n_episodes,
+                                                          double* __restrict__ sum, double* __restrict__ sumsq,
+                                                          double* __restrict__ count) {
+  __shared__ double s_a[32][33], s_b[32][33], s_c[32][33];
+  const int e = blockIdx.x * 32 + threadIdx.x;
   double a = 0.0, b = 0.0, c = 0.0;
-  for (int s = 0; s < n_slabs; ++s) {
-    const double* p = partial + ((size_t)s * 3) * n_episodes;
-    a += p[e];
-    b += p[n_episodes + e];
-    c += p[2 * n_episodes + e];
+  if (e < n_episodes) {
+    for (int s = threadIdx.y; s < n_slabs; s += 32) {
+      const double* p = partial + ((size_t)s * 3) * n_episodes;
+      a += p[e];
+      b += p[n_episodes + e];
+      c += p[2 * n_episodes + e];
+    }
   }
-  sum[e] = a;
-  sumsq[e] = b;
-  count[e] = c;
+  s_a[threadIdx.y][threadIdx.x] = a;
+  s_b[threadIdx.y][threadIdx.x] = b;
+  s_c[threadIdx.y][threadIdx.x] = c;
+  __syncthreads();
+  if (threadIdx.y == 0 && e < n_episodes) {
+    for (int y = 1; y < 32; ++y) {
+      a += s_a[y][threadIdx.x];
+      b += s_b[y][threadIdx.x];
+      c += s_c[y][threadIdx.x];
+    }
+    sum[e] = a;
+    sumsq[e] = b;
+    count[e] = c;
+  }
 }
 
 // one warp per replica: lanes stride over the replica's episodes, then a shuffle tree folds the warp
@@ -118,7 +133,8 @@ extern "C" int ols_reduce_curves(const double* Gs, const int32_t* ep_index, int6
     curve_partial_kernel<<<grid, dim3(32, 8), 0, stream>>>(Gs, ep_index, n_replicas, ep_cap, n_episodes, (double*)scratch);
     OLS_LAUNCH_CHECK();
   }
-  curve_fold_kernel<<<ols_div_up(n_episodes, 256), 256, 0, stream>>>((const double*)scratch, n_slabs, n_episodes, sum, sumsq, count);
+  if (n_episodes > 0)
+    curve_fold_kernel<<<ols_div_up(n_episodes, 32), dim3(32, 32), 0, stream>>>((const double*)scratch, n_slabs, n_episodes, sum, sumsq, count);
   OLS_LAUNCH_CHECK();
   return OLS_OK;
 }

@@ -148,6 +148,7 @@ static int step_impl(const ols_queues_t* q, const ols_replicas_t* r, const uint8
     default: e = ols_launch_step_nv4(*q, *r, mask, p_new, p_new_is_f64, p_stride, reject_mode, compute_mode, lanes, *out, grid, (cudaStream_t)stream, act); break;
   }
   OLS_REQUIRE(e == cudaSuccess, OLS_ERR_CUDA, "%s: launch failed: %s", who, cudaGetErrorString(e));
+  ols_note_launch(1);
   return OLS_OK;
 }
 
@@ -266,5 +267,6 @@ extern "C" int ols_run(const ols_queues_t* q, const ols_replicas_t* r, const ols
     default: e = ols_launch_run_nv4(*q, *r, *c, L, ppl); break;
   }
   OLS_REQUIRE(e == cudaSuccess, OLS_ERR_CUDA, "ols_run: launch failed: %s", cudaGetErrorString(e));
+  ols_note_launch(1);
   return OLS_OK;
 }
