@@ -387,61 +387,36 @@ def gather_stress_leg(ob, torch, dev, hbm_peak, launches=5, warm=3, hot="tail"):
             "algorithmic_bytes_per_launch": pops * log.rec_bytes}
 
 
-def queue_evaluator_leg(ob, torch, dev, hbm_peak, steps=40, warm=5):
-    """the batched QueueEvaluator step (queues keyed by (z, a), the agent's own action picks the queue,
-    no rejection; queue_evaluator.py:121-131) — one `ols_step_action` launch per simulated step over 1M replicas, with the
-    replicas whose transition was terminal re-started by `ols_reset` in between.  Rank 0, one GPU, a second or two."""
+def queue_evaluator_leg(ob, torch, dev, hbm_peak, steps=200, launches=5, warm=2):
+    """SURVEY §8f rank 1: the QueueEvaluator (queues keyed by (z, a), the agent's own action picks the queue, no rejection;
+    queue_evaluator.py:113-131) as a FUSED run — `ols_run_actions`: 1M replicas, each resets and steps `steps` times per
+    launch with actions sampled from a uniform policy by its own counter-based stream.  Rank 0, one GPU, a second or two."""
     N, nS, nA, R = 20_000_000, 1000, 4, 1_000_000
     cols = ob.synth_columns(N, nS, behaviour_table(nS, nA, None), seed=3, device=dev)
     log = ob.BucketedLog(z=cols["z"], z_next=cols["z_next"], action=cols["action"], reward=cols["reward"], terminal=cols["terminal"],
                          p_log=cols["p_log"], steps=cols["steps"], n_buckets=nS, z_offset=0, device=dev, key_by_action=True)
     del cols
-    sim = ob.BatchedPSRS(log, R, rng="philox", seed=5, ring=True, ring_seed=11, lanes=1)
-    acts = torch.randint(0, nA, (steps + warm, R), dtype=torch.int32, device=dev)
-    a_now = torch.empty(R, dtype=torch.int32, device=dev)
-    done = torch.zeros((), dtype=torch.int64, device=dev)
-    sim.reset()
-
-    def one():                     # one simulated step of every replica + restart of the finished episodes
-        out = sim.step_action(a_now)
-        done.add_((out["row"] >= 0).sum())
-        sim.reset(mask=out["terminal"])
-
-    # the loop is launch-bound (two small kernels per step): capture one step in a CUDA graph and replay it
-    side = torch.cuda.Stream(device=dev)
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        a_now.copy_(acts[0])
-        one()                      # warm-up outside capture (lazy module loading)
-    torch.cuda.current_stream().wait_stream(side)
-    try:
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            one()
-    except Exception:              # capture not possible here: run the step eagerly
-        graph = None
+    sim = ob.BatchedPSRS(log, R, rng="philox", seed=5, ring=True, ring_seed=11, lanes=1, reject="accept_all")
+    pi = np.full((nS, nA), 1.0 / nA)
+    res, ms, n = None, [], 0.0
+    for i in range(launches + warm):
+        sim.restart()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = sim.run_actions(EP_CAP - 1, GAMMA, pi=pi, max_steps=steps, ep_cap=EP_CAP, outputs=res)
+        e1.record()
         torch.cuda.synchronize()
-    for i in range(steps + warm):
-        if i == warm:
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            done.zero_()
-            e0.record()
-        a_now.copy_(acts[i])
-        if graph is not None:
-            graph.replay()
-        else:
-            one()
-    e1.record()
-    torch.cuda.synchronize()
-    t = e0.elapsed_time(e1) / 1e3
-    n = float(done)
-    per = log.rec_bytes + 8 + 8 + 4 + 21        # record, cursor r/w, current state r/w, action in, step outputs
-    return {"row": "QueueEvaluator.step over (z, a)-keyed queues (queue_evaluator.py:121-131), batched", "rows": N, "states": nS,
-            "actions": nA, "replicas": R, "steps": steps, "value": n / t, "unit": "transitions/s", "launches": 2 * steps,
-            "achieved": n * per / t / 1e9, "peak": hbm_peak, "roofline_unit": "GB/s", "frac": n * per / t / 1e9 / hbm_peak,
-            "algorithmic_bytes_per_transition": per, "note": ("one CUDA-graph replay (step kernel + reset kernel + count) per simulated step" if graph is not None
-                     else "eager: one launch of each kernel per simulated step") + "; random 32-byte record reads"}
+        if i >= warm:
+            ms.append(e0.elapsed_time(e1))
+            n = float(sim.accepted.sum())
+    t = sum(ms) / len(ms) / 1e3
+    per = log.rec_bytes + 8                      # the record + the replica's cursor (read, write)
+    return {"row": "QueueEvaluator reset/step over (z, a)-keyed queues (queue_evaluator.py:113-131), fused multi-step run (ols_run_actions)",
+            "rows": N, "states": nS, "actions": nA, "replicas": R, "steps_per_launch": steps, "value": n / t, "unit": "transitions/s",
+            "launches": launches, "kernel_ms": 1e3 * t, "achieved": n * per / t / 1e9, "peak": hbm_peak, "roofline_unit": "GB/s",
+            "frac": n * per / t / 1e9 / hbm_peak, "algorithmic_bytes_per_transition": per,
+            "note": "one launch per %d simulated steps of every replica; one random 32-byte record read and one random cursor "
+                    "read-modify-write per transition (isolated DRAM accesses, not streaming)" % steps}
 
 
 # ------------------------------------------------------------------------------------------------- GPU arm

@@ -237,10 +237,28 @@ typedef struct ols_run {
   int64_t trace_cap;
 } ols_run_t;
 
+/* ---- fused QueueEvaluator run (queue_evaluator.py:113-131 for many steps in one launch) -------------------------- */
+typedef struct ols_queue_run {
+  int32_t n_states;           /* rows of pi (sampled-policy mode)                                 */
+  int32_t pi_is_f64;
+  int32_t n_episodes;         /* stop a replica after this many completed episodes                */
+  int32_t ep_cap;             /* row length of Gs / lengths (>= n_episodes + 1)                   */
+  int64_t max_steps;          /* > 0: stop after this many transitions in THIS call (resumable)   */
+  double gamma;
+  const void* pi;             /* [n_states][n_actions] fixed policy the agent samples its actions from, or NULL */
+  const int32_t* actions;     /* or: the agent's actions, element [replica * a_stride + k] for its k-th step() call */
+  int64_t actions_len;
+  int64_t a_stride;           /* 0: one list shared by all replicas                               */
+  double* Gs;                 /* [n_replicas][ep_cap] discounted return per COMPLETED episode     */
+  int32_t* lengths;           /* [n_replicas][ep_cap] episode lengths (also the one cut by an empty queue) */
+  int32_t* trace_row;         /* [n_replicas][trace_cap] log rows served, or NULL                 */
+  int64_t trace_cap;
+} ols_queue_run_t;
+
 /* ---- library ------------------------------------------------------------------------------ */
 int ols_abi_version(void);
 const char* ols_last_error(void);                          /* HOST string, thread-local          */
-/* sizeof() of each struct as compiled, indexed 0..4 = log, queues, replicas, step_out, run —
+/* sizeof() of each struct as compiled, indexed 0..5 = log, queues, replicas, step_out, run, queue_run —
  * lets a binding verify its mirror of the layouts.                                            */
 size_t ols_struct_bytes(int which);
 /* kernels this library has launched in this process so far (every entry point counts its own launches; memsets and the
@@ -318,6 +336,13 @@ int ols_reseed(const ols_replicas_t* r, const uint64_t* seeds, const uint8_t* ma
 /* psrs.py:119-271 `qlearn_psrs` / `expSARSA_psrs` / `evalMC_psrs`, one independent run per replica,
  * fused with the agent update and the per-episode return evaluator.                            */
 int ols_run(const ols_queues_t* q, const ols_replicas_t* r, const ols_run_t* run, void* stream);
+/* queue_evaluator.py:113-131 as a fused loop, one independent run per replica: reset, then step(a) with the agent's own
+ * actions (a fed list, or sampled from a fixed policy with the replica's counter-based stream) until the episode ends, and
+ * again; returns are accumulated as in evalMC_psrs (psrs.py:241-271).  The queues must be keyed by (z, a) as for
+ * ols_step_action.  r->ties counts the actions taken (the index into the list / the stream), r->pops the records served.
+ * Statuses: DONE (n_episodes reached), INIT_EMPTY, QUEUE_EMPTY (step returned None), NO_QUEUE (KeyError), FEED_EMPTY
+ * (action list used up), RUNNING (budget).                                                                              */
+int ols_run_actions(const ols_queues_t* q, const ols_replicas_t* r, const ols_queue_run_t* run, void* stream);
 /* bytes of ols_run_t.sched for a run over n_replicas replicas with the given lane-group width   */
 size_t ols_run_sched_bytes(int64_t n_replicas, int32_t lanes);
 

@@ -15,7 +15,7 @@ from . import _abi  # noqa: F401  (ctypes mirror of the C ABI; loading the libra
 
 
 def __getattr__(name):
-    if name in ("BucketedLog", "BatchedPSRS", "RunResult", "synth_columns"):
+    if name in ("BucketedLog", "BatchedPSRS", "BatchedPSRSExo", "RunResult", "synth_columns"):
         from . import engine
         return getattr(engine, name)
     raise AttributeError(name)

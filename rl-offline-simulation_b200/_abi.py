@@ -62,7 +62,13 @@ class Run(C.Structure):
                 ("lengths", p), ("trace_row", p), ("td_error", p), ("trace_cap", i64)]
 
 
-STRUCTS = [Log, Queues, Replicas, StepOut, Run]
+class QueueRun(C.Structure):
+    _fields_ = [("n_states", i32), ("pi_is_f64", i32), ("n_episodes", i32), ("ep_cap", i32), ("max_steps", i64), ("gamma", f64),
+                ("pi", p), ("actions", p), ("actions_len", i64), ("a_stride", i64), ("Gs", p), ("lengths", p), ("trace_row", p),
+                ("trace_cap", i64)]
+
+
+STRUCTS = [Log, Queues, Replicas, StepOut, Run, QueueRun]
 
 # every symbol include/ols_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
@@ -88,6 +94,7 @@ SIGNATURES = {
                                C.POINTER(StepOut), p, p]),
     "ols_reseed": (C.c_int, [C.POINTER(Replicas), p, p, p]),
     "ols_run": (C.c_int, [C.POINTER(Queues), C.POINTER(Replicas), C.POINTER(Run), p]),
+    "ols_run_actions": (C.c_int, [C.POINTER(Queues), C.POINTER(Replicas), C.POINTER(QueueRun), p]),
     "ols_run_sched_bytes": (C.c_size_t, [i64, i32]),
     "ols_curve_scratch_bytes": (C.c_size_t, [i64, i32]),
     "ols_reduce_curves": (C.c_int, [p, p, i64, i32, i32, p, p, p, p, C.c_size_t, p]),

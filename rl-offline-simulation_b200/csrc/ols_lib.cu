@@ -45,6 +45,7 @@ extern "C" size_t ols_struct_bytes(int which) {
     case 2: return sizeof(ols_replicas_t);
     case 3: return sizeof(ols_step_out_t);
     case 4: return sizeof(ols_run_t);
+    case 5: return sizeof(ols_queue_run_t);
     default: return 0;
   }
 }

@@ -585,6 +585,48 @@ class BatchedPSRS:
         return self._run(abi.AGENT_FIXED_PI, n_states, n_episodes, gamma, pi=pi, max_steps=max_steps,
                          trace_cap=trace_cap, compute=compute, ep_cap=ep_cap, outputs=outputs)
 
+    def run_actions(self, n_episodes, gamma, actions=None, pi=None, max_steps=0, trace_cap=0, ep_cap=None, outputs=None) -> RunResult:
+        """queue_evaluator.py:113-131 as ONE launch for many steps: every replica resets, steps with the agent's own actions
+        until its episode ends, and again.  ``actions``: [n_steps] shared or [R, n_steps] per replica (the k-th ``step()``
+        call of a replica takes element k), or ``pi`` [n_states, nA]: the agent samples from a fixed policy with the
+        replica's counter-based stream.  Needs ``BucketedLog(..., key_by_action=True)``.  Returns / lengths as evalMC_psrs."""
+        if not self.log.key_by_action:
+            raise ValueError("run_actions needs BucketedLog(..., key_by_action=True)")
+        if (actions is None) == (pi is None):
+            raise ValueError("give either actions or pi")
+        self._need_cursor_table("run_actions()")
+        dev, R, nA = self.device, self.R, self.log.n_actions
+        with torch.cuda.device(dev):
+            ep_cap = int(ep_cap or (n_episodes + 1))
+            if outputs is None:
+                Gs = torch.zeros((max(R, 1), ep_cap), dtype=torch.float64, device=dev)
+                lengths = torch.zeros((max(R, 1), ep_cap), dtype=torch.int32, device=dev)
+                trace_row = torch.full((max(R, 1), trace_cap), -1, dtype=torch.int32, device=dev) if trace_cap else None
+            else:
+                Gs, lengths, trace_row = outputs.Gs, outputs.lengths, outputs.trace_row
+            a_t = pi_t = None
+            a_len = a_stride = n_states = pi_is_f64 = 0
+            if actions is not None:
+                a_t = _as_tensor(actions, dev, torch.int32)
+                if a_t.dim() == 2 and a_t.shape[0] != R:
+                    raise ValueError("actions must be [n_steps] or [n_replicas, n_steps]")
+                a_len, a_stride = (int(a_t.shape[0]), 0) if a_t.dim() == 1 else (int(a_t.shape[1]), int(a_t.stride(0)))
+            else:
+                pi_t = _as_tensor(pi, dev)
+                if pi_t.dtype not in (torch.float32, torch.float64):
+                    pi_t = pi_t.to(torch.float64)
+                if pi_t.dim() != 2 or pi_t.shape[1] != nA:
+                    raise ValueError("pi must be [n_states, n_actions]")
+                n_states, pi_is_f64 = int(pi_t.shape[0]), int(pi_t.dtype == torch.float64)
+            cfg = abi.QueueRun(n_states=n_states, pi_is_f64=pi_is_f64, n_episodes=int(n_episodes), ep_cap=ep_cap, max_steps=int(max_steps),
+                               gamma=float(gamma), pi=_ptr(pi_t), actions=_ptr(a_t), actions_len=a_len, a_stride=a_stride, Gs=_ptr(Gs),
+                               lengths=_ptr(lengths), trace_row=_ptr(trace_row), trace_cap=int(trace_cap))
+            q, r = self.log.queues_struct(), self.replicas_struct()
+            abi.check(self.lib.ols_run_actions(C.byref(q), C.byref(r), C.byref(cfg), _stream_ptr()))
+            return RunResult(Gs=Gs, lengths=lengths, n_returns=self.ep_index.clone(), n_lengths=self.ep_len_count.clone(),
+                             status=self.status.clone(), accepted=self.accepted.clone(), pops=self.pops.clone(), trace_row=trace_row,
+                             td_error=None)
+
     # ------------------------------------------------------------------ evaluators
     def learning_curve(self, result: RunResult, n_episodes: int, all_reduce: bool = True):
         """Per-episode ``(sum, sumsq, count)`` of the returns over replicas — over ALL ranks when
@@ -612,6 +654,69 @@ class BatchedPSRS:
                                                   _ptr(result.n_lengths), self.R, int(result.Gs.shape[1]), _ptr(ret),
                                                   _ptr(ln), _stream_ptr()))
         return ret, ln
+
+
+class BatchedPSRSExo:
+    """R independent ``PSRS_Exo`` simulators (psrs.py:59-117) — the batched vector form: observations split into an
+    endogenous state s and an exogenous state x; ``log_s`` / ``log_x`` are the SAME rows bucketed by s and by x (x' in the
+    ``z_next`` column of ``log_x``); one pop consumes the head of both queues, the accept rule runs on the s-record.
+    ``reset(seeds)`` re-seeds each replica's PCG64 generator like ``PSRS_Exo.reset(seed)`` (psrs.py:92) and pops its next
+    initial (s, x); ``step(p_new)`` is psrs.py:99-117 for every running replica."""
+
+    def __init__(self, log_s: BucketedLog, log_x: BucketedLog, n_replicas: int, seed: int = 0, lanes: int = 4):
+        if log_s.n_rows != log_x.n_rows or log_s.n_init != log_x.n_init:
+            raise ValueError("log_s and log_x must bucket the same rows")
+        self.log_s, self.log_x = log_s, log_x
+        self.sim = BatchedPSRS(log_s, n_replicas, rng="pcg64", seed=seed, lanes=lanes)
+        dev, R = self.sim.device, self.sim.R
+        with torch.cuda.device(dev):
+            self.cursor_x = torch.zeros((max(R, 1), log_x.n_buckets), dtype=torch.int32, device=dev)
+            self.cur_x = torch.zeros(max(R, 1), dtype=torch.int32, device=dev)
+            self.out_x_next = torch.zeros(max(R, 1), dtype=torch.int32, device=dev)
+
+    def restart(self, log_s: Optional[BucketedLog] = None, log_x: Optional[BucketedLog] = None):
+        """``reset_sampler`` for the replica side: fresh cursors; pass the ``seeded(k)`` logs to switch queue order."""
+        if log_s is not None:
+            self.log_s, self.log_x = log_s, log_x
+        self.sim.restart(self.log_s)
+        self.cursor_x.zero_()
+
+    def reset(self, seeds=None, mask=None):
+        """psrs.py:91-97 for every replica (or those with ``mask``): ``seeds`` [R] (or one int) re-seed the generators."""
+        sim = self.sim
+        with torch.cuda.device(sim.device):
+            m = None if mask is None else _as_tensor(mask, sim.device, torch.uint8)
+            sd = None
+            if seeds is not None:
+                arr = np.full(sim.R, int(seeds), dtype=np.uint64) if np.ndim(seeds) == 0 else np.asarray(seeds, dtype=np.uint64)
+                sd = _as_tensor(arr.view(np.int64), sim.device)
+            r = sim.replicas_struct()
+            abi.check(sim.lib.ols_reseed(C.byref(r), _ptr(sd), _ptr(m), _stream_ptr()))
+            before = sim.init_cursor.clone()
+            sim.reset(mask)
+            took = sim.init_cursor > before                      # replicas that popped an initial state: its x comes with it
+            idx = (sim.init_cursor - 1).clamp(min=0).long()
+            self.cur_x.copy_(torch.where(took, self.log_x.init_z[idx.clamp(max=max(self.log_x.n_init - 1, 0))], self.cur_x))
+        return sim.cur_z, self.cur_x, sim.status
+
+    def step(self, p_new, mask=None):
+        """psrs.py:99-117 for every RUNNING replica; returns the dict of :meth:`BatchedPSRS.step` plus ``x_next``."""
+        sim = self.sim
+        with torch.cuda.device(sim.device):
+            p = _as_tensor(p_new, sim.device)
+            if p.dtype not in (torch.float32, torch.float64):
+                p = p.to(torch.float64)
+            stride = 0 if p.dim() == 1 else int(p.stride(0))
+            compute = abi.COMPUTE_F32 if (p.dtype == torch.float32 and self.log_s.p_source_f32) else abi.COMPUTE_F64
+            m = None if mask is None else _as_tensor(mask, sim.device, torch.uint8)
+            qs, qx, r = self.log_s.queues_struct(), self.log_x.queues_struct(), sim.replicas_struct()
+            out = abi.StepOut(row=_ptr(sim.out_row), action=_ptr(sim.out_action), reward=_ptr(sim.out_reward),
+                              terminal=_ptr(sim.out_terminal), s_next=_ptr(sim.out_s_next), z_from=_ptr(sim.out_z_from))
+            abi.check(sim.lib.ols_step_exo(C.byref(qs), C.byref(qx), C.byref(r), _ptr(self.cursor_x), _ptr(self.cur_x), _ptr(m), _ptr(p),
+                                           int(p.dtype == torch.float64), stride, compute, sim.lanes, C.byref(out),
+                                           _ptr(self.out_x_next), _stream_ptr()))
+        return dict(row=sim.out_row, action=sim.out_action, reward=sim.out_reward, terminal=sim.out_terminal, s_next=sim.out_s_next,
+                    x_next=self.out_x_next, z_from=sim.out_z_from, status=sim.status)
 
 
 # ----------------------------------------------------------------------------------------------- synthetic data

@@ -379,6 +379,93 @@ def test_queue_evaluator_matches_reference(ob, golden, seed):
     assert status == str(g[f"status_{seed}"]) and k == int(g[f"nacts_{seed}"])
 
 
+@pytest.mark.parametrize("seed", [0, 4])
+def test_fused_queue_evaluator_run_matches_reference(ob, golden, seed):
+    """BatchedPSRS.run_actions (ols_run_actions: reset / step(a) for many steps in ONE launch) under the fixed action sequence
+    the unmodified reference's QueueEvaluator_impl was driven with: same served rows, same end of run, same action count."""
+    import torch
+    from offsim4rl_b200 import _abi as abi
+    g = golden("queue_evaluator")
+    N, nS, nA = len(g["z"]), 6, 3
+    log = ob.BucketedLog(z=g["z"], z_next=g["z_next"], action=g["a"], reward=g["r"], terminal=g["done"], p_log=g["p_log"],
+                         steps=g["t"], n_buckets=nS, key_by_action=True).seeded(seed)
+    sim = ob.BatchedPSRS(log, 3, rng="philox", seed=1, reject="accept_all")
+    res = sim.run_actions(N, gamma=0.9, actions=g["acts"], trace_cap=N)
+    expect = g[f"trace_{seed}"]
+    want_status = abi.NO_QUEUE if str(g[f"status_{seed}"]) == "keyerror" else None
+    for r in range(3):
+        n = int(res.accepted[r])
+        assert n == expect.size and np.array_equal(res.trace_row[r, :n].cpu().numpy(), expect)
+        assert int(sim.ties[r]) == int(g[f"nacts_{seed}"])                       # actions taken, incl. the one that found an empty queue
+        st = int(res.status[r])
+        assert st == want_status if want_status is not None else st in (abi.QUEUE_EMPTY, abi.INIT_EMPTY)
+        # returns of the completed episodes and all lengths, from the served rows
+        ends = np.nonzero(g["done"][expect])[0]
+        lens = np.diff(np.r_[-1, ends])
+        ne = int(res.n_returns[r])
+        assert ne == ends.size and np.array_equal(res.lengths[r, :ne].cpu().numpy(), lens)
+        Gs, k = [], 0
+        for L in lens:
+            Gs.append(sum(0.9 ** t * float(g["r"][expect[k + t]]) for t in range(L))); k += L
+        np.testing.assert_allclose(res.Gs[r, :ne].cpu().numpy(), Gs, rtol=1e-12, atol=1e-12)
+    # chunked == one launch
+    sim2 = ob.BatchedPSRS(log, 3, rng="philox", seed=1, reject="accept_all")
+    out = None
+    for _ in range(N):
+        out = sim2.run_actions(N, gamma=0.9, actions=g["acts"], trace_cap=N, max_steps=7, outputs=out)
+        if bool((out.status != abi.RUNNING).all()):
+            break
+    assert torch.equal(out.trace_row, res.trace_row) and torch.equal(out.Gs, res.Gs) and torch.equal(out.status, res.status)
+
+
+def test_fused_queue_evaluator_run_with_a_sampled_policy_matches_the_oracle(ob):
+    """The agent samples its own actions from a fixed policy with the replica's counter-based stream (protocol in
+    csrc/ols_queue_run.cu, restated here with tests/helpers.py): the python oracle's QueueEvaluator, driven with the same
+    actions, serves the same rows — thousands of replicas, ring offsets off (the oracle class has none)."""
+    from oracle import psrs_oracle as O
+    from tests.helpers import stream_word
+    from offsim4rl_b200 import _abi as abi
+    rng = np.random.default_rng(12)
+    N, nS, nA, R = 30000, 12, 4, 300
+    z, zn = rng.integers(0, nS, N), rng.integers(0, nS, N)
+    a = rng.integers(0, nA, N)
+    done = rng.random(N) < 0.1
+    t = np.where(np.r_[True, done[:-1]], 0, 1)
+    r = rng.normal(size=N).astype(np.float32)
+    pi = rng.dirichlet(np.ones(nA), size=nS)
+    log = ob.BucketedLog(z=z, z_next=zn, action=a, reward=r, terminal=done, p_log=np.full((N, nA), 0.25, np.float32), steps=t,
+                         n_buckets=nS, key_by_action=True)
+    sim = ob.BatchedPSRS(log, R, rng="philox", seed=77, replica_id0=4000, reject="accept_all")
+    res = sim.run_actions(25, gamma=0.95, pi=pi, trace_cap=2000)
+    cum = np.cumsum(pi, axis=1)
+    for rep in (0, 7, R - 1):
+        env = O.OracleQueueEvaluator(z, zn, z, zn, a, steps=t, n_state_keys=nS, n_actions=nA)
+        trace, k, episodes, status = [], 0, 0, None
+        while episodes < 25:
+            s = env.reset()
+            if s is None:
+                status = abi.INIT_EMPTY
+                break
+            while True:
+                v = stream_word(77, 4000 + rep, 1, k) * (1.0 / 4294967296.0)
+                act = min(int((cum[int(env.cur_s)] <= v).sum()), nA - 1)
+                k += 1
+                row = env.step(act)
+                if row is None:
+                    status = abi.QUEUE_EMPTY
+                    break
+                trace.append(row)
+                if done[row]:
+                    episodes += 1
+                    break
+            if status is not None:
+                break
+        status = abi.DONE if status is None else status
+        n = int(res.accepted[rep])
+        assert n == len(trace) and np.array_equal(res.trace_row[rep, :n].cpu().numpy(), trace)
+        assert int(res.status[rep]) == status and int(sim.ties[rep]) == k
+
+
 def test_batched_queue_evaluator_and_dataset_front_end(ob, golden):
     import torch
     from oracle import psrs_oracle as O
@@ -458,6 +545,47 @@ def test_psrs_exo_matches_reference(ob, golden, seed):
             ob_ = env.reset(seed=episode)
             obs.append(-1 if ob_ is None else ob_)
     assert n == expect.size and np.array_equal(np.array(obs, dtype=np.int64), g[f"obs_{seed}"])
+
+
+@pytest.mark.parametrize("seed", [1, 6])
+def test_batched_psrs_exo_matches_reference(ob, golden, seed):
+    """BatchedPSRSExo — the vector form of PSRS_Exo: five replicas driven like the reference run of the golden file (reset with
+    seed = episode index re-seeds each generator, psrs.py:92), every one serving the golden's rows and observations."""
+    import torch
+    from offsim4rl_b200 import _abi as abi
+    g = golden("psrs_exo")
+    nX, N, R = 3, len(g["z"]), 5
+    common = dict(action=g["a"], reward=g["r"], terminal=g["done"], p_log=g["p_log"], steps=g["t"])
+    log_s = ob.BucketedLog(z=g["z"], z_next=g["z_next"], **common).seeded(seed)
+    log_x = ob.BucketedLog(z=g["x"], z_next=g["x_next"], **common).seeded(seed)
+    sim = ob.BatchedPSRSExo(log_s, log_x, R, seed=seed)
+    expect, want_obs = g[f"trace_{seed}"], g[f"obs_{seed}"]
+    episode = torch.zeros(R, dtype=torch.int64)
+    s, x, status = sim.reset(seeds=episode.numpy())
+    obs = [[int(s[r]) * nX + int(x[r]) if int(status[r]) == abi.RUNNING else -1] for r in range(R)]
+    rows = [[] for _ in range(R)]
+    alive = (status == abi.RUNNING).cpu()
+    for _ in range(4 * N):
+        if not bool(alive.any()):
+            break
+        out = sim.step(g["p_new"], mask=alive.to(torch.uint8))
+        row, term = out["row"].cpu(), out["terminal"].cpu().bool()
+        s2, x2 = out["s_next"].cpu(), out["x_next"].cpu()
+        stepped = alive & (row >= 0)
+        for r in torch.nonzero(stepped).flatten().tolist():
+            rows[r].append(int(row[r]))
+            obs[r].append(int(s2[r]) * nX + int(x2[r]))
+        alive = stepped.clone()
+        ended = stepped & term
+        if bool(ended.any()):
+            episode += ended.long()
+            s, x, status = sim.reset(seeds=episode.numpy(), mask=ended.to(torch.uint8))
+            for r in torch.nonzero(ended).flatten().tolist():
+                ok = int(status[r]) == abi.RUNNING
+                obs[r].append(int(s[r]) * nX + int(x[r]) if ok else -1)
+                alive[r] = ok
+    for r in range(R):
+        assert np.array_equal(rows[r], expect) and np.array_equal(obs[r], want_obs)
 
 
 # --------------------------------------------------------------------------- ingest (SURVEY §8f rank 4)
