@@ -279,6 +279,13 @@ int ols_encode_mlp(const float* obs, int64_t n, int32_t d_obs, const float* W1, 
                    const float* W2, const float* b2, int32_t n_latent, float negative_slope, int32_t* ids,
                    void* stream);
 
+/* The same ids, plus what a caller needs to AUDIT them against another float32 implementation of the same network (torch's
+ * sgemm sums in a different order, so rows whose two largest logits are closer than the rounding error of a dot product may
+ * get another id there): margin[i] = largest - second largest logit, hnorm[i] = sum_j |h_j| of the hidden vector.        */
+int ols_encode_mlp_audit(const float* obs, int64_t n, int32_t d_obs, const float* W1, const float* b1, int32_t hidden,
+                         const float* W2, const float* b2, int32_t n_latent, float negative_slope, int32_t* ids, float* margin,
+                         float* hnorm, void* stream);
+
 /* ---- bucketing: psrs.py:19-30 `PSRS.reset_sampler` ---------------------------------------- */
 int32_t ols_record_bytes(int32_t n_actions);
 size_t ols_bucket_scratch_bytes(int64_t n_rows, int32_t n_buckets);

@@ -79,6 +79,7 @@ SIGNATURES = {
     "ols_encode_grid": (C.c_int, [p, i64, i32, i32, p, p]),
     "ols_encode_cartpole_box": (C.c_int, [p, i32, i64, p, p]),
     "ols_encode_mlp": (C.c_int, [p, i64, i32, p, p, i32, p, p, i32, C.c_float, p, p]),
+    "ols_encode_mlp_audit": (C.c_int, [p, i64, i32, p, p, i32, p, p, i32, C.c_float, p, p, p, p]),
     "ols_record_bytes": (i32, [i32]),
     "ols_bucket_scratch_bytes": (C.c_size_t, [i64, i32]),
     "ols_bucket": (C.c_int, [C.POINTER(Log), C.POINTER(Queues), p, C.c_size_t, p]),

@@ -91,11 +91,15 @@ constexpr int kMlpKB = 8;  // latent states per block of the output layer
 
 __host__ __device__ inline int mlp_padded_latent(int n_latent) { return (n_latent + kMlpKB - 1) / kMlpKB * kMlpKB; }
 
+// AUDIT: also write, per row, the margin between the two largest logits and sum_j |h_j| — what a caller needs to bound the
+// effect of the accumulation order on the arg-max (ols_encode_mlp_audit)
+template <bool AUDIT>
 __global__ void __launch_bounds__(kMlpThreads) encode_mlp_kernel(const float* __restrict__ obs, int64_t n, int d_obs,
                                                                   const float* __restrict__ W1, const float* __restrict__ b1,
                                                                   int hidden, const float* __restrict__ W2,
                                                                   const float* __restrict__ b2, int n_latent, float slope,
-                                                                  int32_t* __restrict__ ids) {
+                                                                  int32_t* __restrict__ ids, float* __restrict__ margin,
+                                                                  float* __restrict__ hnorm) {
   extern __shared__ __align__(16) float smem[];
   const int KP = mlp_padded_latent(n_latent);
   float* sW2t = smem;                      // [hidden][KP], 16-byte aligned rows
@@ -123,13 +127,16 @@ __global__ void __launch_bounds__(kMlpThreads) encode_mlp_kernel(const float* __
     __syncthreads();
     int64_t i = base + t;
     if (i < n) {
+      float hn = 0.0f;
       for (int j = 0; j < hidden; ++j) {
         float acc = sb1[j];
         for (int d = 0; d < d_obs; ++d) acc = __fmaf_rn(sx[d * kMlpThreads + t], sW1[j * d_obs + d], acc);
-        sh[j * kMlpThreads + t] = acc > 0.0f ? acc : __fmul_rn(acc, slope);
+        const float h = acc > 0.0f ? acc : __fmul_rn(acc, slope);
+        sh[j * kMlpThreads + t] = h;
+        if (AUDIT) hn += fabsf(h);
       }
       int best = 0;
-      float best_v = 0.0f;
+      float best_v = 0.0f, second_v = -INFINITY;
       for (int kb = 0; kb < KP; kb += kMlpKB) {
         float acc[kMlpKB];
         const float4 ba = *(const float4*)(sb2 + kb), bb = *(const float4*)(sb2 + kb + 4);
@@ -153,12 +160,19 @@ __global__ void __launch_bounds__(kMlpThreads) encode_mlp_kernel(const float* __
         for (int u = 0; u < kMlpKB; ++u) {
           const int k = kb + u;
           if (k < n_latent && (k == 0 || acc[u] > best_v)) {  // strict >: first maximum wins
+            if (AUDIT && k > 0) second_v = best_v;
             best_v = acc[u];
             best = k;
+          } else if (AUDIT && k < n_latent && acc[u] > second_v) {
+            second_v = acc[u];
           }
         }
       }
       ids[i] = best;
+      if (AUDIT) {
+        margin[i] = best_v - second_v;  // +inf with a single latent state
+        hnorm[i] = hn;
+      }
     }
     __syncthreads();
   }
@@ -194,23 +208,42 @@ extern "C" int ols_encode_cartpole_box(const void* obs, int32_t obs_is_f64, int6
   return OLS_OK;
 }
 
-extern "C" int ols_encode_mlp(const float* obs, int64_t n, int32_t d_obs, const float* W1, const float* b1,
-                              int32_t hidden, const float* W2, const float* b2, int32_t n_latent, float negative_slope,
-                              int32_t* ids, void* stream) {
-  OLS_REQUIRE(n >= 0 && d_obs >= 1 && hidden >= 1 && n_latent >= 1, OLS_ERR_INVALID, "ols_encode_mlp: bad sizes");
+static int encode_mlp_impl(const float* obs, int64_t n, int32_t d_obs, const float* W1, const float* b1, int32_t hidden,
+                           const float* W2, const float* b2, int32_t n_latent, float negative_slope, int32_t* ids, float* margin,
+                           float* hnorm, void* stream, const char* who) {
+  OLS_REQUIRE(n >= 0 && d_obs >= 1 && hidden >= 1 && n_latent >= 1, OLS_ERR_INVALID, "%s: bad sizes", who);
   if (n == 0) return OLS_OK;
-  OLS_REQUIRE(obs && W1 && b1 && W2 && b2 && ids, OLS_ERR_INVALID, "ols_encode_mlp: null pointer");
+  OLS_REQUIRE(obs && W1 && b1 && W2 && b2 && ids, OLS_ERR_INVALID, "%s: null pointer", who);
   const int KP = mlp_padded_latent(n_latent);
   size_t smem = sizeof(float) * ((size_t)hidden * d_obs + hidden + (size_t)KP * hidden + KP +
                                  (size_t)(d_obs + hidden) * kMlpThreads);
-  OLS_REQUIRE(smem <= 227 * 1024, OLS_ERR_UNSUPPORTED,
-              "ols_encode_mlp: weights + activations need %zu B of shared memory (> 227 KB)", smem);
-  if (smem > 48 * 1024)
-    OLS_CUDA_CHECK(cudaFuncSetAttribute(encode_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  OLS_REQUIRE(smem <= 227 * 1024, OLS_ERR_UNSUPPORTED, "%s: weights + activations need %zu B of shared memory (> 227 KB)", who, smem);
+  const bool audit = margin != nullptr;
+  if (smem > 48 * 1024) {
+    if (audit) OLS_CUDA_CHECK(cudaFuncSetAttribute(encode_mlp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else OLS_CUDA_CHECK(cudaFuncSetAttribute(encode_mlp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
   int64_t blocks = (n + kMlpThreads - 1) / kMlpThreads;
   int grid = (int)(blocks < OLS_SM_COUNT * 4 ? blocks : OLS_SM_COUNT * 4);
-  encode_mlp_kernel<<<grid, kMlpThreads, smem, (cudaStream_t)stream>>>(obs, n, d_obs, W1, b1, hidden, W2, b2, n_latent,
-                                                                       negative_slope, ids);
+  if (audit)
+    encode_mlp_kernel<true><<<grid, kMlpThreads, smem, (cudaStream_t)stream>>>(obs, n, d_obs, W1, b1, hidden, W2, b2, n_latent,
+                                                                               negative_slope, ids, margin, hnorm);
+  else
+    encode_mlp_kernel<false><<<grid, kMlpThreads, smem, (cudaStream_t)stream>>>(obs, n, d_obs, W1, b1, hidden, W2, b2, n_latent,
+                                                                                negative_slope, ids, nullptr, nullptr);
   OLS_LAUNCH_CHECK();
   return OLS_OK;
+}
+
+extern "C" int ols_encode_mlp(const float* obs, int64_t n, int32_t d_obs, const float* W1, const float* b1,
+                              int32_t hidden, const float* W2, const float* b2, int32_t n_latent, float negative_slope,
+                              int32_t* ids, void* stream) {
+  return encode_mlp_impl(obs, n, d_obs, W1, b1, hidden, W2, b2, n_latent, negative_slope, ids, nullptr, nullptr, stream, "ols_encode_mlp");
+}
+
+extern "C" int ols_encode_mlp_audit(const float* obs, int64_t n, int32_t d_obs, const float* W1, const float* b1, int32_t hidden,
+                                    const float* W2, const float* b2, int32_t n_latent, float negative_slope, int32_t* ids,
+                                    float* margin, float* hnorm, void* stream) {
+  OLS_REQUIRE(n == 0 || (margin && hnorm), OLS_ERR_INVALID, "ols_encode_mlp_audit: null margin / hnorm");
+  return encode_mlp_impl(obs, n, d_obs, W1, b1, hidden, W2, b2, n_latent, negative_slope, ids, margin, hnorm, stream, "ols_encode_mlp_audit");
 }

@@ -76,3 +76,32 @@ class HOMEREncoder:
 
     def encode(self, observations):
         return self.encode_device(observations).cpu().numpy().astype(np.int64)
+
+    def audit_device(self, observations):
+        """``(ids, near_tie)`` on the device: ``near_tie[i]`` marks the rows whose two largest logits are closer than a
+        forward-error bound of the float32 dot products — the only rows where another float32 implementation of the same
+        network (the reference's torch forward, whose sgemm sums in another order) can return a different id.  The ids are
+        this package's own (bias first, then ``fmaf`` over the inputs in index order; bit-exact against the oracle)."""
+        if self._w is None:
+            raise ValueError("Model not initialized. Either train a new model for the encoder or load an existing one.")
+        dev = _require_cuda(self._device)
+        W1, b1, W2, b2 = self._w
+        with torch.cuda.device(dev):
+            obs = _as_tensor(observations, dev, torch.float32)
+            if obs.dim() != 2 or obs.shape[1] != self.obs_dim:
+                raise ValueError(f"expected observations of shape [N, {self.obs_dim}]")
+            n = obs.shape[0]
+            ids = torch.empty(n, dtype=torch.int32, device=dev)
+            margin = torch.empty(n, dtype=torch.float32, device=dev)
+            hnorm = torch.empty(n, dtype=torch.float32, device=dev)
+            abi.check(abi.load().ols_encode_mlp_audit(_ptr(obs), n, self.obs_dim, _ptr(W1), _ptr(b1), self.hidden_size, _ptr(W2),
+                                                      _ptr(b2), self.latent_size, C.c_float(self.negative_slope), _ptr(ids),
+                                                      _ptr(margin), _ptr(hnorm), _stream_ptr()))
+            # |error of a logit| <= gamma_{H+1} (|b2| + sum_j |h_j| |W2_kj|) + sum_j |dh_j| |W2_kj|, with the hidden units
+            # themselves off by |dh_j| <= gamma_{dO+1} (|b1_j| + sum_d |x_d| |W1_jd|); both implementations err, hence the 2
+            eps = 2.0 ** -24
+            w2max, b2max = W2.abs().max(), b2.abs().max()
+            layer1 = (obs.abs() @ W1.abs().t() + b1.abs()).sum(1)
+            bound = 2.0 * eps * 1.01 * ((self.hidden_size + 1) * (b2max + hnorm * w2max) + (self.obs_dim + 1) * layer1 * w2max)
+            near = margin <= 2.0 * bound            # the DIFFERENCE of two logits
+        return ids, near

@@ -369,6 +369,12 @@ def test_mlp_encoder_matches_fma_oracle_bit_exact(ob, golden, tag):
     assert np.array_equal(ids, O.mlp_ids(x, W1, b1, W2, b2))
     # against torch (the reference's own forward): equal except float32 near-ties (see the oracle test)
     assert (ids != g[f"{tag}_ids"]).sum() <= 2
+    # ... and every such row is flagged by the audit (margin of the two largest logits within the rounding-error bound),
+    # which flags few rows: a caller can list exactly the ids that depend on the accumulation order
+    ids2, near = enc.audit_device(x)
+    near = near.cpu().numpy()
+    assert np.array_equal(ids2.cpu().numpy(), ids)
+    assert near[ids != g[f"{tag}_ids"]].all() and near.mean() < 0.02
 
 
 def test_grid_encoder(ob):
