@@ -15,8 +15,9 @@ from .psrs import PSRS
 
 
 class PerStateRejectionSampling(RevealedRandomnessEnv):
-    # "default": psrs.py:53-57.  Subclasses that accept every transition set "accept_all" instead of overriding
-    # `_reject` (a Python callback cannot run inside the CUDA step).
+    # "default": psrs.py:53-57, inside the CUDA step.  Subclasses that accept every transition set "accept_all" (also on the
+    # device).  A subclass that OVERRIDES `_reject` with Python code (per_state_rejection.py:97-98 is a hook) is served by the
+    # host-driven single-pop loop of `PSRS` — API compatibility, not a fast path.
     _reject_mode = "default"
 
     def __init__(self, dataset, num_states=None, encoder=None, new_step_api=False, device=None):
@@ -26,10 +27,7 @@ class PerStateRejectionSampling(RevealedRandomnessEnv):
             raise ValueError("num_states and encoder either both need to be None, or both need to be specified")
         if not is_discrete(dataset.action_space):
             raise ValueError("PerStateRejectionSampling currently only supports discrete action spaces")
-        if type(self)._reject is not PerStateRejectionSampling._reject:
-            raise NotImplementedError(
-                "overriding _reject with Python code is not supported on the device; set the class attribute "
-                "_reject_mode = 'accept_all' (see trivial_baselines) or use the default rule")
+        overridden = type(self)._reject is not PerStateRejectionSampling._reject
         self._dataset = dataset
         exp = dataset.experience
         obs, next_obs = exp["observations"], exp["next_observations"]
@@ -45,7 +43,8 @@ class PerStateRejectionSampling(RevealedRandomnessEnv):
         self._impl = PSRS.from_arrays(
             z=zs, z_next=next_zs, action=exp["actions"], reward=exp["rewards"], terminal=exp["terminals"],
             p_log=exp["action_distributions"], steps=exp.get("steps"), s=None, s_next=None,
-            nS=num_states if num_states is not None else 25, nA=nA, reject=self._reject_mode, device=device)
+            nS=num_states if num_states is not None else 25, nA=nA, reject=self._reject if overridden else self._reject_mode,
+            device=device)
         # the environment hands back the logged observations themselves, not their ids
         self._impl._s_rows, self._impl._s_next_rows = obs, next_obs
         if self._impl.s is not None:

@@ -29,16 +29,16 @@ class PSRS(object):
     """Rejection sampler that acts as an environment (reference: psrs.py:5-57).
 
     ``buffer`` holds legacy tuples ``(s, a, r, s', done, p, info)`` with ``info['z']``, ``info['z_next']``
-    (or ``'next_z'``) and ``info['t']`` (psrs.py:8,17,22).  ``reject_func`` cannot be arbitrary Python on
-    the device: pass ``None``/``"default"`` for psrs.py:53-57 or ``"accept_all"`` for the trivial
-    baselines (trivial_baselines.py:8-10).
+    (or ``'next_z'``) and ``info['t']`` (psrs.py:8,17,22).  ``reject_func``: ``None``/``"default"`` for psrs.py:53-57 and
+    ``"accept_all"`` for the trivial baselines (trivial_baselines.py:8-10) run inside the CUDA step; any other callable
+    ``reject_func(p_new, p_log, a) -> bool`` (psrs.py:11,47) is honoured through a HOST-driven loop — one single-record pop
+    on the GPU per call of the function — which is API compatibility, not a fast path (and keeps such an env out of the
+    fused drivers).  ``env.rejection_sampling_rng`` is then the reference's ``default_rng(seed)`` for the callable to use.
     """
 
     def __init__(self, buffer, nS=25, nA=5, reject_func=None, device=None):
-        if reject_func not in _REJECT_NAMES:
-            raise NotImplementedError(
-                "a Python reject_func cannot run inside the CUDA step; use reject_func=None (the reference's "
-                "_default_reject) or reject_func='accept_all' (FollowObservationOnly / ServeRandomTransitions)")
+        if not (callable(reject_func) or reject_func in _REJECT_NAMES):
+            raise ValueError("reject_func must be None, 'default', 'accept_all' or a callable (p_new, p_log, a) -> bool")
         rows = list(buffer)                               # the reference also materialises it (psrs.py:17)
         n = len(rows)
         z = np.fromiter((r[6]["z"] for r in rows), dtype=np.int64, count=n)
@@ -49,7 +49,7 @@ class PSRS(object):
             z=z, z_next=z_next, action=np.array([r[1] for r in rows]), reward=np.array([r[2] for r in rows]),
             terminal=np.array([bool(r[4]) for r in rows]), p_log=p_log, steps=t,
             s=[r[0] for r in rows], s_next=[r[3] for r in rows], nS=nS, nA=nA,
-            reject=_REJECT_NAMES[reject_func], device=device)
+            reject=reject_func if callable(reject_func) else _REJECT_NAMES[reject_func], device=device)
 
     @classmethod
     def from_arrays(cls, z, z_next, action, reward, terminal, p_log, steps=None, s=None, s_next=None, nS=25, nA=None,
@@ -86,7 +86,10 @@ class PSRS(object):
                                 z_next=z_next_in if isinstance(z_next_in, torch.Tensor) else self._z_next,
                                 action=action, reward=reward, terminal=terminal,
                                 p_log=p_log, s=s_int, s_next=s_next_int, steps=steps, device=device)
-        self._reject = reject
+        # a Python callable decides on the host, one popped record at a time; the device then serves single pops
+        self._host_reject = reject if callable(reject) else None
+        self._reject = "accept_all" if callable(reject) else reject
+        self.rejection_sampling_rng = None
         self._sim = None
         self.s = self.z = None
         self.reset_sampler()
@@ -97,6 +100,8 @@ class PSRS(object):
         if seed is None:
             seed = secrets.randbits(63)          # default_rng(None): fresh OS entropy (psrs.py:13,20)
         self._seed = int(seed)
+        if self._host_reject is not None:
+            self.rejection_sampling_rng = np.random.default_rng(self._seed)       # psrs.py:20, for the callable's own use
         self._cur = self._log.seeded(self._seed)
         self._init_rows_host = self._cur.init_row[: self._cur.n_init].cpu().numpy()
         if self._sim is None:
@@ -147,15 +152,23 @@ class PSRS(object):
         p = np.asarray(p_new)
         if p.dtype not in (np.float32, np.float64):
             p = p.astype(np.float64)
-        out = self._sim.step(p)
-        row = int(out["row"][0])
-        if row < 0:
-            status = int(self._sim.status[0])
-            if status == abi.NO_QUEUE:
-                raise KeyError(self.z)            # psrs.py:44 — queues[z] for a z never logged as a from-state
-            if status == abi.FEED_EMPTY:
-                raise IndexError("the fed uniform stream is exhausted")
-            return None, None, None, None         # psrs.py:44-45
+        while True:
+            out = self._sim.step(p)               # with a host callable: ONE record popped, accepted unconditionally
+            row = int(out["row"][0])
+            if row < 0:
+                status = int(self._sim.status[0])
+                if status == abi.NO_QUEUE:
+                    raise KeyError(self.z)        # psrs.py:44 — queues[z] for a z never logged as a from-state
+                if status == abi.FEED_EMPTY:
+                    raise IndexError("the fed uniform stream is exhausted")
+                return None, None, None, None     # psrs.py:44-45
+            if self._host_reject is None or not self._host_reject(p_new, self._p_log[row], self._action[row]):
+                break
+            # psrs.py:46-48 — rejected: the record is gone, the state is unchanged; pop again
+            self._sim.cur_z.fill_(int(self.z))
+            if _is_int_like(self.s):
+                self._sim.cur_s.fill_(int(self.s))
+            self._sim.accepted -= 1
         z_from = self.z
         self.s = self._s_next_rows[row]
         self.z = int(self._z_next[row])
@@ -300,7 +313,7 @@ def _schedule(x):
 
 
 def _fusable(env):
-    return isinstance(env, PSRS)
+    return isinstance(env, PSRS) and env._host_reject is None
 
 
 def _rows_to_memory(env, rows):

@@ -203,8 +203,60 @@ def test_unseen_state_raises_keyerror_like_the_reference(ob):
     with pytest.raises(KeyError):
         env.step(p)
     assert env.reset() is None                                              # psrs.py:33-35
-    with pytest.raises(NotImplementedError):
-        PSRS(rows, nS=3, nA=2, reject_func=lambda *a: False)
+    with pytest.raises(ValueError):
+        PSRS(rows, nS=3, nA=2, reject_func="no such rule")
+
+
+def test_python_reject_callbacks_run_through_the_host_loop(ob, golden):
+    """psrs.py:11,47 `reject_func` and per_state_rejection.py:97-98 `_reject` are hooks for arbitrary Python: they are served
+    by a host-driven loop (one single-record pop on the GPU per call).  With the reference's own rule written as a callable
+    over the fed uniform stream, the run equals the golden run of the unmodified reference (which decided on the device
+    path's behalf in every other test)."""
+    from offsim4rl_b200.evaluators.psrs import PSRS, evalMC_psrs, qlearn_psrs
+    from offsim4rl_b200.agents import tabular
+    g = golden("drivers_f64")
+    nS, nA = g["pi"].shape
+    U, k = g["U"], [0]
+
+    def reject(p_new, p_log, a):                       # psrs.py:53-57 on the harness's uniforms
+        a = int(a)
+        M = (p_new / p_log).max()
+        u = U[k[0]]
+        k[0] += 1
+        return u > p_new[a] / p_log[a] / M
+
+    env = PSRS(_legacy(g), nS=nS, nA=nA, reject_func=reject)
+    env.reset_sampler(seed=int(g["sampler_seed"]))
+    assert env.rejection_sampling_rng is not None
+    Gs, lengths = evalMC_psrs(env, n_episodes=40, pi=g["pi"], gamma=0.97)
+    assert np.array_equal(lengths, g["mc_lengths"]) and k[0] == int(g["mc_draws"])
+    np.testing.assert_allclose(Gs, g["mc_Gs"], rtol=1e-5, atol=1e-5)
+    assert int(env._sim.accepted[0]) == g["mc_trace"].size and env.pops == int(g["mc_draws"])
+    # the gym-style wrapper with an overridden _reject hook
+    from offsim4rl_b200.evaluators import PerStateRejectionSampling
+    from offsim4rl_b200.data import OfflineDataset, ProbDistribution
+    from offsim4rl_b200 import spaces
+    w = golden("wrapper")
+    calls = [0]
+
+    class AcceptEveryOther(PerStateRejectionSampling):
+        def _reject(self, p_new, p_log, a):
+            calls[0] += 1
+            return calls[0] % 2 == 0
+
+    ds = OfflineDataset(observation_space=spaces.Discrete(8), action_space=spaces.Discrete(4), action_dist_type=ProbDistribution.Discrete,
+                        observations=w["disc_z"], actions=w["disc_a"], action_distributions=w["disc_p_log"], rewards=w["disc_r"],
+                        next_observations=w["disc_z_next"], terminals=w["disc_done"])
+    envw = AcceptEveryOther(ds)
+    envw.reset_sampler(seed=2)
+    obs, served = envw.reset(), 0
+    while obs is not None and served < 20:
+        res = envw.step_dist(w["disc_target"])
+        if res[0] is None:
+            break
+        served += 1
+        obs = envw.reset() if res[3] else res[1]
+    assert served > 0 and calls[0] >= served and envw._impl.pops == calls[0]
 
 
 # ----------------------------------------------------------------------------- gym-style wrapper
