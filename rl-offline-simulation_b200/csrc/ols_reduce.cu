@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) curve_partial_kernel(const double* __rest
 
 // block = 32 episodes (x) by 32 slab stripes (y): stripe y folds slabs y, y + 32, ... in order, then the stripes are folded in
 // order — a fixed summation tree, so the curve is deterministic (and independent of the launch geometry)
-__global__ void __launch_bounds__(1024) curve_fold_kernel(const double* __restrict__ partial, int n_slabs, int n_episodes,
+__global__ void __launch_bounds__(1024, 1) curve_fold_kernel(const double* __restrict__ partial, int n_slabs, int n_episodes,
                                                           double* __restrict__ sum, double* __restrict__ sumsq,
                                                           double* __restrict__ count) {
   __shared__ double s_a[32][33], s_b[32][33], s_c[32][33];
@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(1024) curve_fold_kernel(const double* __restri
   s_c[threadIdx.y][threadIdx.x] = c;
   __syncthreads();
   if (threadIdx.y == 0 && e < n_episodes) {
+#pragma unroll 4
     for (int y = 1; y < 32; ++y) {
       a += s_a[y][threadIdx.x];
       b += s_b[y][threadIdx.x];
