@@ -255,10 +255,29 @@ typedef struct ols_queue_run {
   int64_t trace_cap;
 } ols_queue_run_t;
 
+/* ---- fused PSRS_Exo evaluation (evalMC_psrs, psrs.py:241-271, over psrs.py:59-117) ------------------------------ */
+typedef struct ols_exo_run {
+  int32_t n_obs;              /* rows of pi: observations o = s * x_mult + x                      */
+  int32_t x_mult;             /* the linear o_combine_func (psrs.py:64): o = s * x_mult + x       */
+  int32_t pi_is_f64;
+  int32_t compute_mode;       /* OLS_COMPUTE_*                                                    */
+  int32_t n_episodes;
+  int32_t ep_cap;             /* row length of Gs / lengths (>= n_episodes + 1)                   */
+  int64_t max_steps;          /* > 0: stop after this many transitions in THIS call (resumable)   */
+  double gamma;
+  const void* pi;             /* [n_obs][n_actions] the evaluated policy                          */
+  const uint64_t* reseed_base;/* PCG64: episode e of replica r re-seeds with reseed_base[r] + e (psrs.py:92 with the
+                                 drivers' reset(seed=episode)); NULL = e, the reference's own seeds                 */
+  double* Gs;                 /* [n_replicas][ep_cap] discounted return per COMPLETED episode     */
+  int32_t* lengths;           /* [n_replicas][ep_cap]                                             */
+  int32_t* trace_row;         /* [n_replicas][trace_cap] accepted log rows, or NULL               */
+  int64_t trace_cap;
+} ols_exo_run_t;
+
 /* ---- library ------------------------------------------------------------------------------ */
 int ols_abi_version(void);
 const char* ols_last_error(void);                          /* HOST string, thread-local          */
-/* sizeof() of each struct as compiled, indexed 0..5 = log, queues, replicas, step_out, run, queue_run —
+/* sizeof() of each struct as compiled, indexed 0..6 = log, queues, replicas, step_out, run, queue_run, exo_run —
  * lets a binding verify its mirror of the layouts.                                            */
 size_t ols_struct_bytes(int which);
 /* kernels this library has launched in this process so far (every entry point counts its own launches; memsets and the
@@ -337,6 +356,11 @@ int ols_step_action(const ols_queues_t* q, const ols_replicas_t* r, const uint8_
 int ols_step_exo(const ols_queues_t* qs, const ols_queues_t* qx, const ols_replicas_t* r, int32_t* cursor_x, int32_t* cur_x,
                  const uint8_t* mask, const void* p_new, int32_t p_new_is_f64, int64_t p_stride, int32_t compute_mode,
                  int32_t lanes, const ols_step_out_t* out, int32_t* out_x_next, void* stream);
+/* evalMC_psrs (psrs.py:241-271) over a PSRS_Exo environment as ONE launch, one independent run per replica: reset(seed =
+ * episode) with the generator re-seeded (PCG64 mode), policy row pi[s * x_mult + x], lock-step pops of the s- and x-queue
+ * (ols_step_exo) until accepted, returns accumulated per episode.  Ring offsets are not applied (as in ols_step_exo).      */
+int ols_run_exo(const ols_queues_t* qs, const ols_queues_t* qx, const ols_replicas_t* r, int32_t* cursor_x, int32_t* cur_x,
+                const ols_exo_run_t* run, void* stream);
 /* psrs.py:92 (PSRS_Exo.reset), queue_evaluator.py:114 — `rejection_sampling_rng = default_rng(seed)` again: re-seed the
  * PCG64 state of the replicas with mask[r] != 0 from seeds[r] (NULL = r->seed) and restart their draw counters.     */
 int ols_reseed(const ols_replicas_t* r, const uint64_t* seeds, const uint8_t* mask, void* stream);

@@ -68,7 +68,13 @@ class QueueRun(C.Structure):
                 ("trace_cap", i64)]
 
 
-STRUCTS = [Log, Queues, Replicas, StepOut, Run, QueueRun]
+class ExoRun(C.Structure):
+    _fields_ = [("n_obs", i32), ("x_mult", i32), ("pi_is_f64", i32), ("compute_mode", i32), ("n_episodes", i32), ("ep_cap", i32),
+                ("max_steps", i64), ("gamma", f64), ("pi", p), ("reseed_base", p), ("Gs", p), ("lengths", p), ("trace_row", p),
+                ("trace_cap", i64)]
+
+
+STRUCTS = [Log, Queues, Replicas, StepOut, Run, QueueRun, ExoRun]
 
 # every symbol include/ols_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
@@ -93,6 +99,7 @@ SIGNATURES = {
     "ols_step_action": (C.c_int, [C.POINTER(Queues), C.POINTER(Replicas), p, p, C.POINTER(StepOut), p]),
     "ols_step_exo": (C.c_int, [C.POINTER(Queues), C.POINTER(Queues), C.POINTER(Replicas), p, p, p, p, i32, i64, i32, i32,
                                C.POINTER(StepOut), p, p]),
+    "ols_run_exo": (C.c_int, [C.POINTER(Queues), C.POINTER(Queues), C.POINTER(Replicas), p, p, C.POINTER(ExoRun), p]),
     "ols_reseed": (C.c_int, [C.POINTER(Replicas), p, p, p]),
     "ols_run": (C.c_int, [C.POINTER(Queues), C.POINTER(Replicas), C.POINTER(Run), p]),
     "ols_run_actions": (C.c_int, [C.POINTER(Queues), C.POINTER(Replicas), C.POINTER(QueueRun), p]),

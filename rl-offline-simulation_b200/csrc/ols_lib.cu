@@ -46,6 +46,7 @@ extern "C" size_t ols_struct_bytes(int which) {
     case 3: return sizeof(ols_step_out_t);
     case 4: return sizeof(ols_run_t);
     case 5: return sizeof(ols_queue_run_t);
+    case 6: return sizeof(ols_exo_run_t);
     default: return 0;
   }
 }

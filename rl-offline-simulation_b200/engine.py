@@ -718,6 +718,38 @@ class BatchedPSRSExo:
         return dict(row=sim.out_row, action=sim.out_action, reward=sim.out_reward, terminal=sim.out_terminal, s_next=sim.out_s_next,
                     x_next=self.out_x_next, z_from=sim.out_z_from, status=sim.status)
 
+    def run_evalmc(self, n_obs, n_episodes, pi, gamma, x_mult, reseed_base=None, max_steps=0, trace_cap=0, ep_cap=None,
+                   outputs=None) -> RunResult:
+        """evalMC_psrs (psrs.py:241-271) over these PSRS_Exo simulators as ONE launch: the agent's policy row is
+        ``pi[s * x_mult + x]`` (the linear ``o_combine_func``); every episode re-seeds the replica's PCG64 generator with
+        ``reseed_base[r] + episode`` (``None``: ``episode``, what the reference's drivers do through ``reset(seed=episode)``)."""
+        sim = self.sim
+        dev, R, nA = sim.device, sim.R, self.log_s.n_actions
+        with torch.cuda.device(dev):
+            ep_cap = int(ep_cap or (n_episodes + 1))
+            if outputs is None:
+                Gs = torch.zeros((max(R, 1), ep_cap), dtype=torch.float64, device=dev)
+                lengths = torch.zeros((max(R, 1), ep_cap), dtype=torch.int32, device=dev)
+                trace_row = torch.full((max(R, 1), trace_cap), -1, dtype=torch.int32, device=dev) if trace_cap else None
+            else:
+                Gs, lengths, trace_row = outputs.Gs, outputs.lengths, outputs.trace_row
+            pi_t = _as_tensor(pi, dev)
+            if pi_t.dtype not in (torch.float32, torch.float64):
+                pi_t = pi_t.to(torch.float64)
+            if tuple(pi_t.shape) != (n_obs, nA):
+                raise ValueError("pi must be [n_obs, n_actions]")
+            compute = abi.COMPUTE_F32 if (pi_t.dtype == torch.float32 and self.log_s.p_source_f32) else abi.COMPUTE_F64
+            rb = None if reseed_base is None else _as_tensor(np.asarray(reseed_base, dtype=np.uint64).view(np.int64), dev)
+            cfg = abi.ExoRun(n_obs=int(n_obs), x_mult=int(x_mult), pi_is_f64=int(pi_t.dtype == torch.float64), compute_mode=compute,
+                             n_episodes=int(n_episodes), ep_cap=ep_cap, max_steps=int(max_steps), gamma=float(gamma), pi=_ptr(pi_t),
+                             reseed_base=_ptr(rb), Gs=_ptr(Gs), lengths=_ptr(lengths), trace_row=_ptr(trace_row), trace_cap=int(trace_cap))
+            qs, qx, r = self.log_s.queues_struct(), self.log_x.queues_struct(), sim.replicas_struct()
+            abi.check(sim.lib.ols_run_exo(C.byref(qs), C.byref(qx), C.byref(r), _ptr(self.cursor_x), _ptr(self.cur_x), C.byref(cfg),
+                                          _stream_ptr()))
+            return RunResult(Gs=Gs, lengths=lengths, n_returns=sim.ep_index.clone(), n_lengths=sim.ep_len_count.clone(),
+                             status=sim.status.clone(), accepted=sim.accepted.clone(), pops=sim.pops.clone(), trace_row=trace_row,
+                             td_error=None)
+
 
 # ----------------------------------------------------------------------------------------------- synthetic data
 def synth_columns(n_rows, n_states, pb_state, seed=0, p_done=1.0 / 50, device=None):

@@ -640,6 +640,43 @@ def test_batched_psrs_exo_matches_reference(ob, golden, seed):
         assert np.array_equal(rows[r], expect) and np.array_equal(obs[r], want_obs)
 
 
+@pytest.mark.parametrize("seed", [1, 6])
+def test_fused_psrs_exo_evaluation_matches_reference(ob, golden, seed):
+    """BatchedPSRSExo.run_evalmc (ols_run_exo: evalMC_psrs over PSRS_Exo in ONE launch, the generator re-seeded with the
+    episode index at every reset) serves the rows of the reference's own PSRS_Exo run (golden psrs_exo: a policy with the same
+    row for every observation), returns and lengths following from them; chunked launches equal one launch."""
+    import torch
+    from offsim4rl_b200 import _abi as abi
+    g = golden("psrs_exo")
+    nX, nS, nA, N, R = 3, 5, 3, len(g["z"]), 4
+    common = dict(action=g["a"], reward=g["r"], terminal=g["done"], p_log=g["p_log"], steps=g["t"])
+    log_s = ob.BucketedLog(z=g["z"], z_next=g["z_next"], **common).seeded(seed)
+    log_x = ob.BucketedLog(z=g["x"], z_next=g["x_next"], **common).seeded(seed)
+    pi = np.tile(g["p_new"], (nS * nX, 1))
+    expect = g[f"trace_{seed}"]
+    sim = ob.BatchedPSRSExo(log_s, log_x, R, seed=seed)
+    res = sim.run_evalmc(nS * nX, N, pi, gamma=0.9, x_mult=nX, trace_cap=N)
+    ends = np.nonzero(g["done"][expect])[0]
+    lens = np.diff(np.r_[-1, ends])
+    for r in range(R):
+        n = int(res.accepted[r])
+        assert n == expect.size and np.array_equal(res.trace_row[r, :n].cpu().numpy(), expect)
+        assert int(res.status[r]) in (abi.QUEUE_EMPTY, abi.INIT_EMPTY)
+        ne = int(res.n_returns[r])
+        assert ne == ends.size and np.array_equal(res.lengths[r, :ne].cpu().numpy(), lens)
+        Gs, k = [], 0
+        for L in lens:
+            Gs.append(sum(0.9 ** t * float(g["r"][expect[k + t]]) for t in range(L))); k += L
+        np.testing.assert_allclose(res.Gs[r, :ne].cpu().numpy(), Gs, rtol=1e-12, atol=1e-12)
+    sim2 = ob.BatchedPSRSExo(log_s, log_x, R, seed=seed)
+    out = None
+    for _ in range(N):
+        out = sim2.run_evalmc(nS * nX, N, pi, gamma=0.9, x_mult=nX, trace_cap=N, max_steps=5, outputs=out)
+        if bool((out.status != abi.RUNNING).all()):
+            break
+    assert torch.equal(out.trace_row, res.trace_row) and torch.equal(out.Gs, res.Gs) and torch.equal(out.status, res.status)
+
+
 # --------------------------------------------------------------------------- ingest (SURVEY §8f rank 4)
 @pytest.mark.gpu
 def test_recorded_dataset_flows_into_the_simulator(ob, tmp_path):
