@@ -31,17 +31,14 @@ constexpr int kLT = OLS_G1_THREADS;  // threads (= replicas) per CTA
 
 struct LearnerCold {
   double ep_G[kLT], ep_disc[kLT];
-  unsigned long long ties[kLT], accepted0[kLT];
+  unsigned long long ties[kLT];
   float4 qrow[kLT];   // Q[S, :] of the current state (the bootstrap row of the previous step)
   float4 qdist[kLT];  // the logged distribution of the current state's queue
   uint2 lim[4][kLT];  // per action: accept below .x, reject above .y (high word of the uniform), see make_limits
   uint2 park[kLT];    // a parked outcome: reward bits, next state | action | terminal
-  float4 nq[kLT];     // staged next state: its Q row ...
-  int4 nb[kLT];       // ... and its queue {bucket or -1, CSR start, length, this replica's cursor}
-  unsigned nstart[kLT];  // ... ring offset
   uint4 blk[kLT];     // the rejection stream's block that holds draw `draws` (block index draws >> 2)
   int ep_index[kLT], ep_len_count[kLT], ep_t[kLT], ep_open[kLT], init_cursor[kLT], status[kLT], n_acc[kLT], pn_ok[kLT],
-      eps_episode[kLT], budget[kLT], qtame[kLT];
+      eps_episode[kLT], qtame[kLT];
   float ipn_base[kLT], ipn_top[kLT];
   unsigned h_rep[kLT];
 };
@@ -105,7 +102,7 @@ __global__ void __launch_bounds__(kLT, OLS_LEARNER_MINB) learner_kernel(ols_queu
   bool live = false;
   C.n_acc[tid] = 0;
   C.eps_episode[tid] = -1;
-  C.budget[tid] = (int)max(0ll, min(budget64, 0x7fffffffll));
+  const int budget = (int)max(0ll, min(budget64, 0x7fffffffll));  // accepted transitions this launch / slice may add (0: no limit)
   C.h_rep[tid] = R.ring_mode ? ols_ring_replica_hash(R.ring_seed, rid) : 0u;
   C.status[tid] = OLS_IDLE;
   if (exists) {
@@ -115,7 +112,6 @@ __global__ void __launch_bounds__(kLT, OLS_LEARNER_MINB) learner_kernel(ols_queu
     C.status[tid] = status;
     C.init_cursor[tid] = __ldcg(R.init_cursor + r);
     C.ties[tid] = __ldcg(R.ties + r);
-    C.accepted0[tid] = __ldcg(R.accepted + r);
     C.ep_index[tid] = __ldcg(R.ep_index + r);
     C.ep_len_count[tid] = __ldcg(R.ep_len_count + r);
     C.ep_t[tid] = __ldcg(R.ep_t + r);
@@ -140,14 +136,13 @@ __global__ void __launch_bounds__(kLT, OLS_LEARNER_MINB) learner_kernel(ols_queu
 
   const int batch = cfg.batch_lanes > 0 ? min(cfg.batch_lanes, 32) : 20;
 
-  // Stage the next state of a parked, accepted transition: its AoS entry (cursor + Q row), its queue and that queue's
-  // distribution go to shared memory, and the hot span the next step will pop first is pulled toward L2.  Runs right before
+  // Stage the next state of a parked, accepted transition: its AoS entry (cursor + Q row), its queue and (to shared memory, for
+  // the next step block) that queue's distribution; the hot span the next step will pop first is pulled toward L2.  Runs right before
   // the update (the entry was prefetched at the accept, so for lanes parked a round or more the loads hit L2).  All loads are
   // issued before any is consumed.  Tried and dropped: staging one loop iteration after the accept, while the lane is still
   // parked (the extra divergent block costs more issue slots than the hidden latency buys: 165 ms against 150 ms), and
   // prefetching the span a rejected round would continue with (173 ms).
-  auto stage_next = [&]() {
-    const uint32_t zw = C.park[tid].y;
+  auto stage_next = [&](uint32_t zw, float4& nq, int4& nb, unsigned& nstart) {
     const int Z2 = ((int)(zw << 3)) >> 3;
     const bool inr = (Z2 >= 0 && Z2 < nS), want_q = inr && !(zw >> 31);
     float4 ea = make_float4(0.f, 0.f, 0.f, 0.f), eb = ea, qd = ea;
@@ -164,7 +159,7 @@ __global__ void __launch_bounds__(kLT, OLS_LEARNER_MINB) learner_kernel(ols_queu
     }
     const bool fresh = (__float_as_int(ea.y) == cfg.state_epoch);  // stale entries read as cursor 0 / Q 0
     const int cur = fresh ? __float_as_int(ea.x) : 0;
-    C.nq[tid] = fresh ? eb : make_float4(0.f, 0.f, 0.f, 0.f);
+    nq = fresh ? eb : make_float4(0.f, 0.f, 0.f, 0.f);
     const int len = hi - lo;
     const bool next_ok = want_q && len > 0;   // psrs.py:44 — a state never logged as a from-state has no queue
     unsigned start = 0;
@@ -176,8 +171,8 @@ __global__ void __launch_bounds__(kLT, OLS_LEARNER_MINB) learner_kernel(ols_queu
       if (pos >= (uint32_t)len) pos -= (uint32_t)len;
       asm volatile("prefetch.global.L2 [%0];" ::"l"(hot + (size_t)(uint32_t)(lo + (int)pos)));
     }
-    C.nb[tid] = make_int4(next_ok ? Z2 : -1, next_ok ? lo : 0, next_ok ? len : 0, next_ok ? cur : 0);
-    C.nstart[tid] = start;
+    nb = make_int4(next_ok ? Z2 : -1, next_ok ? lo : 0, next_ok ? len : 0, next_ok ? cur : 0);
+    nstart = start;
   };
 
   while (__any_sync(kFull, live)) {
@@ -364,7 +359,8 @@ __global__ void __launch_bounds__(kLT, OLS_LEARNER_MINB) learner_kernel(ols_queu
       pend = false;
       const int ep_index = C.ep_index[tid], lc = C.ep_len_count[tid], t_old = C.ep_t[tid], n_acc_old = C.n_acc[tid];
       const double G_old = C.ep_G[tid], disc = C.ep_disc[tid];
-      const long long acc_idx = (long long)C.accepted0[tid] + n_acc_old;
+      // index of this transition in the replica's lifetime (for the optional taps only)
+      const long long acc_idx = (cfg.trace_row || cfg.td_error) ? (long long)__ldcg(R.accepted + r) + n_acc_old : 0;
       const int b_done = b_cur, cur_done = b_pos;  // the queue just popped from and its new cursor
       const int S = cur_z;
       int new_status = -1;
@@ -382,12 +378,13 @@ __global__ void __launch_bounds__(kLT, OLS_LEARNER_MINB) learner_kernel(ols_queu
       const int A = (int)((p_zw >> 29) & 3u);
       if (accepted) {
         const double Rw = (double)__uint_as_float(p_rw);
-        stage_next();
-        const float4 nq = C.nq[tid];
-        const int4 nb = C.nb[tid];
+        float4 nq;
+        int4 nb;
+        unsigned nstart;
+        stage_next(p_zw, nq, nb, nstart);
         const bool next_ok = nb.x >= 0;
         if (!done) {
-          b_cur = nb.x; b_lo = nb.y; b_len = nb.z; b_pos = nb.w; b_start = C.nstart[tid];
+          b_cur = nb.x; b_lo = nb.y; b_len = nb.z; b_pos = nb.w; b_start = nstart;
         }
         if (next_ok && b_cur == b_done) b_pos = cur_done;  // a self-loop: the cursor in memory is still the old one
         bucket_valid = next_ok;
@@ -448,7 +445,6 @@ __global__ void __launch_bounds__(kLT, OLS_LEARNER_MINB) learner_kernel(ols_queu
         C.ep_G[tid] = G_new;
         C.ep_disc[tid] = __dmul_rn(disc, cfg.gamma);
         C.ep_t[tid] = t_new;
-        const int budget = C.budget[tid];
         if (budget > 0 && n_acc_old + 1 >= budget) live = false;  // budget: stays resumable
       }
       if (close_ep) {
@@ -473,7 +469,7 @@ __global__ void __launch_bounds__(kLT, OLS_LEARNER_MINB) learner_kernel(ols_queu
     R.pops[r] = __ldcg(R.pops + r) + (unsigned long long)(draws - __ldcg(R.draws + r));
     R.draws[r] = draws;
     R.ties[r] = C.ties[tid];
-    R.accepted[r] = C.accepted0[tid] + (unsigned long long)C.n_acc[tid];
+    R.accepted[r] = __ldcg(R.accepted + r) + (unsigned long long)C.n_acc[tid];
     R.ep_index[r] = C.ep_index[tid];
     R.ep_len_count[r] = C.ep_len_count[tid];
     R.ep_t[r] = C.ep_t[tid];
