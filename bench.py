@@ -357,7 +357,7 @@ def gather_stress_leg(ob, torch, dev, hbm_peak, launches=5, warm=3, hot="tail"):
                          hot_records=hot)
     del cols
     sim = ob.BatchedPSRS(log, R, rng="philox", seed=4321, ring=True, ring_seed=7, lanes=wl["lanes"])
-    pi = np.full((nS, nA), 1.0 / nA)
+    pi = torch.full((nS, nA), 1.0 / nA, dtype=torch.float64, device=dev)
     res, ms, pops = None, [], 0.0
     for i in range(launches + warm):
         sim.restart()
@@ -397,7 +397,7 @@ def queue_evaluator_leg(ob, torch, dev, hbm_peak, steps=200, launches=5, warm=2)
                          p_log=cols["p_log"], steps=cols["steps"], n_buckets=nS, z_offset=0, device=dev, key_by_action=True)
     del cols
     sim = ob.BatchedPSRS(log, R, rng="philox", seed=5, ring=True, ring_seed=11, lanes=1, reject="accept_all")
-    pi = np.full((nS, nA), 1.0 / nA)
+    pi = torch.full((nS, nA), 1.0 / nA, dtype=torch.float64, device=dev)
     res, ms, n = None, [], 0.0
     for i in range(launches + warm):
         sim.restart()
@@ -492,7 +492,7 @@ def main():
     N, nS, nA, R, T = wl["rows"], wl["states"], wl["actions"], wl["replicas"], wl["budget"]
     pb = behaviour_table(nS, nA, wl["delta"])
     qlearn = wl["delta"] is None
-    uniform_pi = np.full((nS, nA), 1.0 / nA)
+    uniform_pi = torch.full((nS, nA), 1.0 / nA, dtype=torch.float64, device=dev)   # resident: no per-step upload of the policy
 
     # ---- setup (untimed): synthetic log generated on the device, bucketed once
     cols = ob.synth_columns(N, nS, pb, seed=0, device=dev)
@@ -548,7 +548,7 @@ def main():
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("OLS_BENCH_NO_SAMPLER"):     # (the switch exists to measure what the sampler itself costs)
         sampler.start()
     for _ in range(args.warmup):
         one_step(False)

@@ -37,6 +37,7 @@ struct LearnerCold {
   uint2 lim[4][kLT];  // per action: accept below .x, reject above .y (high word of the uniform), see make_limits
   uint2 park[kLT];    // a parked outcome: reward bits, next state | action | terminal
   uint4 blk[kLT];     // the rejection stream's block that holds draw `draws` (block index draws >> 2)
+  uint4 tblk[kLT];    // the tie-break stream's block that holds tie `ties` (block index ties >> 2)
   int ep_index[kLT], ep_len_count[kLT], ep_t[kLT], ep_open[kLT], init_cursor[kLT], status[kLT], n_acc[kLT], pn_ok[kLT],
       eps_episode[kLT], qtame[kLT];
   float ipn_base[kLT], ipn_top[kLT];
@@ -121,6 +122,10 @@ __global__ void __launch_bounds__(kLT, OLS_LEARNER_MINB) learner_kernel(ols_queu
     live = (status == OLS_IDLE || status == OLS_RUNNING) && !no_budget;  // terminated replicas stay terminated
     const ols_u4 o = ols_stream_block(PK, rid, 0u, draws >> 2);
     C.blk[tid] = make_uint4(o.x, o.y, o.z, o.w);
+    if (R.tie_mode != OLS_RNG_FEED) {
+      const ols_u4 t = ols_stream_block(PK, rid, 1u, C.ties[tid] >> 2);
+      C.tblk[tid] = make_uint4(t.x, t.y, t.z, t.w);
+    }
   }
 
   // the queue of the current state
@@ -229,7 +234,14 @@ __global__ void __launch_bounds__(kLT, OLS_LEARNER_MINB) learner_kernel(ols_queu
             if ((int64_t)t0 < R.tie_feed_len) v = __ldg(R.tie_feed + rr * R.tie_stride + (int64_t)t0);
             else have = false;
           } else {
-            v = (double)ols_u4_word(ols_stream_block(PK, rid, 1u, t0 >> 2), (int)(t0 & 3)) * 2.3283064365386963e-10;
+            // stream 1, high word only (v = hi * 2^-32); four ties per block, the block carried in shared memory
+            const uint4 tb = C.tblk[tid];
+            const int w = (int)(t0 & 3);
+            v = (double)(w == 0 ? tb.x : w == 1 ? tb.y : w == 2 ? tb.z : tb.w) * 2.3283064365386963e-10;
+            if (w == 3) {
+              const ols_u4 t = ols_stream_block(PK, rid, 1u, (t0 >> 2) + 1);
+              C.tblk[tid] = make_uint4(t.x, t.y, t.z, t.w);
+            }
           }
           if (!have) {
             new_status = OLS_FEED_EMPTY;

@@ -484,7 +484,15 @@ class BatchedPSRS:
             vals = [float(x(e)) for e in range(n_episodes)]
             vals = vals + [vals[-1] if vals else 0.0]
         elif np.ndim(x) == 0:
-            vals = [float(x)] * (n_episodes + 1)
+            # constant schedules are kept on the device: building them again would put a blocking host-to-device copy (and so
+            # a pipeline bubble) in front of every run
+            key = (float(x), int(n_episodes))
+            cache = self.__dict__.setdefault("_sched_cache", {})
+            if key not in cache:
+                if len(cache) > 64:
+                    cache.clear()
+                cache[key] = torch.full((n_episodes + 1,), float(x), dtype=torch.float64, device=self.device)
+            return cache[key]
         else:
             vals = [float(v) for v in x]
             if len(vals) < n_episodes:
