@@ -5,8 +5,9 @@
 
 using namespace ols_sim;
 
-// ols_learner.cu
+// ols_learner.cu, ols_eval.cu
 cudaError_t ols_launch_learner(const ols_queues_t&, const ols_replicas_t&, const ols_run_t&, const ols_sim::RunLaunch&);
+cudaError_t ols_launch_eval(const ols_queues_t&, const ols_replicas_t&, const ols_run_t&, cudaStream_t);
 
 namespace {
 
@@ -254,6 +255,12 @@ extern "C" int ols_run(const ols_queues_t* q, const ols_replicas_t* r, const ols
   int ppl = c->pops_per_lane;
   if (ppl == 0) ppl = (r->rng_mode == OLS_RNG_PCG64 || c->reject_mode == OLS_REJECT_ACCEPT_ALL) ? 1 : 2;
   cudaError_t e;
+  if (tail_eval && c->lanes == 32 && slices <= 1 && !q->s_next && r->cursor) {
+    // the streaming evaluator: one warp per replica, warp-uniform control flow (ols_eval.cu)
+    e = ols_launch_eval(*q, *r, *c, (cudaStream_t)stream);
+    OLS_REQUIRE(e == cudaSuccess, OLS_ERR_CUDA, "ols_run: launch failed: %s", cudaGetErrorString(e));
+    return OLS_OK;
+  }
   if (fast_learner) {
     L.smem = 0;
     e = ols_launch_learner(*q, *r, *c, L);
