@@ -376,7 +376,8 @@ def gather_stress_leg(ob, torch, dev, hbm_peak, launches=5, warm=3, hot="tail"):
             "tail": "4 TAIL hot records of 8 bytes"}[hot]
     tr = load_traffic().get("c5_" + ("tail" if hot == "tail" else "probs" if hot else "full"), {})
     return {"workload": "c5: " + wl["desc"],
-            "kernel": "run_kernel (fixed-policy evaluation, lanes=32 x %s per round)" % kind,
+            "kernel": ("eval_kernel (streaming fixed-policy evaluation, one warp per replica x %s per lane and round)" if hot == "tail"
+                       else "run_kernel (fixed-policy evaluation, lanes=32 x %s per round)") % kind,
             "bytes_read_per_rejected_pop": read_per_pop, "pops_per_s": pops / t,
             "accepted_per_s": float(sim.accepted.sum()) / t, "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
             "frac_note": "contract bytes (SURVEY 8d: 32 B per popped record) / time / measured HBM copy peak; the kernel itself reads "
@@ -716,7 +717,9 @@ def main():
         roofline = {
             "bound": "hbm",
             "kernel": ("learner_kernel (one thread per replica: PSRS pops over TAIL hot records + epsilon-greedy Q-learning update, ols_learner.cu)"
-                       if (qlearn and tail_on and wl["lanes"] == 1) else "run_kernel (fused PSRS step + agent update / return evaluator)"),
+                       if (qlearn and tail_on and wl["lanes"] == 1) else
+                       "eval_kernel (one warp per replica: streaming PSRS pops over TAIL hot records + return evaluator, ols_eval.cu)"
+                       if (not qlearn and tail_on and wl["lanes"] == 32) else "run_kernel (fused PSRS step + agent update / return evaluator)"),
             "achieved": gather_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gather_gbs / hbm_peak,
             "frac_note": "contract bytes (SURVEY 8d: 32 B per popped record) / kernel time / measured HBM copy peak",
             "traffic": per_unit * units if per_unit else None,
