@@ -276,7 +276,10 @@ class BucketedLog:
 class RunResult:
     """Outputs of a fused learner run, as device tensors (reference: psrs.py:180-185, 235-239, 271).
 
-    ``Q`` is [R, nS, nA]; with the AoS replica state it is gathered from the live entries on first access."""
+    ``Q`` is [R, nS, nA]; with the AoS replica state it is gathered from the live entries on first access.  The
+    per-replica counters are snapshots taken when the run returned.  ``trace_row`` / ``td_error`` are indexed by the replica's
+    LIFETIME accepted count (since the last ``restart``): a resumed run continues the same trace, so pass the previous
+    result back through ``outputs=`` when chunking (fresh buffers would start at the resumed index, not at 0)."""
     Gs: torch.Tensor                     # [R, ep_cap] discounted returns; row r valid up to n_returns[r]
     lengths: torch.Tensor                # [R, ep_cap] episode lengths; row r valid up to n_lengths[r]
     n_returns: torch.Tensor              # [R]
