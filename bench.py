@@ -551,12 +551,15 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0 and not os.environ.get("OLS_BENCH_NO_SAMPLER"):     # (the switch exists to measure what the sampler itself costs)
         sampler.start()
+    acc_total = torch.zeros(2, dtype=torch.float64, device=dev)
     for _ in range(args.warmup):
         one_step(False)
+        acc_total[0] += sim.accepted.sum()      # every kernel of the timed loop runs once before it (CUDA loads modules lazily:
+        acc_total[1] += sim.pops.sum()          # the first launch of a kernel costs 10-40 ms and would land in the first timed step)
     barrier()
     sampler.begin()
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-    acc_total = torch.zeros(2, dtype=torch.float64, device=dev)
+    acc_total.zero_()
     launches0 = int(ob._abi.load().ols_kernel_launches())
     t0.record()
     for _ in range(args.steps):
@@ -754,6 +757,7 @@ def main():
             "bucketing": {"rows": N, "ms": bucket_ms, "GBps": bucket_bytes / bucket_ms / 1e6, "frac": bucket_bytes / bucket_ms / 1e6 / hbm_peak,
                           "note": "ols_bucket + ols_init_queue kernels; bytes = z twice + order + log columns + packed record per row"},
             "step_breakdown_ms": {k: sum(a.elapsed_time(b) for a, b in v) / max(1, len(v)) for k, v in k_ev.items()},
+            "step_ms_each": [round(a[0].elapsed_time(b[0]), 3) for a, b in zip(k_ev["restart"], k_ev["restart"][1:] + [(t1, None)])],
             "gather_stress": stress, "next_rows": next_rows,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches_timed),
             "gpu_launches_note": "kernels of libols_b200.so launched inside the timed region, counted by the library (ols_kernel_launches)",
