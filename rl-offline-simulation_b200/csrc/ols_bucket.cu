@@ -331,7 +331,9 @@ __global__ void __launch_bounds__(256) hot_pack_kernel(ols_queues_t q) {
   }
 }
 
-// Per queue: does every record hold the distribution of the first one (bitwise)?  One CTA per queue (grid-strided).
+// Per queue: does every record hold the distribution of the first one (bitwise)?  One CTA per queue (grid-strided).  The same
+// pass writes the hot records (when asked to), so the packed queues are read once for both.
+template <bool WRITE_HOT>
 __global__ void __launch_bounds__(256) queue_dist_kernel(ols_queues_t q) {
   __shared__ int s_diff;
   for (int b = blockIdx.x; b < q.n_buckets; b += gridDim.x) {
@@ -343,9 +345,18 @@ __global__ void __launch_bounds__(256) queue_dist_kernel(ols_queues_t q) {
     if (hi > lo) {
       p0 = __ldg((const float4*)((const char*)q.records + (size_t)lo * 32));
       for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        const float4 p = __ldg((const float4*)((const char*)q.records + (size_t)i * 32));
+        const float4* rp = (const float4*)((const char*)q.records + (size_t)i * 32);
+        const float4 p = __ldg(rp);
         diff |= (__float_as_uint(p.x) != __float_as_uint(p0.x)) | (__float_as_uint(p.y) != __float_as_uint(p0.y)) |
                 (__float_as_uint(p.z) != __float_as_uint(p0.z)) | (__float_as_uint(p.w) != __float_as_uint(p0.w));
+        if (WRITE_HOT) {
+          const float4 tail = __ldg(rp + 1);
+          const uint32_t meta = __float_as_uint(tail.w);
+          if (q.hot_kind == OLS_HOT_TAIL)
+            ((uint2*)q.hot)[i] = ols_hot_tail_pack(ols_meta_action(meta), tail.x, __float_as_int(tail.y), ols_meta_terminal(meta));
+          else
+            ((uint2*)q.hot)[i] = ols_hot_pack(p, ols_meta_action(meta), q.n_actions);
+        }
       }
     }
     if (diff) s_diff = 1;
@@ -375,8 +386,16 @@ inline int pack_hot(const ols_queues_t* q, cudaStream_t stream) {
     OLS_REQUIRE((uintptr_t)q->queue_dist % 32 == 0, OLS_ERR_INVALID, "queue_dist must be 32-byte aligned");
     if (q->const_info) OLS_CUDA_CHECK(cudaMemsetAsync(q->const_info, 0, sizeof(int32_t), stream));
     int blocks = q->n_buckets < OLS_SM_COUNT * 8 ? q->n_buckets : OLS_SM_COUNT * 8;
-    queue_dist_kernel<<<blocks, 256, 0, stream>>>(*q);
+    // queues of a few thousand records and more: one pass checks the distributions and writes the hot records
+    const bool fused = q->hot != nullptr && q->n_rows / q->n_buckets >= 1024;
+    if (fused) {
+      OLS_REQUIRE((uintptr_t)q->hot % 8 == 0, OLS_ERR_INVALID, "hot records must be 8-byte aligned");
+      queue_dist_kernel<true><<<blocks, 256, 0, stream>>>(*q);
+    } else {
+      queue_dist_kernel<false><<<blocks, 256, 0, stream>>>(*q);
+    }
     OLS_LAUNCH_CHECK();
+    if (fused) return OLS_OK;
   }
   if (q->hot) {
     OLS_REQUIRE(q->hot_kind != OLS_HOT_TAIL || q->queue_dist, OLS_ERR_INVALID, "OLS_HOT_TAIL needs queue_dist");
