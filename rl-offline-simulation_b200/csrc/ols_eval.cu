@@ -15,6 +15,9 @@ constexpr int kEvalThreads = 256;  // 8 replicas per CTA
 #ifndef OLS_EVAL_MINB
 #define OLS_EVAL_MINB 4
 #endif
+#ifndef OLS_EVAL_U
+#define OLS_EVAL_U 2  // 32-byte sectors per lane and round (measured: 1 -> 6.5 ms, 2 -> 6.1 ms, 4 -> 7.4+ ms on C5)
+#endif
 
 // The cold end of a lane's four slots: those whose high word fell inside the band are decided by the exact rule psrs.py:53-57 on
 // the queue's distribution and the policy row pi[S], in queue order; returns the lane's first accepting slot (4 = none).
@@ -34,6 +37,7 @@ __device__ __noinline__ int resolve_slots(const float* dist, const void* pi_row,
   return 4;
 }
 
+template <int U>
 __global__ void __launch_bounds__(kEvalThreads, OLS_EVAL_MINB) eval_kernel(ols_queues_t q, ols_replicas_t R, ols_run_t cfg, ols_philox_keys PK) {
   constexpr int NA = 4;
   __shared__ uint2 s_lim[kEvalThreads / 32][4];  // per replica and action: accept below .x / reject above .y (make_limits)
@@ -77,70 +81,144 @@ __global__ void __launch_bounds__(kEvalThreads, OLS_EVAL_MINB) eval_kernel(ols_q
       return pi_is_f64 ? __ldg((const double*)pi_tab + off + j) : (double)__ldg((const float*)pi_tab + off + j);
     };
     {
-      Policy<NA> P;
-      finish_policy<NA>(P, pn_fn, nA);
-      const float4 qd = __ldg((const float4*)q.queue_dist + 2 * (size_t)B.b);
+      // the step's limits (finish_policy + make_limits, same arithmetic), one action per lane: lane j & 3 holds action j
+      const int j = lane & 3;
+      const float pj = (j < nA) ? (float)pn_fn(j) : 0.f;
+      const bool okj = (j >= nA) || pj == 0.f || (pj >= 9.094947e-13f && pj <= 1.0f);
+      const float ipn = (pj == 0.f) ? __int_as_float(0x7f800000) : __frcp_rn(pj);  // +inf for pi = 0 and for padding entries
+      const float pq = __ldg(q.queue_dist + 8 * (size_t)B.b + j);
       const bool tame = (__ldg((const int*)q.queue_dist + 8 * (size_t)B.b + 4) & 2) != 0;
-      const float ipn4[4] = {P.ipn[0], P.ipn[1], P.ipn[2], P.ipn[3]};
-      uint2 lim[4];
-      make_limits(qd, P.ok && tame, ipn4, lim);
+      const bool ok = __all_sync(kFull, okj) && __any_sync(kFull, pj > 0.f) && tame;
+      const float t = pq * ipn;
+      float inv_m = fminf(t, __shfl_xor_sync(kFull, t, 1));   // (all t > 0 or +inf when ok: the order of the min is immaterial)
+      inv_m = fminf(inv_m, __shfl_xor_sync(kFull, inv_m, 2));
+      const float thr = __fdiv_rn(inv_m, t);
+      const float lo = __fmul_rd(thr, 4294836224.0f), hi = __fmul_ru(thr, 4295098368.0f);
+      const bool fine = ok && (thr == thr);
+      const unsigned lo32 = __float2uint_rd(lo), hi32 = __float2uint_ru(hi);
+      uint2 lim;
+      lim.x = !fine ? 0u : (lo32 > 2u ? lo32 - 2u : 0u);
+      lim.y = !fine ? 0xffffffffu : (hi32 < 0xfffffffdu ? hi32 + 2u : 0xffffffffu);
       __syncwarp();
-      if (lane < 4) s_lim[wib][lane] = lane == 0 ? lim[0] : lane == 1 ? lim[1] : lane == 2 ? lim[2] : lim[3];
+      if (lane < 4) s_lim[wib][lane] = lim;
       __syncwarp();
     }
-    // ---------------- env.step(p): pop rounds of 128 records until one is accepted (psrs.py:39-57)
+    // ---------------- env.step(p): pop rounds of 128 * U records until one is accepted (psrs.py:39-57)
+    // A round examines one CONTIGUOUS piece of the queue's ring, and its lanes are aligned to the MEMORY: lane L reads the
+    // 32-byte sectors (A + 4 (L + 32 u)) .. + 3, u < U, each with one 256-bit load (A = the round's first record rounded down to
+    // a sector).  The draws are aligned differently (record k of the round consumes draw `draws + k`, stream block
+    // (draws + k) >> 2), so a lane computes the block that starts inside its sector and takes the rest from its neighbour.
     uint2 won = make_uint2(0u, 0u);
-    int first_acc = -1;
     bool empty = false;
     for (;;) {
       const int remaining = B.len - B.cur;
       if (remaining <= 0) { empty = true; break; }  // psrs.py:44-45
-      const int align = (int)(draws & 3);           // rounds are aligned to four draws: one stream block per lane
-      const int n_eval = min(128 - align, remaining);
-      const int k0 = 4 * lane - align;
-      uint32_t pos = B.start + (uint32_t)(B.cur + k0);  // (k0 = -align..-1 only in lane 0: masked slots)
-      uint2 h[4];
+      uint32_t pos0 = B.start + (uint32_t)B.cur;    // ring position of the next record
+      if (pos0 >= (uint32_t)B.len) pos0 -= (uint32_t)B.len;
+      const uint32_t P = (uint32_t)B.lo + pos0;     // its index in the hot array
+      const int mis = (int)(P & 3u);
+      const long long D1 = (long long)draws - mis;  // the draw the sector's first record would consume (>= -3)
+      const int s = (int)(D1 & 3);                  // where the sectors start inside the stream blocks
+      // up to the ring's wrap, and as far as the lanes' blocks reach (the last lane has no neighbour)
+      const int n_eval = min(min(remaining, B.len - (int)pos0), 128 * U - mis - s);
+      const uint2* const base = hot + (size_t)(P - (uint32_t)mis);
+      uint2 h[U][4];
+      ols_u4 o[U];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint32_t p = pos + (uint32_t)i;
-        if (p >= (uint32_t)B.len) p -= (uint32_t)B.len;
-        h[i] = ((unsigned)(k0 + i) < (unsigned)n_eval) ? __ldg(hot + (size_t)(uint32_t)(B.lo + (int32_t)p)) : make_uint2(0u, 0u);
+      for (int u = 0; u < U; ++u) {
+        const int g = 4 * (lane + 32 * u);  // the sector's first record, relative to A
+        const int k0 = g - mis;             // ... relative to the round's first record
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[u][i] = make_uint2(0u, 0u);
+        if (k0 + 3 >= 0 && k0 < n_eval) {
+          if ((long long)(P - (uint32_t)mis) + g + 4 <= q.n_rows) {
+            asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(h[u][0].x), "=r"(h[u][0].y), "=r"(h[u][1].x), "=r"(h[u][1].y), "=r"(h[u][2].x), "=r"(h[u][2].y),
+                           "=r"(h[u][3].x), "=r"(h[u][3].y)
+                         : "l"(base + g));
+          } else {  // the array's last, partial sector
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if ((unsigned)(k0 + i) < (unsigned)n_eval) h[u][i] = __ldg(base + g + i);
+          }
+        }
       }
       if (pf_rounds > 0) {
         // the reject chains of this regime are hundreds of records long: pull the span a later round will examine toward L2
-        const int kp = k0 + pf_rounds * 128;
-        if (kp + 3 < remaining) {
-          uint32_t pp = B.start + (uint32_t)(B.cur + kp);
-          if (pp >= (uint32_t)B.len) pp -= (uint32_t)B.len;
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(hot + (size_t)(uint32_t)(B.lo + (int32_t)pp)));
+        const int gp = 4 * lane + pf_rounds * 128 * U;
+        if (gp - mis < min(remaining, B.len - (int)pos0)) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + gp));
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        o[u] = ols_stream_block(PK, rid, 0u, (uint64_t)((D1 >> 2) + (long long)(lane + 32 * u)));
+      int mine[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        uint32_t w0 = o[u].x, w1 = o[u].y, w2 = o[u].z, w3 = o[u].w;
+        if (s != 0) {  // warp-uniform
+          // the neighbour's block: lane L + 1's of the same u; for the last lane, lane 0's of the next u
+          uint32_t n0, n1, n2;
+          if (u + 1 < U) {
+            const ols_u4 nx = o[u + 1 < U ? u + 1 : u];
+            n0 = __shfl_sync(kFull, lane == 0 ? nx.x : o[u].x, (lane + 1) & 31);
+            n1 = __shfl_sync(kFull, lane == 0 ? nx.y : o[u].y, (lane + 1) & 31);
+            n2 = __shfl_sync(kFull, lane == 0 ? nx.z : o[u].z, (lane + 1) & 31);
+          } else {
+            n0 = __shfl_down_sync(kFull, o[u].x, 1);
+            n1 = __shfl_down_sync(kFull, o[u].y, 1);
+            n2 = __shfl_down_sync(kFull, o[u].z, 1);
+          }
+          if (s == 1) { w0 = o[u].y; w1 = o[u].z; w2 = o[u].w; w3 = n0; }
+          else if (s == 2) { w0 = o[u].z; w1 = o[u].w; w2 = n0; w3 = n1; }
+          else { w0 = o[u].w; w1 = n0; w2 = n1; w3 = n2; }
+        }
+        const uint32_t wv[4] = {w0, w1, w2, w3};
+        const int k0 = 4 * (lane + 32 * u) - mis;
+        // the common case first: is any of the four slots NOT plainly rejected?  (one 4-byte shared-memory load and two compares each)
+        bool some = false;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t ly = *(const uint32_t*)((const char*)&s_lim[wib][0] + ((h[u][i].y >> 26) & 0x18u) + 4);
+          some = some || ((unsigned)(k0 + i) < (unsigned)n_eval && wv[i] <= ly);
+        }
+        int m = 4;
+        if (some) {
+          // 2 bits per slot: 0 reject, 1 accept, 2 undecided (inside the band: 6e-5 of the pops)
+          unsigned decs = 0, acts = 0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const unsigned a = (h[u][i].y >> 29) & 3u;
+            const uint2 lm = s_lim[wib][a];
+            const uint32_t hi = wv[i];
+            const unsigned dec = ((unsigned)(k0 + i) >= (unsigned)n_eval || hi > lm.y) ? 0u : (hi < lm.x) ? 1u : 2u;
+            decs |= dec << (2 * i);
+            acts |= a << (2 * i);
+          }
+          m = decs ? (__ffs(decs) - 1) >> 1 : 4;  // the lane's first slot that is not a plain reject
+          if (m < 4 && ((decs >> (2 * m)) & 3u) == 2u) {
+            const void* pi_row = pi_is_f64 ? (const void*)((const double*)pi_tab + off) : (const void*)((const float*)pi_tab + off);
+            m = resolve_slots(q.queue_dist + 8 * (size_t)B.b, pi_row, pi_is_f64, ols_keys_seed(PK), rid, draws + (uint64_t)(int64_t)k0,
+                              decs, acts, nA, cfg.compute_mode);
+          }
+        }
+        mine[u] = m;
+      }
+      int first_acc = -1;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (first_acc >= 0) break;
+        const unsigned any = __ballot_sync(kFull, mine[u] < 4);
+        if (any) {
+          const int w = __ffs(any) - 1;
+          const int wi = __shfl_sync(kFull, mine[u], w);
+          const int m = mine[u];
+          const uint2 mw = (m == 0) ? h[u][0] : (m == 1) ? h[u][1] : (m == 2) ? h[u][2] : h[u][3];
+          won.x = __shfl_sync(kFull, mw.x, w);
+          won.y = __shfl_sync(kFull, mw.y, w);
+          first_acc = 4 * (w + 32 * u) + wi - mis;
         }
       }
-      const ols_u4 o = ols_stream_block(PK, rid, 0u, ((draws - (uint64_t)align) >> 2) + (uint64_t)lane);
-      // 2 bits per slot: 0 reject, 1 accept, 2 undecided (inside the band: 6e-5 of the pops)
-      unsigned decs = 0, acts = 0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const unsigned a = (h[i].y >> 29) & 3u;
-        const uint2 lm = s_lim[wib][a];
-        const uint32_t hi = ols_u4_word(o, i);
-        const unsigned dec = ((unsigned)(k0 + i) >= (unsigned)n_eval || hi > lm.y) ? 0u : (hi < lm.x) ? 1u : 2u;
-        decs |= dec << (2 * i);
-        acts |= a << (2 * i);
-      }
-      int mine = decs ? (__ffs(decs) - 1) >> 1 : 4;  // the lane's first slot that is not a plain reject
-      if (mine < 4 && ((decs >> (2 * mine)) & 3u) == 2u) {
-        const void* pi_row = pi_is_f64 ? (const void*)((const double*)pi_tab + off) : (const void*)((const float*)pi_tab + off);
-        mine = resolve_slots(q.queue_dist + 8 * (size_t)B.b, pi_row, pi_is_f64, ols_keys_seed(PK), rid, draws + (uint64_t)(int64_t)k0, decs,
-                             acts, nA, cfg.compute_mode);
-      }
-      const unsigned any = __ballot_sync(kFull, mine < 4);
-      if (any) {
-        const int w = __ffs(any) - 1;
-        const int wi = __shfl_sync(kFull, mine, w);
-        const uint2 mw = (mine == 0) ? h[0] : (mine == 1) ? h[1] : (mine == 2) ? h[2] : h[3];
-        won.x = __shfl_sync(kFull, mw.x, w);
-        won.y = __shfl_sync(kFull, mw.y, w);
-        first_acc = 4 * w + wi - align;
+      if (first_acc >= 0) {
         B.cur += first_acc + 1;
         draws += (uint64_t)(first_acc + 1);
         break;
@@ -218,7 +296,7 @@ __global__ void __launch_bounds__(kEvalThreads, OLS_EVAL_MINB) eval_kernel(ols_q
 cudaError_t ols_launch_eval(const ols_queues_t& q, const ols_replicas_t& r, const ols_run_t& c, cudaStream_t stream) {
   const int per = ols_sim::kEvalThreads / 32;
   const int grid = (int)((r.n_replicas + per - 1) / per);
-  ols_sim::eval_kernel<<<grid, ols_sim::kEvalThreads, 0, stream>>>(q, r, c, ols_philox_make_keys(r.seed));
+  ols_sim::eval_kernel<OLS_EVAL_U><<<grid, ols_sim::kEvalThreads, 0, stream>>>(q, r, c, ols_philox_make_keys(r.seed));
   ols_note_launch(1);
   return cudaGetLastError();
 }
