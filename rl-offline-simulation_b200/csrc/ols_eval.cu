@@ -40,7 +40,7 @@ __device__ __noinline__ int resolve_slots(const float* dist, const void* pi_row,
 template <int U>
 __global__ void __launch_bounds__(kEvalThreads, OLS_EVAL_MINB) eval_kernel(ols_queues_t q, ols_replicas_t R, ols_run_t cfg, ols_philox_keys PK) {
   constexpr int NA = 4;
-  __shared__ uint2 s_lim[kEvalThreads / 32][4];  // per replica and action: accept below .x / reject above .y (make_limits)
+  __shared__ __align__(32) uint2 s_lim[kEvalThreads / 32][4];  // per replica and action: accept below .x / reject above .y (make_limits)
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t r = (int64_t)blockIdx.x * (kEvalThreads / 32) + wib;
   if (r >= R.n_replicas) return;  // warp-uniform
@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(kEvalThreads, OLS_EVAL_MINB) eval_kernel(ols_q
   B.start = 0;
   bool bucket_valid = false;
   const int pf_rounds = cfg.prefetch;
+  const unsigned lim_y = (unsigned)__cvta_generic_to_shared(&s_lim[wib][0]) + 4u;  // + 8 a: the reject limit of action a (32-byte aligned row)
   for (;;) {
     // ---------------- episode start and the policy of the current state (psrs.py:246-255)
     if (!ep_open) {
@@ -124,19 +125,22 @@ __global__ void __launch_bounds__(kEvalThreads, OLS_EVAL_MINB) eval_kernel(ols_q
       const uint2* const base = hot + (size_t)(P - (uint32_t)mis);
       uint2 h[U][4];
       ols_u4 o[U];
+      bool sv[U];  // the lane's sector holds records of this round
+      const bool all_in = (long long)(P - (uint32_t)mis) + 128 * U <= q.n_rows;  // (warp-uniform) no sector runs past the array's end
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int g = 4 * (lane + 32 * u);  // the sector's first record, relative to A
         const int k0 = g - mis;             // ... relative to the round's first record
+        sv[u] = k0 + 3 >= 0 && k0 < n_eval;
 #pragma unroll
         for (int i = 0; i < 4; ++i) h[u][i] = make_uint2(0u, 0u);
-        if (k0 + 3 >= 0 && k0 < n_eval) {
-          if ((long long)(P - (uint32_t)mis) + g + 4 <= q.n_rows) {
+        if (sv[u]) {
+          if (all_in) {
             asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                          : "=r"(h[u][0].x), "=r"(h[u][0].y), "=r"(h[u][1].x), "=r"(h[u][1].y), "=r"(h[u][2].x), "=r"(h[u][2].y),
                            "=r"(h[u][3].x), "=r"(h[u][3].y)
                          : "l"(base + g));
-          } else {  // the array's last, partial sector
+          } else {  // near the array's end: record by record
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               if ((unsigned)(k0 + i) < (unsigned)n_eval) h[u][i] = __ldg(base + g + i);
@@ -145,8 +149,11 @@ __global__ void __launch_bounds__(kEvalThreads, OLS_EVAL_MINB) eval_kernel(ols_q
       }
       if (pf_rounds > 0) {
         // the reject chains of this regime are hundreds of records long: pull the span a later round will examine toward L2
-        const int gp = 4 * lane + pf_rounds * 128 * U;
-        if (gp - mis < min(remaining, B.len - (int)pos0)) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + gp));
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int gp = 4 * (lane + 32 * u) + pf_rounds * (128 * U - 4);
+          if (gp - mis < min(remaining, B.len - (int)pos0)) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + gp));
+        }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u)
@@ -174,13 +181,13 @@ __global__ void __launch_bounds__(kEvalThreads, OLS_EVAL_MINB) eval_kernel(ols_q
         }
         const uint32_t wv[4] = {w0, w1, w2, w3};
         const int k0 = 4 * (lane + 32 * u) - mis;
-        // the common case first: is any of the four slots NOT plainly rejected?  (one 4-byte shared-memory load and two compares each)
-        bool some = false;
+        // the common case first: is any of the four slots NOT plainly rejected?  One 4-byte shared-memory load (its address
+        // one shift and one and-or away from the record) and one compare each; slots outside the round are sorted out below.
+        uint32_t ly[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t ly = *(const uint32_t*)((const char*)&s_lim[wib][0] + ((h[u][i].y >> 26) & 0x18u) + 4);
-          some = some || ((unsigned)(k0 + i) < (unsigned)n_eval && wv[i] <= ly);
-        }
+        for (int i = 0; i < 4; ++i)
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ly[i]) : "r"(lim_y | ((h[u][i].y >> 26) & 0x18u)));
+        const bool some = sv[u] & ((wv[0] <= ly[0]) | (wv[1] <= ly[1]) | (wv[2] <= ly[2]) | (wv[3] <= ly[3]));
         int m = 4;
         if (some) {
           // 2 bits per slot: 0 reject, 1 accept, 2 undecided (inside the band: 6e-5 of the pops)
