@@ -373,7 +373,7 @@ def gather_stress_leg(ob, torch, dev, hbm_peak, launches=5, warm=3, hot="tail"):
     gbs = pops * log.rec_bytes / t / 1e9
     read_per_pop = 8 if hot else log.rec_bytes
     kind = {False: "2 full records of 32 bytes", True: "4 PROBS hot records of 8 bytes", "probs": "4 PROBS hot records of 8 bytes",
-            "tail": "4 TAIL hot records of 8 bytes"}[hot]
+            "tail": "8 TAIL hot records of 8 bytes (two 32-byte sectors)"}[hot]
     tr = load_traffic().get("c5_" + ("tail" if hot == "tail" else "probs" if hot else "full"), {})
     return {"workload": "c5: " + wl["desc"],
             "kernel": ("eval_kernel (streaming fixed-policy evaluation, one warp per replica x %s per lane and round)" if hot == "tail"

@@ -4,9 +4,10 @@
 // for statement, as run_kernel<1, FIXED_PI, float, PHILOX, 4, AOS = 0, GT = 0, HOT = 2> with lanes = 32 (the tests compare
 // both with oracle/ols_oracle.c draw for draw); what differs is that everything but the per-record decision is
 // warp-uniform here: no lane groups, no shared-memory replica block, no phased reads and writes — a pop round is
-//     4 x LDG.64 (the lane's four consecutive 8-byte records)  +  one Philox4x32-7 block (the high words of its four draws)
-//     +  4 x { action -> limits (one LDS.64), two integer compares }  +  one ballot / two shuffles
-// for 128 records, i.e. about one warp-instruction per popped record: the loop is bound by the 8 bytes per record it reads.
+//     U x one 256-bit load (the lane's 32-byte sectors, four 8-byte records each)  +  U Philox4x32-7 blocks (the high words of its
+//     draws; the words that belong to the neighbour's sector travel by shuffle)  +  per record { action -> reject limit (one
+//     LDS.32), one compare }  +  one ballot per sector row
+// for 128 U records: 1.7 warp-instructions per popped record at U = 2 (profiles/r04g_ncu_eval_kernel_c5.txt).
 #include "ols_sim_kernels.cuh"
 
 namespace ols_sim {
