@@ -1,8 +1,10 @@
 """Map an ncu report's per-SASS-instruction counts to source lines using nvdisasm line info of the matching .so."""
 import csv, re, collections, subprocess, sys, os
-rep, so, kernel_substr = sys.argv[1], sys.argv[2], sys.argv[3]
+rep, so, kernel_substr = os.path.abspath(sys.argv[1]), os.path.abspath(sys.argv[2]), sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 45
 ELF = "/tmp/ols_elf"; os.makedirs(ELF, exist_ok=True)
+for f in os.listdir(ELF):          # (stale cubins of another build would be matched by name)
+    os.remove(os.path.join(ELF, f))
 subprocess.run(f"cd {ELF} && cuobjdump -xelf all {so} > /dev/null 2>&1", shell=True)
 src_csv = subprocess.run(f"ncu -i {rep} --page source --csv", shell=True, capture_output=True, text=True).stdout
 rows = list(csv.reader(src_csv.splitlines()))
