@@ -307,6 +307,12 @@ static void run_replica(const oracle_sim_t* S, int64_t r, int32_t* cursor) {
       disc = disc * S->gamma;
       ++t;
       ++steps;
+      if (!done) {
+        /* The accepted transition leads to a state without a queue: the reference's NEXT env.step raises KeyError (psrs.py:44)
+         * and the whole run is lost; the replica ends here (committed transition, nothing appended), whatever the budget says. */
+        const int b2 = cz + S->z_offset;
+        if (b2 < 0 || b2 >= S->n_buckets || S->offsets[b2 + 1] == S->offsets[b2]) { status = ST_NO_QUEUE; break; }
+      }
       if (S->max_steps > 0 && steps >= S->max_steps) { budget_hit = 1; break; }
     }
     if (status == ST_NO_QUEUE || status == ST_FEED_EMPTY) break;          /* error: nothing is appended */

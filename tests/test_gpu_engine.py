@@ -869,6 +869,61 @@ def test_hot_records_never_change_a_run(ob, agent, lanes, ring, seeded):
     assert int(a.accepted.sum()) > 0.5 * R * 400
 
 
+@pytest.mark.parametrize("ring", [True, False])
+@pytest.mark.parametrize("N,nS", [(100003, 400), (4099, 37)])
+def test_streaming_evaluator_matches_c_oracle_on_ragged_queues(ob, ring, N, nS):
+    """eval_kernel (one warp per replica over TAIL hot records; rounds aligned to the 32-byte sectors of the hot array, stream
+    words aligned to blocks of four draws) on the geometry that stresses that alignment: Zipf-distributed queue lengths from one
+    record to thousands, a row count that is not a multiple of four (the array's last sector is partial), ring offsets that
+    wrap inside a sector, long reject chains that exhaust queues in mid-episode, resumed launches — against
+    oracle/ols_oracle.c draw for draw."""
+    import torch
+    from oracle import c_oracle as CO
+    from offsim4rl_b200 import _abi as abi
+    rng = np.random.default_rng(N)
+    w = 1.0 / np.arange(1, nS + 1) ** 1.8
+    w /= w.sum()
+    g = make_log(101, N, nS, 4, ep_len=15)
+    g["z"] = rng.choice(nS, size=N, p=w).astype(np.int64)
+    g["z_next"] = rng.choice(nS, size=N, p=w).astype(np.int64)
+    d = 1e-2
+    pb = np.full((nS, 4), d / 3, dtype=np.float32)
+    pb[np.arange(nS), rng.integers(0, 4, nS)] = 1 - d
+    g["p_log"] = pb[g["z"]]
+    g["a"] = (rng.random(N)[:, None] > np.cumsum(pb[g["z"]], 1)).sum(1).clip(0, 3).astype(np.int64)
+    pi = np.full((nS, 4), 0.25)
+    pi[::5] = [0.7, 0.1, 0.1, 0.1]
+    pi[3::11] = [0.0, 0.5, 0.5, 0.0]                                   # exact zeros: thr = 0 for two actions
+    R = 1200
+    log = device_log(ob, g, n_buckets=nS, hot_records="tail")
+    assert log.hot_kind == abi.HOT_TAIL
+    lens = np.bincount(g["z"], minlength=nS)
+    assert lens[lens > 0].min() <= 3 and lens.max() > 300 and N % 4 != 0
+    sim = ob.BatchedPSRS(log, R, rng="philox", seed=2024, ring=ring, ring_seed=11, replica_id0=7 * 10**5, lanes=32)
+    res = None
+    for budget in (7, 40):                                             # the second launch resumes in mid-episode
+        res = sim.run_evalmc(nS, 63, pi=pi, gamma=0.97, max_steps=budget, ep_cap=64, trace_cap=47, outputs=res)
+    clog = CO.Log(z=g["z"], z_next=g["z_next"], action=g["a"], reward=g["r"], terminal=g["done"], p_log=g["p_log"],
+                  steps=g["t"], n_buckets=nS)
+    ref = CO.run(clog, R, CO.FIXED_PI, nS, 63, gamma=0.97, pi=pi, seed=2024, replica_id0=7 * 10**5, ring=ring, ring_seed=11,
+                 max_steps=47, ep_cap=64, trace_cap=47, threads=8)
+    assert np.array_equal(res.accepted.cpu().numpy(), ref["accepted"])
+    assert np.array_equal(res.pops.cpu().numpy(), ref["pops"]) and np.array_equal(sim.draws.cpu().numpy(), ref["draws"])
+    st_gpu, st_ref = res.status.cpu().numpy(), ref["status"]
+    bad = np.flatnonzero(st_gpu != st_ref)
+    assert bad.size == 0, (bad[:10], st_gpu[bad[:10]], st_ref[bad[:10]], ref["accepted"][bad[:10]], sim.cur_z.cpu().numpy()[bad[:10]])
+    assert np.array_equal(res.trace_row.cpu().numpy(), ref["trace_row"])                 # bit-exact accepted rows
+    assert np.array_equal(res.n_returns.cpu().numpy(), ref["n_returns"])
+    nl = ref["n_lengths"]
+    assert np.array_equal(res.n_lengths.cpu().numpy(), nl)
+    mask = np.arange(64)[None, :] < nl[:, None]
+    assert np.array_equal(res.lengths.cpu().numpy()[mask], ref["lengths"][mask])
+    mask = np.arange(64)[None, :] < ref["n_returns"][:, None]
+    np.testing.assert_allclose(res.Gs.cpu().numpy()[mask], ref["Gs"][mask], rtol=1e-12, atol=1e-12)
+    st = ref["status"]
+    assert (st == abi.QUEUE_EMPTY).sum() > 0 and int(ref["pops"].sum()) > 10 * int(ref["accepted"].sum())
+
+
 @pytest.mark.parametrize("lanes,ring,seeded,pi_dtype", [(32, True, None, np.float64), (8, False, 4, np.float32), (2, True, None, np.float64),
                                                         (16, True, 7, np.float32)])
 def test_hot_records_never_change_an_evaluation(ob, lanes, ring, seeded, pi_dtype):

@@ -169,3 +169,26 @@ def test_c_mlp_equals_python_fma_emulation(golden):
     for tag in ["mlp_grid", "mlp_cart", "mlp_wide"]:
         x, W1, b1, W2, b2 = (g[f"{tag}_{k}"] for k in ["x", "W1", "b1", "W2", "b2"])
         assert np.array_equal(CO.mlp_ids(x, W1, b1, W2, b2), O.mlp_ids(x, W1, b1, W2, b2))
+
+
+def test_c_transition_into_a_state_without_queue_ends_the_replica_at_once():
+    """psrs.py:44: `self.queues[self.z]` raises KeyError on the step AFTER a transition into a state that was never logged as
+    a from-state, and the reference's whole run is lost.  The restatement (like the device kernels) ends the replica at the
+    transition itself: committed and counted, nothing appended, and the same whether or not a step budget ends there too."""
+    # state 0 -> state 1 (logged, two rows) -> state 2 (never a from-state); all rows initial, uniform behaviour and target
+    z = np.array([0, 1, 1], dtype=np.int64)
+    zn = np.array([1, 2, 2], dtype=np.int64)
+    a = np.zeros(3, dtype=np.int64)
+    r = np.array([1.0, 2.0, 3.0], dtype=np.float32)
+    done = np.zeros(3, dtype=bool)
+    p = np.full((3, 2), 0.5, dtype=np.float32)
+    log = CO.Log(z=z, z_next=zn, action=a, reward=r, terminal=done, p_log=p, steps=np.array([0, 1, 2]), n_buckets=3)
+    pi = np.full((3, 2), 0.5)
+    U = np.zeros((1, 16))                                   # u = 0 accepts every pop
+    for budget in (0, 2, 5):
+        out = CO.run(log, 1, CO.FIXED_PI, 3, 4, gamma=1.0, pi=pi, u_feed=U, trace_cap=8, max_steps=budget, ep_cap=4, threads=1)
+        assert out["status"][0] == 4                        # NO_QUEUE
+        assert out["accepted"][0] == 2 and list(out["trace_row"][0, :2]) == [0, 1]
+        assert out["n_returns"][0] == 0 and out["n_lengths"][0] == 0
+    out = CO.run(log, 1, CO.FIXED_PI, 3, 4, gamma=1.0, pi=pi, u_feed=U, trace_cap=8, max_steps=1, ep_cap=4, threads=1)
+    assert out["status"][0] == 0 and out["accepted"][0] == 1    # the budget ended the run one step earlier: RUNNING
