@@ -46,7 +46,11 @@ enum {
   OLS_DONE = 1,           /* a fused driver reached n_episodes (psrs.py:149)                       */
   OLS_QUEUE_EMPTY = 2,    /* psrs.py:44-45 — step() returned (None,)*4: the state's queue ran dry  */
   OLS_INIT_EMPTY = 3,     /* psrs.py:33-35 — reset() returned None: no initial state left          */
-  OLS_NO_QUEUE = 4,       /* psrs.py:44 raises KeyError — state never logged as a from-state       */
+  OLS_NO_QUEUE = 4,       /* psrs.py:44 raises KeyError — state never logged as a from-state.  The fused
+                             drivers set it AT the accepted transition that leads into such a state (the
+                             transition is committed and counted, no episode is appended, a step budget
+                             ending on the same transition does not hide it); the reference would raise
+                             on its next env.step and lose the whole run                               */
   OLS_FEED_EMPTY = 5,     /* harness-fed uniform / tie stream exhausted (parity mode only)         */
   OLS_IDLE = 6            /* fresh replica: reset() has not been called yet                        */
 };
