@@ -869,6 +869,54 @@ def test_hot_records_never_change_a_run(ob, agent, lanes, ring, seeded):
     assert int(a.accepted.sum()) > 0.5 * R * 400
 
 
+@pytest.mark.parametrize("lanes,aos,hot,slices", [(1, True, "tail", 4), (1, True, True, 0), (4, False, False, 0), (32, True, "tail", 3)])
+def test_float32_learner_matches_c_oracle_on_ragged_queues(ob, lanes, aos, hot, slices):
+    """The learners on a log with Zipf-distributed queue lengths (one record to tens of thousands), states that were never
+    logged as from-states (the reference's KeyError: OLS_NO_QUEUE at the transition that leads there) and queues that run
+    dry in mid-episode (partial returns are appended, psrs.py:160-162,177) — every counter, status, row, return and Q table
+    against oracle/ols_oracle.c in its float32-learner mode."""
+    import torch
+    from oracle import c_oracle as CO
+    from offsim4rl_b200 import _abi as abi
+    N, nS, R, budget = 100003, 400, 1500, 300
+    rng = np.random.default_rng(5)
+    w = 1.0 / np.arange(1, nS + 1) ** 1.8
+    w /= w.sum()
+    g = make_log(102, N, nS, 4, ep_len=15)
+    z = rng.choice(nS, size=N, p=w).astype(np.int64)
+    pb = rng.dirichlet(np.ones(4), size=nS).clip(0.05)
+    pb = (pb / pb.sum(1, keepdims=True)).astype(np.float32)                    # one logged distribution per state
+    g["z"], g["z_next"] = z, rng.choice(nS, size=N, p=w).astype(np.int64)
+    g["p_log"] = pb[z]
+    g["a"] = (rng.random(N)[:, None] > np.cumsum(pb[z].astype(np.float64), 1)).sum(1).clip(0, 3).astype(np.int64)
+    log = device_log(ob, g, n_buckets=nS, hot_records=hot)
+    assert hot != "tail" or log.hot_kind == abi.HOT_TAIL
+    sim = ob.BatchedPSRS(log, R, rng="philox", seed=313, ring=True, ring_seed=17, replica_id0=3 * 10**5, lanes=lanes,
+                         aos_state=aos, slices=slices)
+    res = sim.run_qlearn(nS, 255, gamma=0.99, alpha=0.1, epsilon=0.1, q_dtype=torch.float32, max_steps=budget, ep_cap=256,
+                         trace_cap=budget)
+    clog = CO.Log(z=g["z"], z_next=g["z_next"], action=g["a"], reward=g["r"], terminal=g["done"], p_log=g["p_log"],
+                  steps=g["t"], n_buckets=nS)
+    ref = CO.run(clog, R, CO.QLEARN, nS, 255, gamma=0.99, alpha=0.1, epsilon=0.1, seed=313, replica_id0=3 * 10**5, ring=True,
+                 ring_seed=17, max_steps=budget, ep_cap=256, trace_cap=budget, threads=16, q_f32=True)
+    assert np.array_equal(res.accepted.cpu().numpy(), ref["accepted"])
+    assert np.array_equal(res.pops.cpu().numpy(), ref["pops"]) and np.array_equal(sim.draws.cpu().numpy(), ref["draws"])
+    st_gpu, st_ref = res.status.cpu().numpy(), ref["status"]
+    bad = np.flatnonzero(st_gpu != st_ref)
+    assert bad.size == 0, (bad[:10], st_gpu[bad[:10]], st_ref[bad[:10]], ref["accepted"][bad[:10]])
+    assert np.array_equal(sim.ties.cpu().numpy(), ref["ties"])
+    assert np.array_equal(res.trace_row.cpu().numpy(), ref["trace_row"])
+    assert np.array_equal(res.n_returns.cpu().numpy(), ref["n_returns"])
+    nl = ref["n_lengths"]
+    assert np.array_equal(res.n_lengths.cpu().numpy(), nl)
+    mask = np.arange(256)[None, :] < nl[:, None]
+    assert np.array_equal(res.lengths.cpu().numpy()[mask], ref["lengths"][mask])
+    mask = np.arange(256)[None, :] < ref["n_returns"][:, None]
+    np.testing.assert_allclose(res.Gs.cpu().numpy()[mask], ref["Gs"][mask], rtol=1e-12, atol=1e-12)
+    assert np.array_equal(res.Q.cpu().numpy(), ref["Q"])
+    assert (st_ref == abi.NO_QUEUE).sum() > 0 and (st_ref == abi.QUEUE_EMPTY).sum() > 0 and (st_ref == abi.RUNNING).sum() > 0
+
+
 @pytest.mark.parametrize("ring", [True, False])
 @pytest.mark.parametrize("N,nS", [(100003, 400), (4099, 37)])
 def test_streaming_evaluator_matches_c_oracle_on_ragged_queues(ob, ring, N, nS):
