@@ -869,6 +869,86 @@ def test_hot_records_never_change_a_run(ob, agent, lanes, ring, seeded):
     assert int(a.accepted.sum()) > 0.5 * R * 400
 
 
+def _fuzz_config(k):
+    rng = np.random.default_rng(1000 + k)
+    pick = lambda xs: xs[int(rng.integers(0, len(xs)))]
+    c = dict(nA=pick([2, 3, 4, 4, 4, 5]), nS=pick([1, 2, 5, 17, 64]), N=pick([1, 2, 3, 5, 37, 300, 5001, 20011]), skew=bool(rng.integers(0, 2)),
+             ep_len=pick([3, 10]), near_det=bool(rng.integers(0, 3) == 0), agent=pick(["qlearn32", "qlearn32", "qlearn64", "evalmc", "expsarsa32"]),
+             lanes=pick([1, 1, 2, 4, 8, 32]), hot=pick([False, True, "tail", "tail"]), aos=bool(rng.integers(0, 2)), slices=pick([0, 0, 3]),
+             ring=bool(rng.integers(0, 2)), budget=pick([0, 5, 40]), R=pick([1, 33, 200]), seed=int(rng.integers(0, 2**40)),
+             pi_zeros=bool(rng.integers(0, 3) == 0))
+    if c["agent"] in ("qlearn64", "evalmc"):
+        c["aos"] = False                      # the AoS table holds float32 Q rows of a learner
+    if c["budget"] == 0:
+        c["slices"] = 0                       # time slices hand out a budget
+    if c["nA"] > 4:
+        c["hot"], c["aos"] = False, False     # hot records and the AoS table are built for <= 4 actions
+    return c
+
+
+@pytest.mark.parametrize("k", range(240))
+def test_randomized_small_configurations_match_c_oracle(ob, k):
+    """Differential fuzzing of the fused drivers against oracle/ols_oracle.c over small random shapes: 1-20011 rows, 1-64 states,
+    2-4 actions, every lane-group width, hot-record kind, state layout, slicing, ring and budget setting the API accepts."""
+    import torch
+    from oracle import c_oracle as CO
+    c = _fuzz_config(k)
+    nA, nS, N, R = c["nA"], c["nS"], c["N"], c["R"]
+    rng = np.random.default_rng(c["seed"] % 2**32)
+    g = make_log(int(c["seed"] % 1000), N, nS, nA, ep_len=c["ep_len"], skew=c["skew"])
+    if c["near_det"]:
+        pb = np.full((nS, nA), 0.02 / (nA - 1), dtype=np.float32)
+        pb[np.arange(nS), rng.integers(0, nA, nS)] = 0.98
+        g["p_log"] = pb[g["z"]]
+        g["a"] = (rng.random(N)[:, None] > np.cumsum(pb[g["z"]].astype(np.float64), 1)).sum(1).clip(0, nA - 1).astype(np.int64)
+    pi = rng.dirichlet(np.ones(nA), size=nS)
+    if c["pi_zeros"]:                         # exact zeros in the target policy: thr = 0 for those actions
+        pi[::2, 0] = 0.0
+        pi /= pi.sum(1, keepdims=True)
+    n_ep, ep_cap, cap = 20, 32, 64
+    try:
+        log = device_log(ob, g, n_buckets=nS, hot_records=c["hot"])
+        sim = ob.BatchedPSRS(log, R, rng="philox", seed=c["seed"], ring=c["ring"], ring_seed=3, replica_id0=12345, lanes=c["lanes"],
+                             aos_state=c["aos"], slices=c["slices"])
+        kw = dict(gamma=0.95, max_steps=c["budget"], ep_cap=ep_cap, trace_cap=cap)
+        if c["agent"].startswith("qlearn"):
+            qd = torch.float32 if c["agent"].endswith("32") else torch.float64
+            res = sim.run_qlearn(nS, n_ep, alpha=0.2, epsilon=0.15, q_dtype=qd, **kw)
+        elif c["agent"] == "evalmc":
+            res = sim.run_evalmc(nS, n_ep, pi=pi, **kw)
+        else:
+            res = sim.run_expsarsa(nS, n_ep, pi=pi, alpha=0.2, q_dtype=torch.float32, **kw)
+    except (ValueError, RuntimeError) as e:
+        if "CUDA" in str(e) or "cuda" in str(e):
+            raise
+        pytest.skip("combination refused by the API: %s" % str(e)[:80])
+    clog = CO.Log(z=g["z"], z_next=g["z_next"], action=g["a"], reward=g["r"], terminal=g["done"], p_log=g["p_log"],
+                  steps=g["t"], n_buckets=nS)
+    okw = dict(gamma=0.95, seed=c["seed"], replica_id0=12345, ring=c["ring"], ring_seed=3, max_steps=c["budget"], ep_cap=ep_cap,
+               trace_cap=cap, threads=4)
+    if c["agent"].startswith("qlearn"):
+        ref = CO.run(clog, R, CO.QLEARN, nS, n_ep, alpha=0.2, epsilon=0.15, q_f32=c["agent"].endswith("32"), **okw)
+    elif c["agent"] == "evalmc":
+        ref = CO.run(clog, R, CO.FIXED_PI, nS, n_ep, pi=pi, **okw)
+    else:
+        ref = CO.run(clog, R, CO.EXPSARSA, nS, n_ep, pi=pi, alpha=0.2, q_f32=True, **okw)
+    tag = str(c)
+    for name, got in (("accepted", res.accepted), ("pops", res.pops), ("draws", sim.draws), ("status", res.status),
+                      ("n_returns", res.n_returns), ("n_lengths", res.n_lengths)):
+        assert np.array_equal(got.cpu().numpy(), ref[name]), (name, tag)
+    if c["agent"] != "evalmc":
+        assert np.array_equal(sim.ties.cpu().numpy(), ref["ties"]), ("ties", tag)
+    n_tr = np.minimum(ref["accepted"], cap)
+    mask = np.arange(cap)[None, :] < n_tr[:, None]
+    assert np.array_equal(res.trace_row.cpu().numpy()[mask], ref["trace_row"][mask]), ("trace", tag)
+    mask = np.arange(ep_cap)[None, :] < np.minimum(ref["n_lengths"], ep_cap)[:, None]
+    assert np.array_equal(res.lengths.cpu().numpy()[mask], ref["lengths"][mask]), ("lengths", tag)
+    mask = np.arange(ep_cap)[None, :] < np.minimum(ref["n_returns"], ep_cap)[:, None]
+    np.testing.assert_allclose(res.Gs.cpu().numpy()[mask], ref["Gs"][mask], rtol=1e-12, atol=1e-12, err_msg=tag)
+    if c["agent"] != "evalmc":
+        assert np.array_equal(res.Q.cpu().numpy(), ref["Q"]), ("Q", tag)
+
+
 @pytest.mark.parametrize("lanes,aos,hot,slices", [(1, True, "tail", 4), (1, True, True, 0), (4, False, False, 0), (32, True, "tail", 3)])
 def test_float32_learner_matches_c_oracle_on_ragged_queues(ob, lanes, aos, hot, slices):
     """The learners on a log with Zipf-distributed queue lengths (one record to tens of thousands), states that were never
