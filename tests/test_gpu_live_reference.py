@@ -271,3 +271,44 @@ def test_fused_psrs_exo_evaluation_equals_the_live_reference(ob, ref, k):
         assert ne == want["Gs"].size and nl == want["lengths"].size, c
         assert np.array_equal(res.lengths[r, :nl].cpu().numpy(), want["lengths"]), c
         np.testing.assert_allclose(res.Gs[r, :ne].cpu().numpy(), want["Gs"], rtol=1e-5, atol=1e-5, err_msg=str(c))
+
+
+# ------------------------------------------------------------------------------------------ the scalar API (psrs.py:5-57)
+@pytest.mark.parametrize("k", range(20))
+def test_scalar_psrs_walk_equals_the_live_reference(ob, ref, k):
+    """`offsim4rl_b200.evaluators.psrs.PSRS` next to the reference's `PSRS` on the same legacy tuples: reset_sampler(seed),
+    then reset / step with a fresh random distribution at every step until the initial states or a queue run out — every
+    return value compared (agent-visible ids distinct from the state ids, psrs.py:36,49-50)."""
+    from offsim4rl_b200.evaluators.psrs import PSRS
+    ref_psrs, _ = ref
+    rng = np.random.default_rng(11000 + k)
+    pick = lambda xs: xs[int(rng.integers(0, len(xs)))]
+    nA, nS = pick([2, 3, 5]), pick([1, 4, 11])
+    N = max(pick([3, 40, 300]), nS)
+    g = random_log(rng, N, nS, nA, pick([np.float32, np.float64]))
+    seed = int(rng.integers(0, 2**31))
+
+    def tuples():
+        return [(int(g["z"][i]) * 7 + 3, g["a"][i], g["r"][i], int(g["z_next"][i]) * 7 + 3, bool(g["done"][i]), np.array(g["p_log"][i], copy=True),
+                 {"z": int(g["z"][i]), "z_next": int(g["z_next"][i]), "t": int(g["t"][i])}) for i in range(N)]
+    a, b = ref_psrs.PSRS(tuples(), nS=nS, nA=nA), PSRS(tuples(), nS=nS, nA=nA)
+    a.reset_sampler(seed=seed)
+    b.reset_sampler(seed=seed)
+    sa, sb = a.reset(), b.reset()
+    steps = 0
+    while True:
+        assert sa == sb
+        if sa is None:
+            break
+        p = rng.dirichlet(np.ones(nA))
+        oa, ob_ = a.step(p), b.step(p)
+        steps += 1
+        if oa[0] is None:
+            assert ob_[0] is None and ob_ == (None, None, None, None)
+            break
+        assert oa[0] == ob_[0] and oa[1] == ob_[1] and bool(oa[2]) == bool(ob_[2])
+        assert oa[3]["z"] == ob_[3]["z"] and oa[3]["a"] == ob_[3]["a"] and np.array_equal(oa[3]["p"], ob_[3]["p"])
+        sa, sb = oa[0], ob_[0]
+        if oa[2]:
+            sa, sb = a.reset(), b.reset()
+    assert steps > 0
