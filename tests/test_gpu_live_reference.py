@@ -312,3 +312,97 @@ def test_scalar_psrs_walk_equals_the_live_reference(ob, ref, k):
         if oa[2]:
             sa, sb = a.reset(), b.reset()
     assert steps > 0
+
+
+# ------------------------------------------------------------------------------------------ QueueEvaluator (queue_evaluator.py:90-131)
+@pytest.fixture(scope="module")
+def ref_queue_impl():
+    """The reference's QueueEvaluator_impl.  Its module imports gym and two package modules at the top for the wrapper class
+    next to it; empty stand-ins satisfy those imports (the impl class itself uses numpy and itertools only)."""
+    import sys
+    import types
+    path = os.path.join(REF_DIR, "evaluators", "queue_evaluator.py")
+    if not os.path.exists(path):
+        pytest.skip("baseline/_ref has no evaluators/queue_evaluator.py (re-run __graft_entry__.build() where /root/reference exists)")
+    stubs = {"gym": types.ModuleType("gym"), "offsim4rl": types.ModuleType("offsim4rl"), "offsim4rl.core": types.ModuleType("offsim4rl.core"),
+             "offsim4rl.data": types.ModuleType("offsim4rl.data")}
+    stubs["gym"].spaces = types.SimpleNamespace(Discrete=type("Discrete", (), {}))
+    stubs["offsim4rl.core"].RevealedRandomnessEnv = type("RevealedRandomnessEnv", (), {})
+    stubs["offsim4rl.data"].OfflineDataset = type("OfflineDataset", (), {})
+    saved = {k: sys.modules.get(k) for k in stubs}
+    sys.modules.update(stubs)
+    try:
+        spec = importlib.util.spec_from_file_location("offsim4rl_live_queue_evaluator", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod.QueueEvaluator_impl
+
+
+@pytest.mark.parametrize("k", range(20))
+def test_queue_evaluator_equals_the_live_reference(ob, ref_queue_impl, k):
+    """The reference's QueueEvaluator_impl, the package's scalar class and the fused BatchedPSRS.run_actions on the same random
+    log, sampler seed and action sequence: every return value of the scalar walk, the served rows, lengths and returns of the
+    fused run."""
+    from offsim4rl_b200.evaluators.queue_evaluator import QueueEvaluator_impl
+    from offsim4rl_b200 import _abi as abi
+    rng = np.random.default_rng(13000 + k)
+    pick = lambda xs: xs[int(rng.integers(0, len(xs)))]
+    nA, nS = pick([2, 3, 4]), pick([1, 4, 9])
+    N = max(pick([30, 200, 1200]), nS * nA)
+    g = random_log(rng, N, nS, nA, np.float32)
+    cover = rng.permutation(N)[:nS * nA]                     # every (z, a) pair has a queue: the reference raises KeyError otherwise
+    g["z"][cover], g["a"][cover] = np.repeat(np.arange(nS), nA), np.tile(np.arange(nA), nS)
+    seed = int(rng.integers(0, 2**31))
+    acts = rng.integers(0, nA, 4 * N)
+
+    def tuples():
+        return [(int(g["z"][i]) * 5 + 1, int(g["a"][i]), g["r"][i], int(g["z_next"][i]) * 5 + 1, bool(g["done"][i]), np.array(g["p_log"][i], copy=True),
+                 {"z": int(g["z"][i]), "next_z": int(g["z_next"][i]), "t": int(g["t"][i])}) for i in range(N)]
+    rows = tuples()
+    id2row = {id(r[5]): i for i, r in enumerate(rows)}
+    a, b = ref_queue_impl(rows, nS=nS, nA=nA), QueueEvaluator_impl(tuples(), nS=nS, nA=nA)
+    a.reset_sampler(seed=seed)
+    b.reset_sampler(seed=seed)
+    trace, lens, Gs, n_act = [], [], [], 0
+    sa, sb = a.reset(), b.reset()
+    G, t = 0.0, 0
+    while True:
+        assert sa == sb
+        if sa is None:
+            break
+        act = int(acts[n_act]); n_act += 1
+        oa, ob_ = a.step(act), b.step(act)
+        if oa[0] is None:
+            assert ob_ == (None, None, None, None)
+            lens.append(t)                                   # (an episode cut short: evalMC-style bookkeeping keeps the length only)
+            break
+        assert oa[0] == ob_[0] and oa[1] == ob_[1] and bool(oa[2]) == bool(ob_[2])
+        assert oa[3]["z"] == ob_[3]["z"] and oa[3]["next_z"] == ob_[3]["next_z"] and oa[3]["a"] == ob_[3]["a"]
+        assert np.array_equal(oa[3]["p"], ob_[3]["p"])
+        trace.append(id2row[id(oa[3]["p"])])
+        G += 0.9 ** t * float(oa[1]); t += 1
+        sa, sb = oa[0], ob_[0]
+        if oa[2]:
+            lens.append(t); Gs.append(G)
+            G, t = 0.0, 0
+            sa, sb = a.reset(), b.reset()
+    # ---- the fused run: one launch for the whole walk
+    log = ob.BucketedLog(z=g["z"], z_next=g["z_next"], action=g["a"], reward=g["r"], terminal=g["done"], p_log=g["p_log"], steps=g["t"],
+                         n_buckets=nS, key_by_action=True).seeded(seed)
+    sim = ob.BatchedPSRS(log, 2, rng="philox", seed=1, reject="accept_all")
+    res = sim.run_actions(N, gamma=0.9, actions=acts, trace_cap=N, ep_cap=N + 1)
+    for r in range(2):
+        n = int(res.accepted[r])
+        assert n == len(trace) and np.array_equal(res.trace_row[r, :n].cpu().numpy(), np.array(trace, dtype=np.int64))
+        assert int(sim.ties[r]) == n_act
+        assert int(res.status[r]) in (abi.QUEUE_EMPTY, abi.INIT_EMPTY)
+        ne, nl = int(res.n_returns[r]), int(res.n_lengths[r])
+        assert ne == len(Gs) and nl == len(lens)
+        assert np.array_equal(res.lengths[r, :nl].cpu().numpy(), np.array(lens))
+        np.testing.assert_allclose(res.Gs[r, :ne].cpu().numpy(), np.array(Gs), rtol=1e-12, atol=1e-12)
