@@ -406,3 +406,39 @@ def test_queue_evaluator_equals_the_live_reference(ob, ref_queue_impl, k):
         assert ne == len(Gs) and nl == len(lens)
         assert np.array_equal(res.lengths[r, :nl].cpu().numpy(), np.array(lens))
         np.testing.assert_allclose(res.Gs[r, :ne].cpu().numpy(), np.array(Gs), rtol=1e-12, atol=1e-12)
+
+
+# ------------------------------------------------------------------------------------------ CartpoleBoxEncoder (heuristic.py:10-71)
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_cartpole_box_encoder_equals_the_live_reference(ob, dtype):
+    """ols_encode_cartpole_box against the reference's own `get_box` loop, in float32 and float64 observations: 20000 random
+    rows over (and beyond) the encoder's range plus every threshold constant, its float32 image and their neighbours on either
+    side in both precisions (comparisons run in the observation dtype, NumPy >= 2 semantics: SURVEY A.9)."""
+    from offsim4rl_b200.encoders import CartpoleBoxEncoder
+    path = os.path.join(REF_DIR, "encoders", "heuristic.py")
+    if not os.path.exists(path):
+        pytest.skip("baseline/_ref has no encoders/heuristic.py (re-run __graft_entry__.build() where /root/reference exists)")
+    spec = importlib.util.spec_from_file_location("offsim4rl_live_heuristic", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(3)
+    lim = np.array([2.6, 1.5, 0.23, 1.6])
+    obs = rng.uniform(-lim, lim, (20000, 4))
+    consts = [2.4, 0.8, 0.5, 0.0174532, 0.1047192, 0.2094384, 0.87266, 0.0]
+    edge = []
+    for c in consts:
+        for sgn in (1.0, -1.0):
+            v64 = np.float64(sgn * c)
+            v32 = np.float64(np.float32(v64))
+            for v in (v64, np.nextafter(v64, np.inf), np.nextafter(v64, -np.inf), v32,
+                      np.float64(np.nextafter(np.float32(v64), np.float32(np.inf))), np.float64(np.nextafter(np.float32(v64), np.float32(-np.inf)))):
+                edge.append(v)
+    edge = np.array(edge)
+    rows = rng.uniform(-lim * 0.3, lim * 0.3, (4 * edge.size, 4))
+    for col in range(4):
+        rows[col * edge.size:(col + 1) * edge.size, col] = edge
+    obs = np.concatenate([obs, rows]).astype(dtype)
+    want = mod.CartpoleBoxEncoder().encode(obs)
+    got = CartpoleBoxEncoder().encode(obs)
+    assert np.array_equal(got, want)
+    assert (want == -1).sum() > 0 and np.unique(want).size > 100
