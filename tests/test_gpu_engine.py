@@ -1,4 +1,6 @@
 """GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden vectors."""
+import os
+
 import numpy as np
 import pytest
 
@@ -886,7 +888,7 @@ def _fuzz_config(k):
     return c
 
 
-@pytest.mark.parametrize("k", range(240))
+@pytest.mark.parametrize("k", range(int(os.environ.get("OLS_FUZZ_N", "240"))))     # OLS_FUZZ_N=3000 for a longer hunt
 def test_randomized_small_configurations_match_c_oracle(ob, k):
     """Differential fuzzing of the fused drivers against oracle/ols_oracle.c over small random shapes: 1-20011 rows, 1-64 states,
     2-4 actions, every lane-group width, hot-record kind, state layout, slicing, ring and budget setting the API accepts."""
